@@ -1,0 +1,108 @@
+/*
+ * splatco_b200.h — C ABI of libsplatco_b200.so, the B200 (sm_100a) implementation of SplatCo's
+ * differentiable render hot path.
+ *
+ * What this boundary replaces.  The reference reaches its native rasterizer through the pybind
+ * module `diff_gaussian_rasterization._C` (package shipped in the reference's submodules.zip;
+ * call sites pinned at /root/reference gaussian_renderer/__init__.py:15, :145-171 (forward),
+ * :208-242 (visible_filter)).  Upstream entry points [SURVEY Appendix A.1]:
+ *     _C.rasterize_gaussians            -> splatco_preprocess_fwd + splatco_binning + splatco_blend_fwd
+ *     _C.rasterize_gaussians_backward   -> splatco_blend_bwd + splatco_preprocess_bwd
+ *     _C.rasterize_aussians_filter      -> splatco_visible_filter            (Scaffold-GS fork)
+ * and the PyTorch decode in generate_neural_gaussians (gaussian_renderer/__init__.py:18-116,
+ * scene/gaussian_model.py:149-169, scene/grids.py:146-201) -> splatco_decode_*.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; splatco_last_error() gives the message
+ *    (thread-local).  Nothing throws, nothing allocates device memory: the caller owns every buffer
+ *    (inputs, outputs and the three opaque workspaces, sized by splatco_*_bytes) and the library
+ *    only borrows pointers for the duration of the call on `stream` (a cudaStream_t).
+ *  - all array pointers are DEVICE pointers unless the name ends in _host.
+ *  - matrices are the reference's transposed (row-vector) 4x4 tensors, read flat:
+ *    out.x = m[0]x + m[4]y + m[8]z + m[12]  (scene/cameras.py:54-56).
+ *  - no thread-affine state: forward runs on the Python main thread, backward on the autograd thread.
+ */
+#ifndef SPLATCO_B200_H
+#define SPLATCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPLATCO_ABI_VERSION 1
+#define SPLATCO_TILE 16              /* BLOCK_X = BLOCK_Y = 16 */
+
+int splatco_abi_version(void);
+const char *splatco_last_error(void);
+
+/* ---- workspace sizing (bytes; every internal chunk is 256-byte aligned) ---------------------- */
+size_t splatco_geom_bytes(int P);                 /* per-Gaussian projected state               */
+size_t splatco_binning_bytes(int64_t R);          /* key/value ping-pong buffers + histograms   */
+size_t splatco_image_bytes(int H, int W);         /* tile ranges, final_T, n_contrib            */
+
+/* Byte offsets of the chunks inside each workspace, for tests and debuggers.
+ * geom   : [0] rec float4[3P] (x,y,conA,conB | conC,opacity,r,g | b,depth,radius,0)  [1] depths f32[P]
+ *          [2] tiles_touched u32[P]  [3] block_sums u32[nb]  [4] block_offsets u32[nb]  [5] total u32
+ * binning: [0] keys0 u64[R] [1] keys1 u64[R] [2] vals0 u32[R] [3] vals1 u32[R] [4] hist u32[256*nsb]
+ *          [5] bin_totals u32[256]
+ * image  : [0] ranges int2[T] [1] final_T f32[HW] [2] n_contrib i32[HW]
+ * Returns the number of chunks written (<= max_chunks). */
+int splatco_geom_layout(int P, size_t *offsets, int max_chunks);
+int splatco_binning_layout(int64_t R, size_t *offsets, int max_chunks);
+int splatco_image_layout(int H, int W, size_t *offsets, int max_chunks);
+/* 0/1: which of the ping-pong buffers (keys0/vals0 or keys1/vals1) holds the sorted list. */
+int splatco_sorted_buffer_index(int H, int W);
+
+/* ---- anchor prefilter: replaces GaussianRasterizer.visible_filter ----------------------------
+ * (gaussian_renderer/__init__.py:239-242).  scales is read with a row stride (in floats) because
+ * the reference passes the strided view get_scaling[:, :3] of an [N,6] tensor. */
+int splatco_visible_filter(int N, const float *means3D, const float *scales, int scale_stride,
+                           const float *rots, float scale_mod, const float *view, const float *proj,
+                           float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
+                           void *stream);
+
+/* ---- forward, stage 1: preprocess + tile counts + scan --------------------------------------
+ * Fills geom, radii_out[P]; leaves the instance count R in geom (device) and, if
+ * num_rendered_host != NULL (pinned host memory), copies it there asynchronously on `stream`. */
+int splatco_preprocess_fwd(int P, const float *means3D, const float *scales, int scale_stride,
+                           const float *rots, const float *opacities, const float *colors,
+                           float scale_mod, const float *view, const float *proj, float tanfovx,
+                           float tanfovy, int H, int W, int32_t *radii_out, void *geom,
+                           int32_t *num_rendered_host, void *stream);
+
+/* ---- forward, stage 2: duplicateWithKeys + 64-bit radix sort + identifyTileRanges ------------
+ * R must be the value produced by stage 1.  The stages are also exported individually so parity
+ * tests can check keys, permutation and ranges one by one. */
+int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
+                    void *binning, void *image, void *stream);
+int splatco_duplicate_with_keys(int P, int64_t R, int H, int W, const int32_t *radii,
+                                const void *geom, void *binning, void *stream);
+int splatco_sort_pairs(int64_t R, int H, int W, void *binning, void *stream);
+int splatco_identify_tile_ranges(int64_t R, int H, int W, const void *binning, void *image,
+                                 void *stream);
+
+/* ---- forward, stage 3: per-tile front-to-back alpha blend ------------------------------------ */
+int splatco_blend_fwd(int64_t R, int H, int W, const float *bg, const void *geom, const void *binning,
+                      void *image, float *out_color /* [3,H,W] */, void *stream);
+
+/* ---- backward --------------------------------------------------------------------------------
+ * blend_bwd ACCUMULATES into the four gradient arrays (caller zero-fills them):
+ * dL_dmean2D[P,3] (x,y scaled by 0.5W / 0.5H, z untouched), dL_dconic[P,3], dL_dopacity[P],
+ * dL_dcolor[P,3].  preprocess_bwd OVERWRITES dL_dmeans3D[P,3], dL_dscales[P,3], dL_drots[P,4]. */
+int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg, const void *geom,
+                      const void *binning, const void *image, const float *dL_dpix /* [3,H,W] */,
+                      float *dL_dmean2D, float *dL_dconic, float *dL_dopacity, float *dL_dcolor,
+                      void *stream);
+int splatco_preprocess_bwd(int P, const float *means3D, const float *scales, int scale_stride,
+                           const float *rots, float scale_mod, const float *view, const float *proj,
+                           float tanfovx, float tanfovy, int H, int W, const int32_t *radii,
+                           const float *dL_dmean2D, const float *dL_dconic, float *dL_dmeans3D,
+                           float *dL_dscales, float *dL_drots, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLATCO_B200_H */

@@ -1,0 +1,69 @@
+"""ctypes binding of libsplatco_b200.so (C ABI in include/splatco_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference surfaces C++ exceptions from its pybind module the same way).
+ctypes releases the GIL for the duration of each call, and the library keeps no thread-affine state,
+so forward (main thread) and backward (autograd thread) can both call in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsplatco_b200.so")
+_lib = None
+
+_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/splatco_b200.h
+SIGNATURES = {
+    "splatco_abi_version": (_i, []),
+    "splatco_last_error": (C.c_char_p, []),
+    "splatco_geom_bytes": (_sz, [_i]),
+    "splatco_binning_bytes": (_sz, [_i64]),
+    "splatco_image_bytes": (_sz, [_i, _i]),
+    "splatco_geom_layout": (_i, [_i, C.POINTER(_sz), _i]),
+    "splatco_binning_layout": (_i, [_i64, C.POINTER(_sz), _i]),
+    "splatco_image_layout": (_i, [_i, _i, C.POINTER(_sz), _i]),
+    "splatco_sorted_buffer_index": (_i, [_i, _i]),
+    "splatco_visible_filter": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp]),
+    "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "splatco_binning": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_duplicate_with_keys": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    "splatco_sort_pairs": (_i, [_i64, _i, _i, _vp, _vp]),
+    "splatco_identify_tile_ranges": (_i, [_i64, _i, _i, _vp, _vp, _vp]),
+    "splatco_blend_fwd": (_i, [_i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_blend_bwd": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_preprocess_bwd": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+}
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m splatco_b200.build` "
+                "(splatco_b200 has no CPU/PyTorch fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.splatco_abi_version() != 1:
+            raise RuntimeError("libsplatco_b200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().splatco_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,259 @@
+"""Drop-in for the `diff_gaussian_rasterization` package SplatCo imports
+(reference gaussian_renderer/__init__.py:15; call sites :145-171 and :208-242).
+
+Same public names and call signatures as the package in the reference's submodules.zip
+(Inria diff-gaussian-rasterization with the Scaffold-GS `visible_filter` addition, SURVEY.md
+Appendix A.1): `GaussianRasterizationSettings`, `GaussianRasterizer`, `rasterize_gaussians`.
+Underneath, everything runs in libsplatco_b200.so (hand-written sm_100a CUDA, C ABI in
+include/splatco_b200.h).  No CPU / PyTorch fallback exists: without the library, calls raise.
+
+Supported argument combinations are the ones the reference uses: `colors_precomp` (not `shs`) and
+`scales` + `rotations` (not `cov3D_precomp`).  The other upstream combinations raise
+NotImplementedError instead of silently doing something else.
+"""
+from __future__ import annotations
+
+import threading
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .._lib import check, ptr
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    # field order = the keyword order used at gaussian_renderer/__init__.py:145-158
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+_tls = threading.local()
+
+
+def _pinned_counter(device: torch.device) -> torch.Tensor:
+    """One pinned int32 per (thread, device) for the num_rendered read-back."""
+    cache = getattr(_tls, "counters", None)
+    if cache is None:
+        cache = _tls.counters = {}
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = cache.get(key)
+    if buf is None:
+        buf = cache[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return buf
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _rows_f32(t: torch.Tensor, cols: int):
+    """Return (tensor, row_stride_in_floats) for a [N,cols] fp32 tensor whose rows may be strided
+    (the reference passes get_scaling[:, :3], a view of an [N,6] tensor)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 2 and t.shape[1] == cols and t.stride(1) == 1 and t.stride(0) >= cols and t.shape[0] > 0:
+        return t, int(t.stride(0))
+    return t.contiguous(), cols
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("splatco_b200 rasterizer needs CUDA tensors (no CPU fallback)")
+
+
+def _debug_sync(settings, what):
+    if settings.debug:
+        torch.cuda.synchronize()
+
+
+class RasterState:
+    """What forward leaves behind for backward and for the stage-wise parity tests."""
+    __slots__ = ("P", "R", "H", "W", "geom", "binning", "image", "radii")
+
+
+def rasterize_forward_state(means3D, colors, opacities, scales, rotations, settings) -> tuple:
+    """Forward pass; returns (color [3,H,W], radii int32 [P], RasterState)."""
+    L = _lib.lib()
+    _require_cuda(means3D, colors, opacities, scales, rotations, settings.bg, settings.viewmatrix,
+                  settings.projmatrix)
+    dev = means3D.device
+    H, W = int(settings.image_height), int(settings.image_width)
+    P = int(means3D.shape[0])
+    bg = _f32c(settings.bg)
+    st = RasterState()
+    st.P, st.H, st.W = P, H, W
+    if P == 0:
+        st.R = 0
+        st.geom = st.binning = None
+        st.image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
+        st.radii = torch.empty(0, dtype=torch.int32, device=dev)
+        color = bg.reshape(3, 1, 1).expand(3, H, W).contiguous()
+        return color, st.radii, st
+    means3D = _f32c(means3D)
+    colors = _f32c(colors)
+    opacities = _f32c(opacities)
+    rotations = _f32c(rotations)
+    scales, sstride = _rows_f32(scales, 3)
+    view = _f32c(settings.viewmatrix)
+    proj = _f32c(settings.projmatrix)
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        radii = torch.empty(P, dtype=torch.int32, device=dev)
+        geom = torch.empty(L.splatco_geom_bytes(P), dtype=torch.uint8, device=dev)
+        counter = _pinned_counter(dev)
+        check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
+                                       ptr(colors), float(settings.scale_modifier), ptr(view), ptr(proj),
+                                       float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(radii),
+                                       ptr(geom), counter.data_ptr(), stream), "splatco_preprocess_fwd")
+        # the one device->host sync of the forward (the reference has the same one)
+        torch.cuda.current_stream(dev).synchronize()
+        R = int(counter.item())
+        _debug_sync(settings, "preprocess")
+        binning = torch.empty(max(L.splatco_binning_bytes(R), 256), dtype=torch.uint8, device=dev)
+        image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
+        check(L.splatco_binning(P, R, H, W, ptr(radii), ptr(geom), ptr(binning), ptr(image), stream),
+              "splatco_binning")
+        _debug_sync(settings, "binning")
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(color), stream),
+              "splatco_blend_fwd")
+        _debug_sync(settings, "blend_fwd")
+    st.R, st.geom, st.binning, st.image, st.radii = R, geom, binning, image, radii
+    return color, radii, st
+
+
+def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotations, settings):
+    """Backward pass; returns dict of gradients (all fp32, same row count as the inputs)."""
+    L = _lib.lib()
+    dev = means3D.device
+    P, R, H, W = st.P, st.R, st.H, st.W
+    flat = torch.zeros(10 * P, dtype=torch.float32, device=dev)
+    g_mean2D = flat[: 3 * P].view(P, 3)
+    g_conic = flat[3 * P: 6 * P].view(P, 3)
+    g_opac = flat[6 * P: 7 * P].view(P, 1)
+    g_color = flat[7 * P:].view(P, 3)
+    g_means3D = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    g_scales = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    g_rots = torch.empty((P, 4), dtype=torch.float32, device=dev)
+    if P == 0:
+        return dict(means3D=g_means3D, means2D=g_mean2D, colors=g_color, opacities=g_opac,
+                    scales=g_scales, rotations=g_rots, conic=g_conic)
+    means3D = _f32c(means3D)
+    rotations = _f32c(rotations)
+    scales, sstride = _rows_f32(scales, 3)
+    grad_color = _f32c(grad_color)
+    bg = _f32c(settings.bg)
+    view = _f32c(settings.viewmatrix)
+    proj = _f32c(settings.projmatrix)
+    stream = _stream_ptr(dev)
+    with torch.cuda.device(dev):
+        check(L.splatco_blend_bwd(P, R, H, W, ptr(bg), ptr(st.geom), ptr(st.binning), ptr(st.image),
+                                  ptr(grad_color), ptr(g_mean2D), ptr(g_conic), ptr(g_opac), ptr(g_color),
+                                  stream), "splatco_blend_bwd")
+        _debug_sync(settings, "blend_bwd")
+        check(L.splatco_preprocess_bwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations),
+                                       float(settings.scale_modifier), ptr(view), ptr(proj),
+                                       float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(st.radii),
+                                       ptr(g_mean2D), ptr(g_conic), ptr(g_means3D), ptr(g_scales), ptr(g_rots),
+                                       stream), "splatco_preprocess_bwd")
+        _debug_sync(settings, "preprocess_bwd")
+    return dict(means3D=g_means3D, means2D=g_mean2D, colors=g_color, opacities=g_opac, scales=g_scales,
+                rotations=g_rots, conic=g_conic)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        if sh is not None and sh.numel() > 0:
+            raise NotImplementedError("splatco_b200: SH colours are not on SplatCo's path (it passes colors_precomp)")
+        if cov3Ds_precomp is not None and cov3Ds_precomp.numel() > 0:
+            raise NotImplementedError("splatco_b200: cov3D_precomp is not on SplatCo's path (it passes scales+rotations)")
+        color, radii, st = rasterize_forward_state(means3D, colors_precomp, opacities, scales, rotations,
+                                                   raster_settings)
+        ctx.raster_settings = raster_settings
+        ctx.state = st
+        ctx.save_for_backward(means3D, scales, rotations)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        means3D, scales, rotations = ctx.saved_tensors
+        g = rasterize_backward_state(ctx.state, grad_out_color, means3D, scales, rotations, ctx.raster_settings)
+        # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings)
+        return (g["means3D"], g["means2D"], None, g["colors"], g["opacities"], g["scales"], g["rotations"],
+                None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        raise NotImplementedError("splatco_b200: markVisible is not on SplatCo's path (use visible_filter)")
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        raster_settings = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, raster_settings)
+
+    def visible_filter(self, means3D, scales=None, rotations=None, cov3D_precomp=None):
+        """Per-anchor radii (int32 [N]); radii > 0 <=> the anchor's Gaussian touches the view
+        (gaussian_renderer/__init__.py:239-244)."""
+        rs = self.raster_settings
+        if cov3D_precomp is not None and (not torch.is_tensor(cov3D_precomp) or cov3D_precomp.numel() > 0):
+            raise NotImplementedError("splatco_b200: visible_filter with cov3D_precomp is not supported")
+        if scales is None or rotations is None:
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        with torch.no_grad():
+            L = _lib.lib()
+            _require_cuda(means3D, scales, rotations, rs.viewmatrix, rs.projmatrix)
+            dev = means3D.device
+            N = int(means3D.shape[0])
+            radii = torch.empty(N, dtype=torch.int32, device=dev)
+            if N == 0:
+                return radii
+            means3D = _f32c(means3D.detach())
+            rotations = _f32c(rotations.detach())
+            scales, sstride = _rows_f32(scales.detach(), 3)
+            view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
+            with torch.cuda.device(dev):
+                check(L.splatco_visible_filter(N, ptr(means3D), ptr(scales), sstride, ptr(rotations),
+                                               float(rs.scale_modifier), ptr(view), ptr(proj), float(rs.tanfovx),
+                                               float(rs.tanfovy), int(rs.image_height), int(rs.image_width),
+                                               ptr(radii), _stream_ptr(dev)), "splatco_visible_filter")
+            _debug_sync(rs, "visible_filter")
+            return radii

@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/splatco_b200.h declares; sizing/layout helpers (no compute calls without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from splatco_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "splatco_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(splatco_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/splatco_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+
+
+def test_abi_version_and_error_string():
+    L = _lib.lib()
+    assert L.splatco_abi_version() == 1
+    assert isinstance(L.splatco_last_error(), bytes)
+
+
+def test_workspace_sizing_monotone_and_aligned():
+    L = _lib.lib()
+    prev = 0
+    for P in (0, 1, 255, 256, 257, 100000):
+        b = L.splatco_geom_bytes(P)
+        assert b % 256 == 0 and b >= prev
+        prev = b
+    assert L.splatco_geom_bytes(1000) >= 1000 * (48 + 4 + 4)
+    assert L.splatco_binning_bytes(1000) >= 1000 * 24
+    assert L.splatco_image_bytes(545, 980) >= 545 * 980 * 8 + 62 * 35 * 8
+    offs = (C.c_size_t * 8)()
+    assert L.splatco_geom_layout(1000, offs, 8) == 6 and list(offs)[:6] == sorted(list(offs)[:6])
+    assert L.splatco_binning_layout(5000, offs, 8) == 6
+    assert L.splatco_image_layout(545, 980, offs, 8) == 3
+
+
+def test_sort_pass_parity_matches_key_width():
+    L = _lib.lib()
+    # 256x256 -> 256 tiles -> 8 tile bits -> 40 key bits -> 5 passes -> sorted data in buffer 1
+    assert L.splatco_sorted_buffer_index(256, 256) == 1
+    # 980x545 -> 62*35=2170 tiles -> 12 bits -> 44 bits -> 6 passes -> buffer 0
+    assert L.splatco_sorted_buffer_index(545, 980) == 0
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    rc = L.splatco_visible_filter(-1, None, None, 3, None, 1.0, None, None, 1.0, 1.0, 16, 16, None, None)
+    assert rc < 0 and b"bad sizes" in L.splatco_last_error()
+    rc = L.splatco_visible_filter(4, None, None, 3, None, 1.0, None, None, 1.0, 1.0, 16, 16, None, None)
+    assert rc < 0 and b"null pointer" in L.splatco_last_error()
+
+
+def test_rasterizer_refuses_cpu_tensors():
+    from splatco_b200.diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    s = GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 1,
+                                      torch.zeros(3), False, False)
+    r = GaussianRasterizer(s)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        r(means3D=torch.zeros(4, 3), means2D=torch.zeros(4, 3), shs=None, colors_precomp=torch.zeros(4, 3),
+          opacities=torch.zeros(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4), cov3D_precomp=None)
+    with pytest.raises(Exception, match="excatly one"):
+        r(means3D=torch.zeros(4, 3), means2D=torch.zeros(4, 3), shs=None, colors_precomp=None,
+          opacities=torch.zeros(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4), cov3D_precomp=None)
