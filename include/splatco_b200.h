@@ -37,6 +37,8 @@ extern "C" {
 
 int splatco_abi_version(void);
 const char *splatco_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (for bench.py's gpu_launches). */
+uint64_t splatco_launch_count(void);
 
 /* ---- workspace sizing (bytes; every internal chunk is 256-byte aligned) ---------------------- */
 size_t splatco_geom_bytes(int P);                 /* per-Gaussian projected state               */

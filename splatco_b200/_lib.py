@@ -20,6 +20,7 @@ _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 SIGNATURES = {
     "splatco_abi_version": (_i, []),
     "splatco_last_error": (C.c_char_p, []),
+    "splatco_launch_count": (C.c_uint64, []),
     "splatco_geom_bytes": (_sz, [_i]),
     "splatco_binning_bytes": (_sz, [_i64]),
     "splatco_image_bytes": (_sz, [_i, _i]),

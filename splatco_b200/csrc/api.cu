@@ -7,12 +7,18 @@ namespace splatco {
 
 static thread_local char g_err[512] = "";
 
+unsigned long long launch_count();
+
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 size_t geom_offsets(int P, size_t off[7]) {
     const size_t p = (size_t)(P > 0 ? P : 0);
@@ -98,6 +104,7 @@ using namespace splatco;
 
 extern "C" int splatco_abi_version(void) { return SPLATCO_ABI_VERSION; }
 extern "C" const char *splatco_last_error(void) { return g_err; }
+extern "C" uint64_t splatco_launch_count(void) { return (uint64_t)launch_count(); }
 
 extern "C" size_t splatco_geom_bytes(int P) { size_t off[7]; return geom_offsets(P, off); }
 extern "C" size_t splatco_binning_bytes(int64_t R) { size_t off[7]; return bin_offsets(R, off); }

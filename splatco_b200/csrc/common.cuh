@@ -21,6 +21,7 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 void set_error(const char *fmt, ...);
+void count_launch(int n = 1);          // process-wide count of kernels this library launched
 
 #define SPLATCO_CHECK_CUDA(expr)                                                           \
     do {                                                                                   \
@@ -32,7 +33,8 @@ void set_error(const char *fmt, ...);
         }                                                                                  \
     } while (0)
 
-#define SPLATCO_CHECK_LAUNCH() SPLATCO_CHECK_CUDA(cudaGetLastError())
+#define SPLATCO_CHECK_LAUNCH()                                                              \
+    do { splatco::count_launch(); SPLATCO_CHECK_CUDA(cudaGetLastError()); } while (0)
 
 #define SPLATCO_REQUIRE(cond, ...)                                                         \
     do {                                                                                   \

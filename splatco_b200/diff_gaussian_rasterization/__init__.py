@@ -20,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
+from ..profiling import stage
 from .._lib import check, ptr
 
 
@@ -120,7 +121,8 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
         radii = torch.empty(P, dtype=torch.int32, device=dev)
         geom = torch.empty(L.splatco_geom_bytes(P), dtype=torch.uint8, device=dev)
         counter = _pinned_counter(dev)
-        check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
+        with stage("preprocess_fwd"):
+          check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
                                        ptr(colors), float(settings.scale_modifier), ptr(view), ptr(proj),
                                        float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(radii),
                                        ptr(geom), counter.data_ptr(), stream), "splatco_preprocess_fwd")
@@ -130,12 +132,14 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
         _debug_sync(settings, "preprocess")
         binning = torch.empty(max(L.splatco_binning_bytes(R), 256), dtype=torch.uint8, device=dev)
         image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
-        check(L.splatco_binning(P, R, H, W, ptr(radii), ptr(geom), ptr(binning), ptr(image), stream),
-              "splatco_binning")
+        with stage("binning"):
+            check(L.splatco_binning(P, R, H, W, ptr(radii), ptr(geom), ptr(binning), ptr(image), stream),
+                  "splatco_binning")
         _debug_sync(settings, "binning")
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-        check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(color), stream),
-              "splatco_blend_fwd")
+        with stage("blend_fwd"):
+            check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(color), stream),
+                  "splatco_blend_fwd")
         _debug_sync(settings, "blend_fwd")
     st.R, st.geom, st.binning, st.image, st.radii = R, geom, binning, image, radii
     return color, radii, st
@@ -166,11 +170,13 @@ def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotat
     proj = _f32c(settings.projmatrix)
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
-        check(L.splatco_blend_bwd(P, R, H, W, ptr(bg), ptr(st.geom), ptr(st.binning), ptr(st.image),
+        with stage("blend_bwd"):
+          check(L.splatco_blend_bwd(P, R, H, W, ptr(bg), ptr(st.geom), ptr(st.binning), ptr(st.image),
                                   ptr(grad_color), ptr(g_mean2D), ptr(g_conic), ptr(g_opac), ptr(g_color),
                                   stream), "splatco_blend_bwd")
         _debug_sync(settings, "blend_bwd")
-        check(L.splatco_preprocess_bwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations),
+        with stage("preprocess_bwd"):
+          check(L.splatco_preprocess_bwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations),
                                        float(settings.scale_modifier), ptr(view), ptr(proj),
                                        float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(st.radii),
                                        ptr(g_mean2D), ptr(g_conic), ptr(g_means3D), ptr(g_scales), ptr(g_rots),
