@@ -104,6 +104,64 @@ int splatco_preprocess_bwd(int P, const float *means3D, const float *scales, int
                            const float *dL_dmean2D, const float *dL_dconic, float *dL_dmeans3D,
                            float *dL_dscales, float *dL_drots, void *stream);
 
+/* ---- anchor decode: replaces generate_neural_gaussians -----------------------------------------
+ * (gaussian_renderer/__init__.py:18-116; FeaturePlanes.forward scene/gaussian_model.py:149-169;
+ * PlaneGrid scene/grids.py:146-201; heads scene/gaussian_model.py:316-337).
+ * The kernels are specialised for feat_dim = 32 and n_offsets = 10 (the reference's defaults,
+ * arguments/__init__.py:50-51); other values are rejected with an error.
+ * All pointers are device pointers; arrays indexed [3] run over activate levels / heads
+ * (heads: 0 opacity, 1 cov, 2 colour).  Entries of levels > `level` may be NULL. */
+typedef struct splatco_decode_desc {
+    int32_t N, V, K, rc, level, app_dim;   /* anchors, visible anchors, n_offsets, channels per plane
+                                              (num_channels // 3), activate_level 0..2, appearance dim */
+    int32_t E[3];                          /* plane edge of k0s[0] (TA level), k0s[1], k0s[2]           */
+    int32_t use_dist[3];                   /* add_opacity_dist, add_cov_dist, add_color_dist            */
+    int32_t update_running;                /* 1: update BatchNorm running stats in place (train mode)   */
+    float xyz_min[3], xyz_max[3], cam[3];
+    float bn_eps, bn_momentum;
+    const float *anchor_feat, *anchor, *offset, *scaling;   /* [N,32] [N,3] [N,K,3] [N,6] (activated)   */
+    const int32_t *vis;                    /* [V] ascending indices of the visible anchors              */
+    const float *plane[9];                 /* [level*3 + {xy,xz,yz}] each [rc,E,E]                       */
+    const float *att[3];                   /* TriPlaneAttention output planes of level 0, [rc,E0,E0]     */
+    const float *bn_w[3], *bn_b[3], *lin_w[3], *lin_b[3];       /* FeaturePlanes.models[l]      */
+    const float *cbn_w[3], *cbn_b[3], *clin_w[3], *clin_b[3];   /* FeaturePlanes.CTX_models[l]  */
+    float *bn_rm[3], *bn_rv[3], *cbn_rm[3], *cbn_rv[3];         /* running_mean / running_var   */
+    int64_t *bn_nbt[3], *cbn_nbt[3];                            /* num_batches_tracked          */
+    const float *w1[3], *b1[3], *w2[3], *b2[3];                 /* head Linear layers (torch [out,in]) */
+    const float *app_vec;                  /* [app_dim] embedding row of this camera, or NULL           */
+    const float *noise;                    /* [V, DP - 6*rc] additive plane-feature noise U(-.5,.5)*Q for
+                                              levels >= 1 (scene/grids.py:159-164), or NULL (Q = 0)     */
+} splatco_decode_desc;
+
+/* Gradient destinations (same shapes as the inputs).  anchor_feat/anchor/offset/scaling must be
+ * zero-filled [N,*] arrays (visible rows are overwritten); plane/att must be zero-filled (atomics
+ * accumulate); the parameter gradients are overwritten.  NULL entries are skipped. */
+typedef struct splatco_decode_grads {
+    float *anchor_feat, *anchor, *offset, *scaling;
+    float *plane[9];
+    float *att[3];
+    float *bn_w[3], *bn_b[3], *lin_w[3], *lin_b[3];
+    float *cbn_w[3], *cbn_b[3], *clin_w[3], *clin_b[3];
+    float *w1[3], *b1[3], *w2[3], *b2[3];
+    float *app_vec;
+} splatco_decode_grads;
+
+size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level);
+size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level);
+/* Stage 1: gather + BN statistics + MLP heads + opacity mask.  Writes neural_opacity[V*K] (tanh
+ * output), mask[V*K] (uint8 0/1) and the survivor count M (device, inside ws; copied to
+ * M_host (pinned) asynchronously if not NULL). */
+int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
+                       int32_t *M_host, void *stream);
+/* Stage 2: stable compaction + post-processing into the M surviving Gaussians. */
+int splatco_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
+                        float *opacity, float *scaling, float *rot, void *stream);
+/* Backward of both stages.  d_neural_opacity ([V*K]) may be NULL. */
+int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M,
+                       const float *d_xyz, const float *d_color, const float *d_opacity,
+                       const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
+                       const splatco_decode_grads *g, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,4 +84,39 @@ __device__ __forceinline__ float ex2_approx(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 
+// ---- exclusive scan of the block sums (single CTA; nb = ceil(P/256) <= ~80k for 20 M Gaussians) --
+static __global__ void __launch_bounds__(1024)
+scan_block_sums_kernel(int nb, const uint32_t *__restrict__ block_sums,
+                       uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ total) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < nb ? block_sums[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += n; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= (uint32_t)d) winc += n; }
+            s_warp[lane] = winc - w;   // exclusive warp offsets
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + s_warp[warp] + inc - v;
+        if (i < nb) block_offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = s_carry;
+}
+
+
 }  // namespace splatco

@@ -1,0 +1,992 @@
+// Anchor decode (generate_neural_gaussians) forward + backward on sm_100a.
+// Reference being replaced (file:line in /root/reference):
+//   gaussian_renderer/__init__.py:18-116   gather visible rows, geo features, MLP heads, mask, compaction
+//   scene/gaussian_model.py:149-169        FeaturePlanes.forward  (sum over levels of BN+Linear branches)
+//   scene/grids.py:146-201                 tri-plane bilinear gather (grid_sample, align_corners=True, zeros)
+//   scene/gaussian_model.py:307-337        opacity / cov / colour heads
+//
+// v1 structure (fp32 throughout, the reference's numerics): the decode is expressed as
+//   gather(+BN batch statistics) -> fold BN into the Linear weights -> a chain of small row-major GEMMs
+//   (hand-written SIMT SGEMM below) with fused epilogues -> mask/scan/compaction,
+// and the backward as the transposed chain plus split-K weight-gradient GEMMs.  BatchNorm in train mode
+// needs grid-wide statistics before the first Linear, and its backward needs two grid-wide sums; both
+// reduce to the column sums S0 and the matrices S1 = dY^T X accumulated by the same GEMM kernel, so no
+// separate BN kernels exist (derivation in DESIGN.md §decode).
+#include "common.cuh"
+
+namespace splatco {
+
+constexpr int KO = 10;                 // n_offsets the kernels are specialised for
+constexpr int FD = 32;                 // feat_dim
+constexpr int GD = FD + 3 + 3 * KO + 6;  // 71: [feat | anchor | offsets | scaling]
+constexpr int XI = 100;                // x100 = [feat 32 | dir 3 | dist 1 | geo 64]
+constexpr int HD = 96;                 // 3 heads x 32 hidden
+constexpr int ZD = 112;                // 10 + 70 + 30 outputs, padded to 112
+constexpr int DEC_MAX_DP = 96;
+
+inline int ru4(int x) { return (x + 3) & ~3; }
+
+struct DecDims {
+    int V, rc, level, DP, LDX;
+};
+inline DecDims dec_dims(int V, int rc, int level) {
+    DecDims d;
+    d.V = V; d.rc = rc; d.level = level;
+    d.DP = rc * (level == 0 ? 6 : (level == 1 ? 9 : 12));
+    d.LDX = ru4(d.DP + GD);
+    return d;
+}
+
+// ---- forward workspace -------------------------------------------------------------------------------
+enum FwdChunk { F_X, F_STATS, F_MU, F_RSTD, F_WPT, F_WCT, F_BGEO, F_W1T, F_B1E, F_W2T, F_B2, F_WPG, F_WCG,
+                F_XIN, F_H, F_Z, F_MASKBITS, F_OFFS, F_BSUM, F_BOFF, F_TOTAL, F_NCHUNK };
+
+static size_t dec_fwd_offsets(const DecDims &d, size_t off[F_NCHUNK + 1]) {
+    const size_t V = (size_t)(d.V > 0 ? d.V : 0);
+    const size_t nb = (V + 255) / 256;
+    size_t o = 0;
+    auto put = [&](int c, size_t bytes) { off[c] = o; o += align_up(bytes); };
+    put(F_X, V * d.LDX * 4);
+    put(F_STATS, 2 * (size_t)d.LDX * 8);
+    put(F_MU, d.LDX * 4); put(F_RSTD, d.LDX * 4);
+    put(F_WPT, DEC_MAX_DP * 32 * 4); put(F_WCT, GD * 32 * 4); put(F_BGEO, 64 * 4);
+    put(F_W1T, XI * HD * 4); put(F_B1E, HD * 4);
+    put(F_W2T, HD * ZD * 4); put(F_B2, ZD * 4);
+    put(F_WPG, 32 * DEC_MAX_DP * 4); put(F_WCG, 32 * GD * 4);
+    put(F_XIN, V * XI * 4); put(F_H, V * HD * 4); put(F_Z, V * ZD * 4);
+    put(F_MASKBITS, V * 4); put(F_OFFS, V * 4); put(F_BSUM, nb * 4); put(F_BOFF, nb * 4); put(F_TOTAL, 4);
+    off[F_NCHUNK] = o;
+    return o;
+}
+
+// ---- backward workspace ------------------------------------------------------------------------------
+enum BwdChunk { B_DZ, B_DH, B_DX, B_DXH, B_DGA, B_GW2T, B_GB2, B_GW1T, B_GB1, B_S1, B_S0, B_M1, B_M2, B_NCHUNK };
+
+static size_t dec_bwd_offsets(const DecDims &d, size_t off[B_NCHUNK + 1]) {
+    const size_t V = (size_t)(d.V > 0 ? d.V : 0);
+    size_t o = 0;
+    auto put = [&](int c, size_t bytes) { off[c] = o; o += align_up(bytes); };
+    put(B_DZ, V * ZD * 4); put(B_DH, V * HD * 4); put(B_DX, V * XI * 4); put(B_DXH, V * d.LDX * 4);
+    put(B_DGA, V * 40 * 4);
+    put(B_GW2T, HD * ZD * 4); put(B_GB2, ZD * 4); put(B_GW1T, XI * HD * 4); put(B_GB1, HD * 4);
+    put(B_S1, 32 * (size_t)d.LDX * 4); put(B_S0, 64 * 4); put(B_M1, d.LDX * 4); put(B_M2, d.LDX * 4);
+    off[B_NCHUNK] = o;
+    return o;
+}
+
+// =======================================================================================================
+// Generic SIMT SGEMM: C[M,N] (+)= epi( sum_k A(m,k) B(k,n) ),  64x32 tile, 256 threads, 2x4 per thread.
+//   A(m,k) = TA ? A[k*lda+m] : A[m*lda+k]      B(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
+//   gridDim.z > 1 => split-K over chunks of `kchunk`, results atomically added (C pre-zeroed, no epilogue).
+// =======================================================================================================
+constexpr int GBM = 64, GBN = 32, GBK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float *__restrict__ A, int lda, const float *__restrict__ B, int ldb,
+             float *__restrict__ C, int ldc, const float *__restrict__ bias, int relu,
+             const float *__restrict__ gate, int ldg, int kchunk) {
+    __shared__ float As[GBK][GBM + 4];
+    __shared__ float Bs[GBK][GBN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * GBN;
+    const int kbeg = kchunk > 0 ? blockIdx.z * kchunk : 0;
+    const int kend = kchunk > 0 ? min(K, kbeg + kchunk) : K;
+    const int ty = tid >> 3, tx = tid & 7;       // rows ty*2..+1, cols tx*4..+3
+    float acc[2][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+        // A tile: 64 x 16
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = tid + i * 256;
+            int m, k;
+            if (TA) { m = e & 63; k = e >> 6; } else { k = e & 15; m = e >> 4; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+        // B tile: 16 x 32
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int e = tid + i * 256;
+            int n, k;
+            if (TB) { k = e & 15; n = e >> 4; } else { n = e & 31; k = e >> 5; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GBK; ++k) {
+            const float a0 = As[k][ty * 2], a1 = As[k][ty * 2 + 1];
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+            acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+            acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+            acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int gm = m0 + ty * 2 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j];
+            if (kchunk > 0) { atomicAdd(&C[(size_t)gm * ldc + gn], v); continue; }
+            if (bias) v += bias[gn];
+            if (relu) v = fmaxf(v, 0.f);
+            if (gate) v = gate[(size_t)gm * ldg + gn] > 0.f ? v : 0.f;
+            C[(size_t)gm * ldc + gn] = v;
+        }
+    }
+}
+
+template <bool TA, bool TB>
+static int sgemm(cudaStream_t st, int M, int N, int K, const float *A, int lda, const float *B, int ldb, float *C,
+                 int ldc, const float *bias = nullptr, int relu = 0, const float *gate = nullptr, int ldg = 0,
+                 int kchunk = 0) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    dim3 grid(ceil_div(M, GBM), ceil_div(N, GBN), kchunk > 0 ? ceil_div(K, kchunk) : 1);
+    sgemm_kernel<TA, TB><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, relu, gate, ldg, kchunk);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+// column sums: out[n] += sum_m A[m*lda + n]   (out pre-zeroed)
+__global__ void __launch_bounds__(128)
+colsum_kernel(int M, int N, const float *__restrict__ A, int lda, float *__restrict__ out, int rows_per_cta) {
+    const int n = blockIdx.y * 128 + threadIdx.x;
+    if (n >= N) return;
+    const int mbeg = blockIdx.x * rows_per_cta, mend = min(M, mbeg + rows_per_cta);
+    float s = 0.f;
+    for (int m = mbeg; m < mend; ++m) s += A[(size_t)m * lda + n];
+    atomicAdd(&out[n], s);
+}
+
+// =======================================================================================================
+// Gather: one warp per visible anchor; lanes run over output channels so that X rows are written
+// coalesced; BN batch statistics (sum, sum of squares) accumulated per lane, reduced per CTA, then fp64 atomics.
+// =======================================================================================================
+struct DecPtrs {
+    const float *anchor_feat, *anchor, *offset, *scaling;
+    const int32_t *vis;
+    const float *plane[3][3];
+    const float *att[3];
+    int E[3];
+    float mn[3], mx[3], cam[3];
+    const float *noise;
+};
+
+struct Bilin { int i00, i01, i10, i11; float w00, w01, w10, w11; };
+
+// u indexes plane rows (size E), v indexes columns (size E): what grid_sample(align_corners=True) does
+__device__ __forceinline__ Bilin bilin_setup(float u, float v, int E) {
+    const float fu = (u + 1.f) * 0.5f * (float)(E - 1);
+    const float fv = (v + 1.f) * 0.5f * (float)(E - 1);
+    const float u0f = floorf(fu), v0f = floorf(fv);
+    const int u0 = (int)u0f, v0 = (int)v0f, u1 = u0 + 1, v1 = v0 + 1;
+    const float wu1 = fu - u0f, wv1 = fv - v0f, wu0 = 1.f - wu1, wv0 = 1.f - wv1;
+    const bool iu0 = u0 >= 0 && u0 < E, iu1 = u1 >= 0 && u1 < E, iv0 = v0 >= 0 && v0 < E, iv1 = v1 >= 0 && v1 < E;
+    Bilin b;
+    b.i00 = (iu0 && iv0) ? u0 * E + v0 : -1; b.w00 = wu0 * wv0;
+    b.i01 = (iu0 && iv1) ? u0 * E + v1 : -1; b.w01 = wu0 * wv1;
+    b.i10 = (iu1 && iv0) ? u1 * E + v0 : -1; b.w10 = wu1 * wv0;
+    b.i11 = (iu1 && iv1) ? u1 * E + v1 : -1; b.w11 = wu1 * wv1;
+    return b;
+}
+__device__ __forceinline__ float bilin_fetch(const float *__restrict__ p, const Bilin &b) {
+    float r = 0.f;
+    if (b.i00 >= 0) r = fmaf(__ldg(p + b.i00), b.w00, r);
+    if (b.i01 >= 0) r = fmaf(__ldg(p + b.i01), b.w01, r);
+    if (b.i10 >= 0) r = fmaf(__ldg(p + b.i10), b.w10, r);
+    if (b.i11 >= 0) r = fmaf(__ldg(p + b.i11), b.w11, r);
+    return r;
+}
+__device__ __forceinline__ void bilin_scatter(float *__restrict__ p, const Bilin &b, float g) {
+    if (b.i00 >= 0) atomicAdd(p + b.i00, g * b.w00);
+    if (b.i01 >= 0) atomicAdd(p + b.i01, g * b.w01);
+    if (b.i10 >= 0) atomicAdd(p + b.i10, g * b.w10);
+    if (b.i11 >= 0) atomicAdd(p + b.i11, g * b.w11);
+}
+
+// channel c of the plane block -> (level, plane 0..2, attended?, channel within plane)
+__device__ __forceinline__ void plane_channel(int c, int rc, int &lvl, int &pl, int &att, int &ch) {
+    if (c < 6 * rc) { lvl = 0; const int g = c / rc; pl = g >> 1; att = g & 1; ch = c - g * rc; }
+    else if (c < 9 * rc) { lvl = 1; const int cc = c - 6 * rc; pl = cc / rc; att = 0; ch = cc - pl * rc; }
+    else { lvl = 2; const int cc = c - 9 * rc; pl = cc / rc; att = 0; ch = cc - pl * rc; }
+}
+
+__device__ __forceinline__ void norm_coords(const DecPtrs &p, float ax, float ay, float az, float ind[3]) {
+    ind[0] = (ax - p.mn[0]) / (p.mx[0] - p.mn[0]) * 2.f - 1.f;
+    ind[1] = (ay - p.mn[1]) / (p.mx[1] - p.mn[1]) * 2.f - 1.f;
+    ind[2] = (az - p.mn[2]) / (p.mx[2] - p.mn[2]) * 2.f - 1.f;
+}
+// plane 0 = xy (rows X, cols Y), 1 = xz (rows X, cols Z), 2 = yz (rows Y, cols Z)   [grids.py:148-150]
+__device__ __forceinline__ void plane_axes(int pl, const float ind[3], float &u, float &v) {
+    u = pl == 2 ? ind[1] : ind[0];
+    v = pl == 0 ? ind[1] : ind[2];
+}
+
+constexpr int GATHER_WARPS = 8;
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__ X, float *__restrict__ XIN,
+                  double *__restrict__ stats) {
+    extern __shared__ float s_red[];     // [GATHER_WARPS][2][LDX]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps_total = gridDim.x * GATHER_WARPS;
+    constexpr int MAXC = 6;              // ceil((96+71)/32)
+    float sum[MAXC], sq[MAXC];
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) sum[j] = sq[j] = 0.f;
+    const int ncols = DP + GD;
+    for (int v = blockIdx.x * GATHER_WARPS + warp; v < V; v += nwarps_total) {
+        const int i = p.vis[v];
+        const float ax = __ldg(p.anchor + 3 * (size_t)i), ay = __ldg(p.anchor + 3 * (size_t)i + 1), az = __ldg(p.anchor + 3 * (size_t)i + 2);
+        float ind[3];
+        norm_coords(p, ax, ay, az, ind);
+        float *xrow = X + (size_t)v * LDX;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            if (c >= ncols) break;
+            float val;
+            if (c < DP) {
+                int lvl, pl, att, ch;
+                plane_channel(c, rc, lvl, pl, att, ch);
+                float u, w;
+                plane_axes(pl, ind, u, w);
+                const int E = p.E[lvl];
+                const Bilin b = bilin_setup(u, w, E);
+                const float *base = (att ? p.att[pl] : p.plane[lvl][pl]) + (size_t)ch * E * E;
+                val = bilin_fetch(base, b);
+                if (p.noise && c >= 6 * rc) val += __ldg(p.noise + (size_t)v * (DP - 6 * rc) + (c - 6 * rc));
+            } else {
+                const int g = c - DP;
+                if (g < FD) val = __ldg(p.anchor_feat + (size_t)i * FD + g);
+                else if (g < FD + 3) val = g == FD ? ax : (g == FD + 1 ? ay : az);
+                else if (g < FD + 3 + 3 * KO) val = __ldg(p.offset + (size_t)i * 3 * KO + (g - FD - 3));
+                else val = __ldg(p.scaling + (size_t)i * 6 + (g - FD - 3 - 3 * KO));
+            }
+            xrow[c] = val;
+            sum[j] += val; sq[j] = fmaf(val, val, sq[j]);
+        }
+        if (lane < LDX - ncols) xrow[ncols + lane] = 0.f;       // zero the row padding
+        // x100 head: feat | dir | dist   (gaussian_renderer/__init__.py:34-38,55)
+        float *xin = XIN + (size_t)v * XI;
+        xin[lane] = __ldg(p.anchor_feat + (size_t)i * FD + lane);
+        if (lane < 4) {
+            const float vx = ax - p.cam[0], vy = ay - p.cam[1], vz = az - p.cam[2];
+            const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
+            xin[FD + lane] = lane == 0 ? vx / dist : (lane == 1 ? vy / dist : (lane == 2 ? vz / dist : dist));
+        }
+    }
+    // CTA reduction of the statistics, then one fp64 atomic per channel per CTA
+    float *mine = s_red + (size_t)warp * 2 * LDX;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+        const int c = lane + 32 * j;
+        if (c < ncols) { mine[c] = sum[j]; mine[LDX + c] = sq[j]; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+        double s = 0.0, q = 0.0;
+#pragma unroll
+        for (int w = 0; w < GATHER_WARPS; ++w) { s += (double)s_red[(size_t)w * 2 * LDX + c]; q += (double)s_red[(size_t)w * 2 * LDX + LDX + c]; }
+        atomicAdd(&stats[c], s);
+        atomicAdd(&stats[LDX + c], q);
+    }
+}
+
+// =======================================================================================================
+// Fold kernel (one CTA): batch mean / rstd, running-stat update, BN folded into the Linear weights,
+// head weights re-laid out as [K][N] GEMM operands.
+// =======================================================================================================
+struct DecWeights {
+    const float *bn_w[3], *bn_b[3], *lin_w[3], *lin_b[3];        // plane branch per level
+    const float *cbn_w[3], *cbn_b[3], *clin_w[3], *clin_b[3];    // context branch per level
+    float *bn_rm[3], *bn_rv[3], *cbn_rm[3], *cbn_rv[3];          // running stats (updated in place; may be null)
+    long long *bn_nbt[3], *cbn_nbt[3];
+    const float *w1[3], *b1[3], *w2[3], *b2[3];                  // opacity, cov, colour heads
+    const float *app_vec;
+    int use_dist[3];
+    int app_dim;
+    float eps, momentum;
+};
+
+__device__ __forceinline__ int level_dim(int l, int rc) { return l == 0 ? 6 * rc : 3 * rc; }
+__device__ __forceinline__ int level_base(int l, int rc) { return l == 0 ? 0 : (l == 1 ? 6 * rc : 9 * rc); }
+
+__global__ void __launch_bounds__(256)
+dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const double *__restrict__ stats,
+                float *__restrict__ mu, float *__restrict__ rstd, float *__restrict__ WpT, float *__restrict__ WcT,
+                float *__restrict__ bgeo, float *__restrict__ W1T, float *__restrict__ b1e, float *__restrict__ W2T,
+                float *__restrict__ b2, float *__restrict__ WpG, float *__restrict__ WcG, int update_running) {
+    const int tid = threadIdx.x;
+    const int ncols = DP + GD;
+    for (int c = tid; c < LDX; c += 256) {
+        if (c >= ncols) { mu[c] = 0.f; rstd[c] = 0.f; continue; }
+        const double mean = stats[c] / (double)V;
+        double var = stats[LDX + c] / (double)V - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mu[c] = (float)mean;
+        rstd[c] = (float)(1.0 / sqrt(var + (double)w.eps));
+        if (update_running) {
+            const float unb = (float)(V > 1 ? var * (double)V / (double)(V - 1) : var);
+            const float m = w.momentum;
+            if (c < DP) {
+                int l = c < 6 * rc ? 0 : (c < 9 * rc ? 1 : 2);
+                const int cl = c - level_base(l, rc);
+                if (w.bn_rm[l]) w.bn_rm[l][cl] = (1.f - m) * w.bn_rm[l][cl] + m * (float)mean;
+                if (w.bn_rv[l]) w.bn_rv[l][cl] = (1.f - m) * w.bn_rv[l][cl] + m * unb;
+            } else {
+                const int g = c - DP;
+                for (int l = 0; l <= level; ++l) {
+                    if (w.cbn_rm[l]) w.cbn_rm[l][g] = (1.f - m) * w.cbn_rm[l][g] + m * (float)mean;
+                    if (w.cbn_rv[l]) w.cbn_rv[l][g] = (1.f - m) * w.cbn_rv[l][g] + m * unb;
+                }
+            }
+        }
+    }
+    if (update_running && tid == 0)
+        for (int l = 0; l <= level; ++l) {
+            if (w.bn_nbt[l]) *w.bn_nbt[l] += 1;
+            if (w.cbn_nbt[l]) *w.cbn_nbt[l] += 1;
+        }
+    __syncthreads();
+    // plane branch
+    for (int e = tid; e < DP * 32; e += 256) {
+        const int c = e >> 5, o = e & 31;
+        const int l = c < 6 * rc ? 0 : (c < 9 * rc ? 1 : 2);
+        const int d = level_dim(l, rc), cl = c - level_base(l, rc);
+        const float gw = w.bn_w[l][cl] * w.lin_w[l][o * d + cl];
+        WpG[o * DP + c] = gw;
+        WpT[c * 32 + o] = gw * rstd[c];
+    }
+    // context branch (all active levels normalise the same g with the same batch statistics)
+    for (int e = tid; e < GD * 32; e += 256) {
+        const int g = e >> 5, o = e & 31;
+        float gw = 0.f;
+        for (int l = 0; l <= level; ++l) gw = fmaf(w.cbn_w[l][g], w.clin_w[l][o * GD + g], gw);
+        WcG[o * GD + g] = gw;
+        WcT[g * 32 + o] = gw * rstd[DP + g];
+    }
+    __syncthreads();
+    // geo bias: Linear bias + beta through the Linear - mean through the folded weights
+    if (tid < 64) {
+        const int o = tid & 31;
+        float b = 0.f;
+        if (tid < 32) {
+            for (int l = 0; l <= level; ++l) {
+                const int d = level_dim(l, rc), base = level_base(l, rc);
+                b += w.lin_b[l][o];
+                for (int cl = 0; cl < d; ++cl) b = fmaf(w.bn_b[l][cl], w.lin_w[l][o * d + cl], b);
+                for (int cl = 0; cl < d; ++cl) b = fmaf(-mu[base + cl], WpT[(base + cl) * 32 + o], b);
+            }
+        } else {
+            for (int l = 0; l <= level; ++l) {
+                b += w.clin_b[l][o];
+                for (int g = 0; g < GD; ++g) b = fmaf(w.cbn_b[l][g], w.clin_w[l][o * GD + g], b);
+            }
+            for (int g = 0; g < GD; ++g) b = fmaf(-mu[DP + g], WcT[g * 32 + o], b);
+        }
+        bgeo[tid] = b;
+    }
+    // hidden layer: x100 = [feat 32 | dir 3 | dist 1 | geo 64]; per-head torch layout is
+    // [feat | dir | (dist) | geo | (appearance, colour head only)]
+    for (int e = tid; e < XI * HD; e += 256) {
+        const int k = e / HD, n = e - k * HD;
+        const int hd = n >> 5, o = n & 31;
+        const int dd = w.use_dist[hd];
+        const int in_h = 35 + dd + 64 + (hd == 2 ? w.app_dim : 0);
+        float v;
+        if (k < 35) v = w.w1[hd][o * in_h + k];
+        else if (k == 35) v = dd ? w.w1[hd][o * in_h + 35] : 0.f;
+        else v = w.w1[hd][o * in_h + 35 + dd + (k - 36)];
+        W1T[e] = v;
+    }
+    if (tid < HD) {
+        const int hd = tid >> 5, o = tid & 31;
+        float b = w.b1[hd][o];
+        if (hd == 2 && w.app_dim > 0) {
+            const int dd = w.use_dist[2];
+            const int in_h = 35 + dd + 64 + w.app_dim;
+            for (int a = 0; a < w.app_dim; ++a) b = fmaf(w.w1[2][o * in_h + 35 + dd + 64 + a], w.app_vec[a], b);
+        }
+        b1e[tid] = b;
+    }
+    // output layer as one block-diagonal [96][112] operand: cols [opacity 0..9 | cov 10..79 | colour 80..109]
+    for (int e = tid; e < HD * ZD; e += 256) {
+        const int i = e / ZD, j = e - i * ZD;
+        const int hd_i = i >> 5, ii = i & 31;
+        float v = 0.f;
+        if (j < KO) { if (hd_i == 0) v = w.w2[0][j * 32 + ii]; }
+        else if (j < 8 * KO) { if (hd_i == 1) v = w.w2[1][(j - KO) * 32 + ii]; }
+        else if (j < 11 * KO) { if (hd_i == 2) v = w.w2[2][(j - 8 * KO) * 32 + ii]; }
+        W2T[e] = v;
+    }
+    if (tid < ZD) {
+        float v = 0.f;
+        if (tid < KO) v = w.b2[0][tid];
+        else if (tid < 8 * KO) v = w.b2[1][tid - KO];
+        else if (tid < 11 * KO) v = w.b2[2][tid - 8 * KO];
+        b2[tid] = v;
+    }
+}
+
+// =======================================================================================================
+// Head activations, opacity mask, per-anchor survivor counts (first scan level)
+// =======================================================================================================
+__global__ void __launch_bounds__(256)
+dec_heads_act_kernel(int V, float *__restrict__ Z, float *__restrict__ neural_opacity, uint8_t *__restrict__ mask_out,
+                     uint32_t *__restrict__ maskbits, uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[8];
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    uint32_t cnt = 0;
+    if (v < V) {
+        float *z = Z + (size_t)v * ZD;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < KO; ++k) {
+            const float t = tanhf(z[k]);
+            z[k] = t;
+            neural_opacity[(size_t)v * KO + k] = t;
+            const bool m = t > 0.f;
+            mask_out[(size_t)v * KO + k] = m ? 1 : 0;
+            bits |= m ? (1u << k) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 3 * KO; ++j) {
+            const float x = z[8 * KO + j];
+            z[8 * KO + j] = 1.f / (1.f + expf(-x));
+        }
+        maskbits[v] = bits;
+        cnt = __popc(bits);
+    }
+    uint32_t s = cnt;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_warp[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// exclusive per-anchor offsets from maskbits + scanned block offsets (same 256-wide partition)
+__global__ void __launch_bounds__(256)
+dec_offsets_kernel(int V, const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ block_offsets,
+                   uint32_t *__restrict__ offs) {
+    __shared__ uint32_t s_warp[8];
+    const int v = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t c = v < V ? __popc(maskbits[v]) : 0u;
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += n; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) woff += (w < (int)warp) ? s_warp[w] : 0u;
+    if (v < V) offs[v] = block_offsets[blockIdx.x] + woff + inc - c;
+}
+
+// compaction + post-processing (gaussian_renderer/__init__.py:96-111), one thread per (anchor, offset)
+__global__ void __launch_bounds__(256)
+dec_compact_kernel(int V, int LDX, int DP, const float *__restrict__ X, const float *__restrict__ Z,
+                   const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ offs,
+                   float *__restrict__ xyz, float *__restrict__ color, float *__restrict__ opacity,
+                   float *__restrict__ scaling, float *__restrict__ rot) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= V * KO) return;
+    const int v = t / KO, k = t - v * KO;
+    const uint32_t bits = maskbits[v];
+    if (!((bits >> k) & 1u)) return;
+    const size_t j = offs[v] + __popc(bits & ((1u << k) - 1u));
+    const float *g = X + (size_t)v * LDX + DP;       // [feat 32 | anchor 3 | offsets 30 | scaling 6]
+    const float *z = Z + (size_t)v * ZD;
+    const float *s6 = g + FD + 3 + 3 * KO;
+    const float *of = g + FD + 3 + 3 * k;
+    xyz[3 * j] = g[FD] + of[0] * s6[0];
+    xyz[3 * j + 1] = g[FD + 1] + of[1] * s6[1];
+    xyz[3 * j + 2] = g[FD + 2] + of[2] * s6[2];
+    color[3 * j] = z[8 * KO + 3 * k]; color[3 * j + 1] = z[8 * KO + 3 * k + 1]; color[3 * j + 2] = z[8 * KO + 3 * k + 2];
+    opacity[j] = z[k];
+    const float *sr = z + KO + 7 * k;
+    scaling[3 * j] = s6[3] / (1.f + expf(-sr[0]));
+    scaling[3 * j + 1] = s6[4] / (1.f + expf(-sr[1]));
+    scaling[3 * j + 2] = s6[5] / (1.f + expf(-sr[2]));
+    const float n = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
+    rot[4 * j] = sr[3] / n; rot[4 * j + 1] = sr[4] / n; rot[4 * j + 2] = sr[5] / n; rot[4 * j + 3] = sr[6] / n;
+}
+
+// =======================================================================================================
+// Backward elementwise stages
+// =======================================================================================================
+// un-compaction: upstream gradients of the five compacted outputs -> dZ rows (pre-activation) and the
+// direct (non-MLP) gradients of anchor / offsets / scaling.  One thread per visible anchor.
+__global__ void __launch_bounds__(128)
+dec_bwd_uncompact_kernel(int V, int LDX, int DP, const float *__restrict__ X, const float *__restrict__ Z,
+                         const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ offs,
+                         const float *__restrict__ d_xyz, const float *__restrict__ d_color,
+                         const float *__restrict__ d_opacity, const float *__restrict__ d_scaling,
+                         const float *__restrict__ d_rot, const float *__restrict__ d_nopac,
+                         float *__restrict__ DZ, float *__restrict__ DGA) {
+    const int v = blockIdx.x * 128 + threadIdx.x;
+    if (v >= V) return;
+    const uint32_t bits = maskbits[v];
+    const float *g = X + (size_t)v * LDX + DP;
+    const float *z = Z + (size_t)v * ZD;
+    const float *s6 = g + FD + 3 + 3 * KO;
+    float *dz = DZ + (size_t)v * ZD;
+    float *dga = DGA + (size_t)v * 40;          // [anchor 3 | offsets 30 | scaling 6 | pad]
+    float da0 = 0.f, da1 = 0.f, da2 = 0.f, ds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    size_t j = offs[v];
+    for (int k = 0; k < KO; ++k) {
+        const bool m = (bits >> k) & 1u;
+        const float no = z[k];
+        float dno = d_nopac ? d_nopac[(size_t)v * KO + k] : 0.f;
+        float dof[3] = {0.f, 0.f, 0.f}, dc[3] = {0.f, 0.f, 0.f}, dsr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (m) {
+            dno += d_opacity[j];
+            const float gx = d_xyz[3 * j], gy = d_xyz[3 * j + 1], gz = d_xyz[3 * j + 2];
+            const float *of = g + FD + 3 + 3 * k;
+            da0 += gx; da1 += gy; da2 += gz;
+            dof[0] = gx * s6[0]; dof[1] = gy * s6[1]; dof[2] = gz * s6[2];
+            ds[0] += gx * of[0]; ds[1] += gy * of[1]; ds[2] += gz * of[2];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float c = z[8 * KO + 3 * k + q];
+                dc[q] = d_color[3 * j + q] * c * (1.f - c);
+            }
+            const float *sr = z + KO + 7 * k;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const float sg = 1.f / (1.f + expf(-sr[q]));
+                const float gsc = d_scaling[3 * j + q];
+                dsr[q] = gsc * s6[3 + q] * sg * (1.f - sg);
+                ds[3 + q] += gsc * sg;
+            }
+            const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
+            const float n = fmaxf(nrm, 1e-12f);
+            const float r0 = sr[3] / n, r1 = sr[4] / n, r2 = sr[5] / n, r3 = sr[6] / n;
+            const float g0 = d_rot[4 * j], g1 = d_rot[4 * j + 1], g2 = d_rot[4 * j + 2], g3 = d_rot[4 * j + 3];
+            if (nrm > 1e-12f) {
+                const float dot = r0 * g0 + r1 * g1 + r2 * g2 + r3 * g3;
+                dsr[3] = (g0 - r0 * dot) / n; dsr[4] = (g1 - r1 * dot) / n;
+                dsr[5] = (g2 - r2 * dot) / n; dsr[6] = (g3 - r3 * dot) / n;
+            } else {
+                dsr[3] = g0 / n; dsr[4] = g1 / n; dsr[5] = g2 / n; dsr[6] = g3 / n;
+            }
+            ++j;
+        }
+        dz[k] = dno * (1.f - no * no);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) dz[KO + 7 * k + q] = dsr[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { dz[8 * KO + 3 * k + q] = dc[q]; dga[3 + 3 * k + q] = dof[q]; }
+    }
+    dz[11 * KO] = 0.f; dz[11 * KO + 1] = 0.f;
+    dga[0] = da0; dga[1] = da1; dga[2] = da2;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) dga[33 + q] = ds[q];
+    dga[39] = 0.f;
+}
+
+// S0/S1 -> parameter gradients of the BN+Linear branches and the per-channel BN-backward constants m1, m2.
+struct DecWeightGrads {
+    float *bn_w[3], *bn_b[3], *lin_w[3], *lin_b[3];
+    float *cbn_w[3], *cbn_b[3], *clin_w[3], *clin_b[3];
+    float *w1[3], *b1[3], *w2[3], *b2[3];
+    float *app_vec;
+};
+
+__global__ void __launch_bounds__(256)
+dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, int DP, int LDX,
+                    const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ WpG,
+                    const float *__restrict__ WcG, const float *__restrict__ S1raw /*[32][LDX]*/,
+                    const float *__restrict__ S0 /*[64]*/, const float *__restrict__ gW1T, const float *__restrict__ gb1,
+                    const float *__restrict__ gW2T, const float *__restrict__ gb2, float *__restrict__ m1,
+                    float *__restrict__ m2) {
+    const int tid = threadIdx.x;
+    const int ncols = DP + GD;
+    const float invV = 1.f / (float)V;
+    // S1[o][c] = sum_rows dgeo[o] * xhat[c] = rstd[c] * (S1raw[o][c] - mu[c] * S0branch[o])
+    for (int c = tid; c < LDX; c += 256) {
+        if (c >= ncols) { m1[c] = 0.f; m2[c] = 0.f; continue; }
+        const bool pl = c < DP;
+        const float *WG = pl ? WpG : WcG;
+        const int ldw = pl ? DP : GD, cc = pl ? c : c - DP;
+        const float *S0b = pl ? S0 : S0 + 32;
+        float a1 = 0.f, a2 = 0.f;
+        for (int o = 0; o < 32; ++o) {
+            const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0b[o]);
+            a1 = fmaf(WG[o * ldw + cc], S0b[o], a1);
+            a2 = fmaf(WG[o * ldw + cc], s1, a2);
+        }
+        m1[c] = a1 * invV;
+        m2[c] = a2 * invV;
+    }
+    // plane branch parameter grads
+    for (int l = 0; l <= level; ++l) {
+        const int d = level_dim(l, rc), base = level_base(l, rc);
+        for (int e = tid; e < 32 * d; e += 256) {
+            const int o = e / d, cl = e - o * d, c = base + cl;
+            const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[o]);
+            if (gw.lin_w[l]) gw.lin_w[l][o * d + cl] = w.bn_w[l][cl] * s1 + w.bn_b[l][cl] * S0[o];
+        }
+        for (int cl = tid; cl < d; cl += 256) {
+            const int c = base + cl;
+            float gg = 0.f, gb = 0.f;
+            for (int o = 0; o < 32; ++o) {
+                const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[o]);
+                gg = fmaf(w.lin_w[l][o * d + cl], s1, gg);
+                gb = fmaf(w.lin_w[l][o * d + cl], S0[o], gb);
+            }
+            if (gw.bn_w[l]) gw.bn_w[l][cl] = gg;
+            if (gw.bn_b[l]) gw.bn_b[l][cl] = gb;
+        }
+        if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] = S0[tid];
+        // context branch
+        for (int e = tid; e < 32 * GD; e += 256) {
+            const int o = e / GD, g = e - o * GD, c = DP + g;
+            const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[32 + o]);
+            if (gw.clin_w[l]) gw.clin_w[l][o * GD + g] = w.cbn_w[l][g] * s1 + w.cbn_b[l][g] * S0[32 + o];
+        }
+        for (int g = tid; g < GD; g += 256) {
+            const int c = DP + g;
+            float gg = 0.f, gb = 0.f;
+            for (int o = 0; o < 32; ++o) {
+                const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[32 + o]);
+                gg = fmaf(w.clin_w[l][o * GD + g], s1, gg);
+                gb = fmaf(w.clin_w[l][o * GD + g], S0[32 + o], gb);
+            }
+            if (gw.cbn_w[l]) gw.cbn_w[l][g] = gg;
+            if (gw.cbn_b[l]) gw.cbn_b[l][g] = gb;
+        }
+        if (tid < 32 && gw.clin_b[l]) gw.clin_b[l][tid] = S0[32 + tid];
+    }
+    // heads: un-fold gW1T[k][n] / gW2T[i][j] into torch layouts
+    for (int hd = 0; hd < 3; ++hd) {
+        const int dd = w.use_dist[hd];
+        const int app = hd == 2 ? w.app_dim : 0;
+        const int in_h = 35 + dd + 64 + app;
+        if (gw.w1[hd])
+            for (int e = tid; e < 32 * in_h; e += 256) {
+                const int o = e / in_h, col = e - o * in_h;
+                const int n = hd * 32 + o;
+                float v;
+                if (col < 35) v = gW1T[col * HD + n];
+                else if (dd && col == 35) v = gW1T[35 * HD + n];
+                else if (col < 35 + dd + 64) v = gW1T[(36 + col - 35 - dd) * HD + n];
+                else v = gb1[n] * w.app_vec[col - 35 - dd - 64];
+                gw.w1[hd][e] = v;
+            }
+        if (gw.b1[hd] && tid < 32) gw.b1[hd][tid] = gb1[hd * 32 + tid];
+        const int nout = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO);
+        const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO);
+        if (gw.w2[hd])
+            for (int e = tid; e < nout * 32; e += 256) {
+                const int j = e >> 5, ii = e & 31;
+                gw.w2[hd][e] = gW2T[(hd * 32 + ii) * ZD + j0 + j];
+            }
+        if (gw.b2[hd])
+            for (int j = tid; j < nout; j += 256) gw.b2[hd][j] = gb2[j0 + j];
+    }
+    if (gw.app_vec && w.app_dim > 0) {
+        const int dd = w.use_dist[2];
+        const int in_h = 35 + dd + 64 + w.app_dim;
+        for (int a = tid; a < w.app_dim; a += 256) {
+            float s = 0.f;
+            for (int o = 0; o < 32; ++o) s = fmaf(w.w1[2][o * in_h + 35 + dd + 64 + a], gb1[64 + o], s);
+            gw.app_vec[a] = s;
+        }
+    }
+}
+
+// Final input gradients: BN backward through the folded branch (dx = rstd (dxhat - m1 - xhat m2)),
+// bilinear scatter into the plane gradients, and the per-anchor rows of the N-row gradient tensors.
+// One warp per visible anchor (same mapping as the gather).
+struct DecInputGrads {
+    float *anchor_feat, *anchor, *offset, *scaling;     // [N,*], visible rows overwritten
+    float *plane[3][3];
+    float *att[3];
+};
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LDX, const float *__restrict__ X,
+                      const float *__restrict__ XIN, const float *__restrict__ mu, const float *__restrict__ rstd,
+                      const float *__restrict__ m1, const float *__restrict__ m2, const float *__restrict__ DXH,
+                      const float *__restrict__ DX, const float *__restrict__ DGA) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps_total = gridDim.x * GATHER_WARPS;
+    const int ncols = DP + GD;
+    for (int v = blockIdx.x * GATHER_WARPS + warp; v < V; v += nwarps_total) {
+        const int i = p.vis[v];
+        const float ax = __ldg(p.anchor + 3 * (size_t)i), ay = __ldg(p.anchor + 3 * (size_t)i + 1), az = __ldg(p.anchor + 3 * (size_t)i + 2);
+        float ind[3];
+        norm_coords(p, ax, ay, az, ind);
+        const float *xrow = X + (size_t)v * LDX, *dxh = DXH + (size_t)v * LDX;
+        const float *dx100 = DX + (size_t)v * XI, *dga = DGA + (size_t)v * 40, *xin = XIN + (size_t)v * XI;
+        // direction / distance gradient -> anchor (every lane computes all three components)
+        float dv0, dv1, dv2;
+        {
+            const float d0 = xin[FD], d1 = xin[FD + 1], d2 = xin[FD + 2], dist = xin[FD + 3];
+            const float g0 = dx100[FD], g1 = dx100[FD + 1], g2 = dx100[FD + 2], gd = dx100[FD + 3];
+            const float dot = d0 * g0 + d1 * g1 + d2 * g2;
+            dv0 = (g0 - d0 * dot) / dist + gd * d0;
+            dv1 = (g1 - d1 * dot) / dist + gd * d1;
+            dv2 = (g2 - d2 * dot) / dist + gd * d2;
+        }
+        for (int c = lane; c < ncols; c += 32) {
+            const float xh = (xrow[c] - mu[c]) * rstd[c];
+            const float dx = rstd[c] * (dxh[c] - m1[c] - xh * m2[c]);
+            if (c < DP) {
+                int lvl, pl, att, ch;
+                plane_channel(c, rc, lvl, pl, att, ch);
+                float u, w;
+                plane_axes(pl, ind, u, w);
+                const int E = p.E[lvl];
+                const Bilin b = bilin_setup(u, w, E);
+                float *base = (att ? gi.att[pl] : gi.plane[lvl][pl]);
+                if (base) bilin_scatter(base + (size_t)ch * E * E, b, dx);
+            } else {
+                const int g = c - DP;
+                if (g < FD) gi.anchor_feat[(size_t)i * FD + g] = dx + dx100[g];
+                else if (g < FD + 3) {
+                    const int q = g - FD;
+                    gi.anchor[3 * (size_t)i + q] = dx + dga[q] + (q == 0 ? dv0 : (q == 1 ? dv1 : dv2));
+                }
+                else if (g < FD + 3 + 3 * KO) gi.offset[(size_t)i * 3 * KO + (g - FD - 3)] = dx + dga[3 + (g - FD - 3)];
+                else gi.scaling[(size_t)i * 6 + (g - FD - 3 - 3 * KO)] = dx + dga[33 + (g - FD - 3 - 3 * KO)];
+            }
+        }
+    }
+}
+
+}  // namespace splatco
+
+using namespace splatco;
+
+namespace {
+
+struct FwdView {
+    float *X, *mu, *rstd, *WpT, *WcT, *bgeo, *W1T, *b1e, *W2T, *b2, *WpG, *WcG, *XIN, *H, *Z;
+    double *stats;
+    uint32_t *maskbits, *offs, *bsum, *boff, *total;
+};
+FwdView fwd_view(void *ws, const DecDims &d) {
+    size_t off[F_NCHUNK + 1];
+    dec_fwd_offsets(d, off);
+    char *b = (char *)ws;
+    FwdView v;
+    v.X = (float *)(b + off[F_X]); v.stats = (double *)(b + off[F_STATS]);
+    v.mu = (float *)(b + off[F_MU]); v.rstd = (float *)(b + off[F_RSTD]);
+    v.WpT = (float *)(b + off[F_WPT]); v.WcT = (float *)(b + off[F_WCT]); v.bgeo = (float *)(b + off[F_BGEO]);
+    v.W1T = (float *)(b + off[F_W1T]); v.b1e = (float *)(b + off[F_B1E]);
+    v.W2T = (float *)(b + off[F_W2T]); v.b2 = (float *)(b + off[F_B2]);
+    v.WpG = (float *)(b + off[F_WPG]); v.WcG = (float *)(b + off[F_WCG]);
+    v.XIN = (float *)(b + off[F_XIN]); v.H = (float *)(b + off[F_H]); v.Z = (float *)(b + off[F_Z]);
+    v.maskbits = (uint32_t *)(b + off[F_MASKBITS]); v.offs = (uint32_t *)(b + off[F_OFFS]);
+    v.bsum = (uint32_t *)(b + off[F_BSUM]); v.boff = (uint32_t *)(b + off[F_BOFF]);
+    v.total = (uint32_t *)(b + off[F_TOTAL]);
+    return v;
+}
+
+struct BwdView {
+    float *DZ, *DH, *DX, *DXH, *DGA, *gW2T, *gb2, *gW1T, *gb1, *S1, *S0, *m1, *m2;
+    char *acc_begin; size_t acc_bytes;
+};
+BwdView bwd_view(void *ws, const DecDims &d) {
+    size_t off[B_NCHUNK + 1];
+    dec_bwd_offsets(d, off);
+    char *b = (char *)ws;
+    BwdView v;
+    v.DZ = (float *)(b + off[B_DZ]); v.DH = (float *)(b + off[B_DH]); v.DX = (float *)(b + off[B_DX]);
+    v.DXH = (float *)(b + off[B_DXH]); v.DGA = (float *)(b + off[B_DGA]);
+    v.gW2T = (float *)(b + off[B_GW2T]); v.gb2 = (float *)(b + off[B_GB2]);
+    v.gW1T = (float *)(b + off[B_GW1T]); v.gb1 = (float *)(b + off[B_GB1]);
+    v.S1 = (float *)(b + off[B_S1]); v.S0 = (float *)(b + off[B_S0]);
+    v.m1 = (float *)(b + off[B_M1]); v.m2 = (float *)(b + off[B_M2]);
+    v.acc_begin = b + off[B_GW2T]; v.acc_bytes = off[B_M1] - off[B_GW2T];
+    return v;
+}
+
+int check_desc(const splatco_decode_desc *d) {
+    SPLATCO_REQUIRE(d, "decode: null descriptor");
+    SPLATCO_REQUIRE(d->K == KO, "decode: n_offsets=%d unsupported (kernels are specialised for %d)", d->K, KO);
+    SPLATCO_REQUIRE(d->level >= 0 && d->level <= 2, "decode: activate_level %d out of range", d->level);
+    SPLATCO_REQUIRE(d->rc >= 1 && d->rc * 12 <= DEC_MAX_DP, "decode: channels per plane %d unsupported", d->rc);
+    SPLATCO_REQUIRE(d->V >= 0 && d->N >= d->V, "decode: bad sizes N=%d V=%d", d->N, d->V);
+    SPLATCO_REQUIRE(d->app_dim >= 0 && (d->app_dim == 0 || d->app_vec), "decode: appearance vector missing");
+    if (d->V == 0) return 0;
+    SPLATCO_REQUIRE(d->anchor_feat && d->anchor && d->offset && d->scaling && d->vis, "decode: null input");
+    for (int l = 0; l <= d->level; ++l) {
+        SPLATCO_REQUIRE(d->E[l] >= 2, "decode: plane edge %d too small", d->E[l]);
+        for (int p = 0; p < 3; ++p) SPLATCO_REQUIRE(d->plane[3 * l + p], "decode: null plane (level %d)", l);
+        SPLATCO_REQUIRE(d->bn_w[l] && d->bn_b[l] && d->lin_w[l] && d->lin_b[l] && d->cbn_w[l] && d->cbn_b[l] &&
+                        d->clin_w[l] && d->clin_b[l], "decode: null BN/Linear parameter (level %d)", l);
+    }
+    for (int p = 0; p < 3; ++p) SPLATCO_REQUIRE(d->att[p], "decode: null attended plane");
+    for (int h = 0; h < 3; ++h)
+        SPLATCO_REQUIRE(d->w1[h] && d->b1[h] && d->w2[h] && d->b2[h], "decode: null head parameter");
+    return 0;
+}
+
+DecPtrs make_ptrs(const splatco_decode_desc *d) {
+    DecPtrs p;
+    p.anchor_feat = d->anchor_feat; p.anchor = d->anchor; p.offset = d->offset; p.scaling = d->scaling;
+    p.vis = d->vis;
+    for (int l = 0; l < 3; ++l) {
+        p.E[l] = d->E[l];
+        for (int q = 0; q < 3; ++q) p.plane[l][q] = d->plane[3 * l + q];
+    }
+    for (int q = 0; q < 3; ++q) { p.att[q] = d->att[q]; p.mn[q] = d->xyz_min[q]; p.mx[q] = d->xyz_max[q]; p.cam[q] = d->cam[q]; }
+    p.noise = d->noise;
+    return p;
+}
+
+DecWeights make_weights(const splatco_decode_desc *d) {
+    DecWeights w;
+    for (int l = 0; l < 3; ++l) {
+        w.bn_w[l] = d->bn_w[l]; w.bn_b[l] = d->bn_b[l]; w.lin_w[l] = d->lin_w[l]; w.lin_b[l] = d->lin_b[l];
+        w.cbn_w[l] = d->cbn_w[l]; w.cbn_b[l] = d->cbn_b[l]; w.clin_w[l] = d->clin_w[l]; w.clin_b[l] = d->clin_b[l];
+        w.bn_rm[l] = d->bn_rm[l]; w.bn_rv[l] = d->bn_rv[l]; w.cbn_rm[l] = d->cbn_rm[l]; w.cbn_rv[l] = d->cbn_rv[l];
+        w.bn_nbt[l] = (long long *)d->bn_nbt[l]; w.cbn_nbt[l] = (long long *)d->cbn_nbt[l];
+        w.w1[l] = d->w1[l]; w.b1[l] = d->b1[l]; w.w2[l] = d->w2[l]; w.b2[l] = d->b2[l];
+        w.use_dist[l] = d->use_dist[l];
+    }
+    w.app_vec = d->app_vec; w.app_dim = d->app_dim; w.eps = d->bn_eps; w.momentum = d->bn_momentum;
+    return w;
+}
+
+int gather_grid(int V) { return min(ceil_div(V, GATHER_WARPS), 148 * 8); }
+
+}  // namespace
+
+extern "C" size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level) {
+    size_t off[F_NCHUNK + 1];
+    return dec_fwd_offsets(dec_dims(V, rc, level), off);
+}
+extern "C" size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level) {
+    size_t off[B_NCHUNK + 1];
+    return dec_bwd_offsets(dec_dims(V, rc, level), off);
+}
+
+extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
+                                  int32_t *M_host, void *stream) {
+    if (check_desc(d)) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->V == 0) { if (M_host) *M_host = 0; return 0; }
+    SPLATCO_REQUIRE(d->V >= 2, "decode: BatchNorm in train mode needs more than 1 visible anchor (got %d)", d->V);
+    SPLATCO_REQUIRE(ws && neural_opacity && mask, "decode_fwd: null pointer");
+    const DecDims dd = dec_dims(d->V, d->rc, d->level);
+    const int V = d->V;
+    FwdView f = fwd_view(ws, dd);
+    const DecPtrs p = make_ptrs(d);
+    const DecWeights w = make_weights(d);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.stats, 0, 2 * (size_t)dd.LDX * sizeof(double), st));
+    dec_gather_kernel<<<gather_grid(V), GATHER_WARPS * 32, GATHER_WARPS * 2 * dd.LDX * sizeof(float), st>>>(
+        p, V, dd.rc, dd.DP, dd.LDX, f.X, f.XIN, f.stats);
+    SPLATCO_CHECK_LAUNCH();
+    dec_fold_kernel<<<1, 256, 0, st>>>(w, V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
+                                       f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
+    SPLATCO_CHECK_LAUNCH();
+    // geo = [ (P - mu) Wp' | (g - mu) Wc' ] + bias, written straight into x100 columns 36..99
+    if (sgemm<false, false>(st, V, 32, dd.DP, f.X, dd.LDX, f.WpT, 32, f.XIN + 36, XI, f.bgeo)) return -2;
+    if (sgemm<false, false>(st, V, 32, GD, f.X + dd.DP, dd.LDX, f.WcT, 32, f.XIN + 68, XI, f.bgeo + 32)) return -2;
+    if (sgemm<false, false>(st, V, HD, XI, f.XIN, XI, f.W1T, HD, f.H, HD, f.b1e, 1)) return -2;
+    if (sgemm<false, false>(st, V, ZD, HD, f.H, HD, f.W2T, ZD, f.Z, ZD, f.b2)) return -2;
+    const int nb = ceil_div(V, 256);
+    dec_heads_act_kernel<<<nb, 256, 0, st>>>(V, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
+    SPLATCO_CHECK_LAUNCH();
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
+    SPLATCO_CHECK_LAUNCH();
+    dec_offsets_kernel<<<nb, 256, 0, st>>>(V, f.maskbits, f.boff, f.offs);
+    SPLATCO_CHECK_LAUNCH();
+    if (M_host) SPLATCO_CHECK_CUDA(cudaMemcpyAsync(M_host, f.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+extern "C" int splatco_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
+                                   float *opacity, float *scaling, float *rot, void *stream) {
+    if (check_desc(d)) return -1;
+    if (d->V == 0 || M == 0) return 0;
+    SPLATCO_REQUIRE(ws && xyz && color && opacity && scaling && rot, "decode_emit: null pointer");
+    const DecDims dd = dec_dims(d->V, d->rc, d->level);
+    FwdView f = fwd_view(const_cast<void *>(ws), dd);
+    dec_compact_kernel<<<ceil_div(d->V * KO, 256), 256, 0, (cudaStream_t)stream>>>(
+        d->V, dd.LDX, dd.DP, f.X, f.Z, f.maskbits, f.offs, xyz, color, opacity, scaling, rot);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M,
+                                  const float *d_xyz, const float *d_color, const float *d_opacity,
+                                  const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
+                                  const splatco_decode_grads *g, void *stream) {
+    if (check_desc(d)) return -1;
+    if (d->V == 0) return 0;
+    SPLATCO_REQUIRE(fwd_ws && bwd_ws && g, "decode_bwd: null pointer");
+    SPLATCO_REQUIRE(M == 0 || (d_xyz && d_color && d_opacity && d_scaling && d_rot), "decode_bwd: null upstream gradient");
+    SPLATCO_REQUIRE(g->anchor_feat && g->anchor && g->offset && g->scaling, "decode_bwd: null per-anchor gradient");
+    cudaStream_t st = (cudaStream_t)stream;
+    const DecDims dd = dec_dims(d->V, d->rc, d->level);
+    const int V = d->V, DP = dd.DP, LDX = dd.LDX;
+    FwdView f = fwd_view(const_cast<void *>(fwd_ws), dd);
+    BwdView b = bwd_view(bwd_ws, dd);
+    const DecPtrs p = make_ptrs(d);
+    const DecWeights w = make_weights(d);
+    DecWeightGrads gw;
+    DecInputGrads gi;
+    for (int l = 0; l < 3; ++l) {
+        gw.bn_w[l] = g->bn_w[l]; gw.bn_b[l] = g->bn_b[l]; gw.lin_w[l] = g->lin_w[l]; gw.lin_b[l] = g->lin_b[l];
+        gw.cbn_w[l] = g->cbn_w[l]; gw.cbn_b[l] = g->cbn_b[l]; gw.clin_w[l] = g->clin_w[l]; gw.clin_b[l] = g->clin_b[l];
+        gw.w1[l] = g->w1[l]; gw.b1[l] = g->b1[l]; gw.w2[l] = g->w2[l]; gw.b2[l] = g->b2[l];
+        for (int q = 0; q < 3; ++q) gi.plane[l][q] = g->plane[3 * l + q];
+        gi.att[l] = g->att[l];
+    }
+    gw.app_vec = g->app_vec;
+    gi.anchor_feat = g->anchor_feat; gi.anchor = g->anchor; gi.offset = g->offset; gi.scaling = g->scaling;
+    const int KCH = 4096;
+
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(b.acc_begin, 0, b.acc_bytes, st));
+    dec_bwd_uncompact_kernel<<<ceil_div(V, 128), 128, 0, st>>>(V, LDX, DP, f.X, f.Z, f.maskbits, f.offs, d_xyz, d_color,
+                                                              d_opacity, d_scaling, d_rot, d_neural_opacity, b.DZ, b.DGA);
+    SPLATCO_CHECK_LAUNCH();
+    // dH = (dZ W2) * [H > 0];   gW2T += H^T dZ;   gb2 = colsum(dZ)
+    if (sgemm<false, true>(st, V, HD, ZD, b.DZ, ZD, f.W2T, ZD, b.DH, HD, nullptr, 0, f.H, HD)) return -2;
+    if (sgemm<true, false>(st, HD, ZD, V, f.H, HD, b.DZ, ZD, b.gW2T, ZD, nullptr, 0, nullptr, 0, KCH)) return -2;
+    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 1024);
+    SPLATCO_CHECK_LAUNCH();
+    // dX100 = dH W1;   gW1T += X100^T dH;   gb1 = colsum(dH)
+    if (sgemm<false, true>(st, V, XI, HD, b.DH, HD, f.W1T, HD, b.DX, XI)) return -2;
+    if (sgemm<true, false>(st, XI, HD, V, f.XIN, XI, b.DH, HD, b.gW1T, HD, nullptr, 0, nullptr, 0, KCH)) return -2;
+    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, HD, b.DH, HD, b.gb1, 1024);
+    SPLATCO_CHECK_LAUNCH();
+    // S1raw = dgeo^T X (both branches), S0 = colsum(dgeo)
+    if (sgemm<true, false>(st, 32, DP, V, b.DX + 36, XI, f.X, LDX, b.S1, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
+    if (sgemm<true, false>(st, 32, GD, V, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
+    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, 64, b.DX + 36, XI, b.S0, 1024);
+    SPLATCO_CHECK_LAUNCH();
+    dec_bwd_fold_kernel<<<1, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+                                           b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
+    SPLATCO_CHECK_LAUNCH();
+    // dxhat = dgeo (gamma W)  for both branches
+    if (sgemm<false, false>(st, V, DP, 32, b.DX + 36, XI, f.WpG, DP, b.DXH, LDX)) return -2;
+    if (sgemm<false, false>(st, V, GD, 32, b.DX + 68, XI, f.WcG, GD, b.DXH + DP, LDX)) return -2;
+    dec_bwd_inputs_kernel<<<gather_grid(V), GATHER_WARPS * 32, 0, st>>>(p, gi, V, dd.rc, DP, LDX, f.X, f.XIN, f.mu, f.rstd,
+                                                                        b.m1, b.m2, b.DXH, b.DX, b.DGA);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}

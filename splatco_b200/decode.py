@@ -1,0 +1,303 @@
+"""Fused anchor decode: host side of splatco_decode_* (include/splatco_b200.h).
+
+Mirrors the contract of the reference's `generate_neural_gaussians`
+(gaussian_renderer/__init__.py:18-116): same inputs read off the same `pc` attributes, same 7-tuple
+(train) / 5-tuple (eval) of outputs, gradients delivered to the same leaves through autograd.
+All arithmetic runs in libsplatco_b200.so; TriPlaneAttention over the whole planes (a dense conv
+pass, view-independent — SURVEY §8 row f2) is still evaluated by the module the model owns and its
+output planes are handed to the kernels, which return their gradients to autograd.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import check
+from .profiling import stage
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class DecodeDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("V", C.c_int32), ("K", C.c_int32), ("rc", C.c_int32), ("level", C.c_int32),
+        ("app_dim", C.c_int32),
+        ("E", C.c_int32 * 3), ("use_dist", C.c_int32 * 3), ("update_running", C.c_int32),
+        ("xyz_min", C.c_float * 3), ("xyz_max", C.c_float * 3), ("cam", C.c_float * 3),
+        ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
+        ("anchor_feat", _vp), ("anchor", _vp), ("offset", _vp), ("scaling", _vp), ("vis", _vp),
+        ("plane", _vp * 9), ("att", _vp * 3),
+        ("bn_w", _vp * 3), ("bn_b", _vp * 3), ("lin_w", _vp * 3), ("lin_b", _vp * 3),
+        ("cbn_w", _vp * 3), ("cbn_b", _vp * 3), ("clin_w", _vp * 3), ("clin_b", _vp * 3),
+        ("bn_rm", _vp * 3), ("bn_rv", _vp * 3), ("cbn_rm", _vp * 3), ("cbn_rv", _vp * 3),
+        ("bn_nbt", _vp * 3), ("cbn_nbt", _vp * 3),
+        ("w1", _vp * 3), ("b1", _vp * 3), ("w2", _vp * 3), ("b2", _vp * 3),
+        ("app_vec", _vp), ("noise", _vp),
+    ]
+
+
+class DecodeGrads(C.Structure):
+    _fields_ = [
+        ("anchor_feat", _vp), ("anchor", _vp), ("offset", _vp), ("scaling", _vp),
+        ("plane", _vp * 9), ("att", _vp * 3),
+        ("bn_w", _vp * 3), ("bn_b", _vp * 3), ("lin_w", _vp * 3), ("lin_b", _vp * 3),
+        ("cbn_w", _vp * 3), ("cbn_b", _vp * 3), ("clin_w", _vp * 3), ("clin_b", _vp * 3),
+        ("w1", _vp * 3), ("b1", _vp * 3), ("w2", _vp * 3), ("b2", _vp * 3),
+        ("app_vec", _vp),
+    ]
+
+
+_registered = False
+
+
+def _register():
+    return _lib.lib()       # signatures live in _lib.SIGNATURES
+
+
+_tls = threading.local()
+
+
+def _pinned_counter(dev):
+    cache = getattr(_tls, "c", None)
+    if cache is None:
+        cache = _tls.c = {}
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in cache:
+        cache[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return cache[key]
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _c(t):
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class DecodeConfig:
+    """Everything that is not a differentiable tensor input."""
+    __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise")
+
+
+# order of the differentiable parameter list handed to the autograd Function
+PER_LEVEL = ("xy", "xz", "yz", "bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b")
+PER_HEAD = ("w1", "b1", "w2", "b2")
+
+
+def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, app_vec, level_params, head_params):
+    d = DecodeDesc()
+    d.N, d.V, d.K, d.rc, d.level, d.app_dim = cfg.N, V, cfg.K, cfg.rc, cfg.level, cfg.app_dim
+    for q in range(3):
+        d.E[q] = cfg.E[q]
+        d.use_dist[q] = int(cfg.use_dist[q])
+        d.xyz_min[q], d.xyz_max[q], d.cam[q] = cfg.xyz_min[q], cfg.xyz_max[q], cfg.cam[q]
+    d.update_running = int(cfg.update_running)
+    d.bn_eps, d.bn_momentum = cfg.bn_eps, cfg.bn_momentum
+    d.anchor_feat, d.anchor, d.offset, d.scaling = (t.data_ptr() for t in (anchor_feat, anchor, offset, scaling))
+    d.vis = cfg.vis_idx.data_ptr()
+    for l, lp in enumerate(level_params):
+        d.plane[3 * l], d.plane[3 * l + 1], d.plane[3 * l + 2] = (lp[k].data_ptr() for k in ("xy", "xz", "yz"))
+        for k in ("bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b"):
+            getattr(d, k)[l] = lp[k].data_ptr()
+        bufs = cfg.buffers[l]
+        for k in ("bn_rm", "bn_rv", "cbn_rm", "cbn_rv", "bn_nbt", "cbn_nbt"):
+            getattr(d, k)[l] = bufs[k].data_ptr() if bufs.get(k) is not None else None
+    for q in range(3):
+        d.att[q] = att[q].data_ptr()
+    for h, hp in enumerate(head_params):
+        for k in PER_HEAD:
+            getattr(d, k)[h] = hp[k].data_ptr()
+    d.app_vec = app_vec.data_ptr() if app_vec is not None else None
+    d.noise = cfg.noise.data_ptr() if cfg.noise is not None else None
+    return d
+
+
+class _FusedDecode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg: DecodeConfig, anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz, app_vec,
+                *params):
+        L = _register()
+        dev = anchor.device
+        nl = cfg.level + 1
+        tensors = [_c(t) for t in (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz)]
+        anchor_feat_c, anchor_c, offset_c, scaling_c, a_xy, a_xz, a_yz = tensors
+        app_c = _c(app_vec) if app_vec is not None else None
+        pc = [_c(t) for t in params]
+        level_params = [dict(zip(PER_LEVEL, pc[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)])) for l in range(nl)]
+        base = nl * len(PER_LEVEL)
+        head_params = [dict(zip(PER_HEAD, pc[base + h * 4: base + h * 4 + 4])) for h in range(3)]
+        V = int(cfg.vis_idx.shape[0])
+        K = cfg.K
+        desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c,
+                          level_params, head_params)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            ws = torch.empty(max(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
+            nopac = torch.empty((V * K, 1), dtype=torch.float32, device=dev)
+            mask = torch.empty(V * K, dtype=torch.bool, device=dev)
+            counter = _pinned_counter(dev)
+            with stage("decode_fwd"):
+                check(L.splatco_decode_fwd(C.byref(desc), _p(ws), _p(nopac), _p(mask), counter.data_ptr(), stream),
+                      "splatco_decode_fwd")
+            torch.cuda.current_stream(dev).synchronize()      # M sizes the outputs (the reference syncs here too: boolean indexing)
+            M = int(counter.item()) if V > 0 else 0
+            xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
+            color = torch.empty((M, 3), dtype=torch.float32, device=dev)
+            opacity = torch.empty((M, 1), dtype=torch.float32, device=dev)
+            scl = torch.empty((M, 3), dtype=torch.float32, device=dev)
+            rot = torch.empty((M, 4), dtype=torch.float32, device=dev)
+            with stage("decode_emit"):
+                check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
+                                            stream), "splatco_decode_emit")
+        ctx.cfg, ctx.desc, ctx.ws, ctx.M, ctx.V = cfg, desc, ws, M, V
+        ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise)           # keeps every pointer in desc alive
+        ctx.shapes = [t.shape for t in (anchor_feat, anchor, offset, scaling)]
+        ctx.has_app = app_vec is not None
+        ctx.mark_non_differentiable(mask)
+        return xyz, color, opacity, scl, rot, nopac, mask
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_color, g_opacity, g_scl, g_rot, g_nopac, _g_mask):
+        L = _register()
+        cfg, desc, V, M = ctx.cfg, ctx.desc, ctx.V, ctx.M
+        tensors, app_c, pc = ctx.keep[:3]
+        dev = tensors[1].device
+        nl = cfg.level + 1
+        N, K = cfg.N, cfg.K
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g_feat, g_anchor, g_offset, g_scaling = z(N, 32), z(N, 3), z(N, K, 3), z(N, 6)
+        g_att = [torch.zeros_like(t) for t in tensors[4:7]]
+        g_params = []
+        for l in range(nl):
+            for k, t in zip(PER_LEVEL, pc[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)]):
+                g_params.append(torch.zeros_like(t) if k in ("xy", "xz", "yz") else torch.empty_like(t))
+        base = nl * len(PER_LEVEL)
+        for t in pc[base:]:
+            g_params.append(torch.empty_like(t))
+        g_app = torch.empty_like(app_c) if app_c is not None else None
+        gd = DecodeGrads()
+        gd.anchor_feat, gd.anchor, gd.offset, gd.scaling = (t.data_ptr() for t in (g_feat, g_anchor, g_offset, g_scaling))
+        for l in range(nl):
+            lp = dict(zip(PER_LEVEL, g_params[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)]))
+            gd.plane[3 * l], gd.plane[3 * l + 1], gd.plane[3 * l + 2] = (lp[k].data_ptr() for k in ("xy", "xz", "yz"))
+            for k in ("bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b"):
+                getattr(gd, k)[l] = lp[k].data_ptr()
+        for q in range(3):
+            gd.att[q] = g_att[q].data_ptr()
+        for h in range(3):
+            hp = dict(zip(PER_HEAD, g_params[base + h * 4: base + h * 4 + 4]))
+            for k in PER_HEAD:
+                getattr(gd, k)[h] = hp[k].data_ptr()
+        gd.app_vec = g_app.data_ptr() if g_app is not None else None
+        if V > 0:
+            ups = [_c(t) if t is not None else None for t in (g_xyz, g_color, g_opacity, g_scl, g_rot, g_nopac)]
+            if M > 0:
+                ups = [u if u is not None else z(*s) for u, s in zip(ups[:5], ((M, 3), (M, 3), (M, 1), (M, 3), (M, 4)))] + [ups[5]]
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            with torch.cuda.device(dev):
+                bws = torch.empty(max(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
+                with stage("decode_bwd"):
+                    check(L.splatco_decode_bwd(C.byref(desc), _p(ctx.ws), _p(bws), M, *[_p(u) for u in ups],
+                                               C.byref(gd), stream), "splatco_decode_bwd")
+        else:
+            for t in g_params:
+                t.zero_()
+            if g_app is not None:
+                g_app.zero_()
+        return (None, g_feat, g_anchor, g_offset, g_scaling, g_att[0], g_att[1], g_att[2],
+                g_app if ctx.has_app else None, *g_params)
+
+
+def _bn_lin(seq):
+    bn, lin = seq[0], seq[1]
+    return bn, lin
+
+
+def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
+    """Read the reference model's attributes (duck-typed GaussianModel) into
+    (cfg, differentiable inputs)."""
+    if getattr(pc, "use_feat_bank", False):
+        raise NotImplementedError(
+            "use_feat_bank is unusable in the reference itself (mlp_feature_bank is Linear(4, .) but is fed 68 "
+            "columns, scene/gaussian_model.py:307-313 vs gaussian_renderer/__init__.py:42-44)")
+    anchor = pc.get_anchor
+    dev = anchor.device
+    if not anchor.is_cuda:
+        raise RuntimeError("splatco_b200 decode needs CUDA tensors (no CPU fallback)")
+    fp = pc.feat_planes
+    feat = fp._feat
+    level = int(feat.activate_level)
+    k0s = feat.k0s
+    cfg = DecodeConfig()
+    cfg.N = int(anchor.shape[0])
+    cfg.K = int(pc.n_offsets)
+    cfg.level = level
+    cfg.rc = int(k0s[0].xy_plane.shape[1])
+    cfg.E = [int(k0s[min(l, len(k0s) - 1)].xy_plane.shape[2]) for l in range(3)]
+    for l in range(level + 1):
+        pl = k0s[l]
+        if not (pl.xy_plane.shape[2] == pl.xy_plane.shape[3] == pl.xz_plane.shape[3] == pl.yz_plane.shape[2]):
+            raise NotImplementedError("splatco_b200 decode supports cubic plane grids only (world_size = [s, s, s])")
+    cfg.use_dist = [bool(pc.add_opacity_dist), bool(pc.add_cov_dist), bool(pc.add_color_dist)]
+    cfg.app_dim = int(pc.appearance_dim) if pc.appearance_dim else 0
+    mn = k0s[0].xyz_min.detach().float().cpu().tolist()
+    mx = k0s[0].xyz_max.detach().float().cpu().tolist()
+    cfg.xyz_min, cfg.xyz_max = mn, mx
+    cfg.cam = viewpoint_camera.camera_center.detach().float().cpu().tolist()
+    bn0 = feat.models[0][0]
+    cfg.bn_eps, cfg.bn_momentum = float(bn0.eps), float(bn0.momentum if bn0.momentum is not None else 0.1)
+    cfg.update_running = bool(update_running)
+    if visible_mask is None:
+        cfg.vis_idx = torch.arange(cfg.N, dtype=torch.int32, device=dev)
+    else:
+        cfg.vis_idx = torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
+    cfg.buffers = []
+    params = []
+    for l in range(level + 1):
+        bn, lin = _bn_lin(feat.models[l])
+        cbn, clin = _bn_lin(feat.CTX_models[l])
+        pl = k0s[l]
+        params += [pl.xy_plane, pl.xz_plane, pl.yz_plane, bn.weight, bn.bias, lin.weight, lin.bias,
+                   cbn.weight, cbn.bias, clin.weight, clin.bias]
+        cfg.buffers.append(dict(bn_rm=bn.running_mean, bn_rv=bn.running_var, cbn_rm=cbn.running_mean,
+                                cbn_rv=cbn.running_var, bn_nbt=bn.num_batches_tracked,
+                                cbn_nbt=cbn.num_batches_tracked))
+    for mlp in (pc.get_opacity_mlp, pc.get_cov_mlp, pc.get_color_mlp):
+        params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
+    # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169), evaluated by the model's own module
+    pl0 = k0s[0]
+    with stage("triplane_attention_torch"):
+        ta = pl0.TA(torch.cat((pl0.xy_plane, pl0.xz_plane, pl0.yz_plane), dim=1))
+        att = torch.chunk(ta, 3, dim=1)
+    app_vec = None
+    if cfg.app_dim > 0:
+        app_vec = pc.get_appearance.embedding.weight[int(viewpoint_camera.uid)]
+    return cfg, att, app_vec, params
+
+
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False):
+    """Drop-in for gaussian_renderer.generate_neural_gaussians (reference :18-116)."""
+    cfg, att, app_vec, params = collect_model(pc, viewpoint_camera, visible_mask)
+    # GaussianLearner.inference always passes Q = self.Q0 (0.03 while training, 0 in render.py):
+    # U(-.5,.5)*Q is added to the plane features of the non-TA levels (scene/grids.py:159-164)
+    Q = float(getattr(pc.feat_planes, "Q0", 0.0) or 0.0)
+    cfg.noise = None
+    if Q != 0.0 and cfg.level >= 1:
+        ncol = cfg.rc * (3 if cfg.level == 1 else 6)
+        cfg.noise = torch.empty((int(cfg.vis_idx.shape[0]), ncol), dtype=torch.float32,
+                                device=cfg.vis_idx.device).uniform_(-0.5, 0.5).mul_(Q)
+    outs = _FusedDecode.apply(cfg, pc._anchor_feat, pc.get_anchor, pc._offset, pc.get_scaling, att[0], att[1], att[2],
+                              app_vec, *params)
+    xyz, color, opacity, scaling, rot, neural_opacity, mask = outs
+    if is_training:
+        return xyz, color, opacity, scaling, rot, neural_opacity, mask
+    return xyz, color, opacity, scaling, rot

@@ -1,0 +1,103 @@
+"""Drop-in for the reference's `gaussian_renderer` package (gaussian_renderer/__init__.py:1-244).
+
+Same public names, signatures, return dicts and error behaviour:
+    generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False)   (:18-116)
+    render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, visible_mask=None, retain_grad=False)  (:118-188)
+    prefilter_voxel(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None)          (:191-244)
+plus the `GaussianModel` re-export render.py relies on (:16, render.py:34) when the reference's
+`scene` package is importable.  Everything below these functions runs in libsplatco_b200.so.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ..decode import generate_neural_gaussians
+from ..diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+try:  # re-export, as the reference module does
+    from scene.gaussian_model import GaussianModel  # type: ignore  # noqa: F401
+except Exception:  # the reference tree is not on sys.path (tests, bench)
+    GaussianModel = None
+
+try:
+    from . import network_gui  # type: ignore  # noqa: F401   (train.py:18 imports it from here)
+except Exception:
+    network_gui = None
+
+
+def _settings(viewpoint_camera, pipe, bg_color, scaling_modifier):
+    tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
+    tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
+    return GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height),
+        image_width=int(viewpoint_camera.image_width),
+        tanfovx=tanfovx,
+        tanfovy=tanfovy,
+        bg=bg_color,
+        scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform,
+        sh_degree=1,
+        campos=viewpoint_camera.camera_center,
+        prefiltered=False,
+        debug=pipe.debug,
+    )
+
+
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, visible_mask=None,
+           retain_grad=False):
+    """Render the scene.  Background tensor (bg_color) must be on GPU!"""
+    is_training = pc.get_color_mlp.training
+    if is_training:
+        xyz, color, opacity, scaling, rot, neural_opacity, mask = generate_neural_gaussians(
+            viewpoint_camera, pc, visible_mask, is_training=is_training)
+    else:
+        xyz, color, opacity, scaling, rot = generate_neural_gaussians(
+            viewpoint_camera, pc, visible_mask, is_training=is_training)
+
+    # zero tensor whose .grad receives the 2D (screen-space) mean gradients (reference :133-138)
+    screenspace_points = torch.zeros_like(xyz, dtype=pc.get_anchor.dtype, requires_grad=True, device="cuda") + 0
+    if retain_grad:
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+
+    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    rendered_image, radii = rasterizer(
+        means3D=xyz,
+        means2D=screenspace_points,
+        shs=None,
+        colors_precomp=color,
+        opacities=opacity,
+        scales=scaling,
+        rotations=rot,
+        cov3D_precomp=None)
+
+    out = {"render": rendered_image,
+           "viewspace_points": screenspace_points,
+           "visibility_filter": radii > 0,
+           "radii": radii}
+    if is_training:
+        out.update({"selection_mask": mask, "neural_opacity": neural_opacity, "scaling": scaling})
+    return out
+
+
+def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+    """Anchor-level frustum/size prefilter: bool[N] (reference :191-244)."""
+    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    means3D = pc.get_anchor
+    scales = None
+    rotations = None
+    cov3D_precomp = None
+    if pipe.compute_cov3D_python:
+        # the reference's branch is broken here (scales stays None and is then sliced, :233-240)
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales = pc.get_scaling
+        rotations = pc.get_rotation
+    radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales[:, :3], rotations=rotations,
+                                           cov3D_precomp=cov3D_precomp)
+    return radii_pure > 0
