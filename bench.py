@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — fwd+bwd ms/view of SplatCo's differentiable render hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
 
 A "step" is one training iteration's render work for the `--mv` multi-view batch (BASELINE.json
-configs[1]: Tanks&Temples-shaped, ~1M Gaussians, 980x545, mv=4): for every view, forward
-(prefilter -> decode -> preprocess -> binning/sort -> blend), L1 loss gradient, backward.  Views
-are sharded across ranks when N > 1 (weak scaling: every rank renders its own mv views; per-Gaussian
-gradients are all-reduced with NCCL after the local backward).
+configs[1]: Tanks&Temples-shaped, 100k anchors x 10 offsets ~ 1M candidate Gaussians, 980x545, mv=4):
+for every view   prefilter_voxel -> generate_neural_gaussians (fused decode) -> preprocess ->
+binning/sort -> blend,   the reference's per-view loss terms that touch the hot path's outputs
+(L1 + 0.01*mean(prod(scaling)), train.py:192-196; SSIM is SURVEY §8 row f3, not timed),   then ONE
+backward over the summed loss (train.py:240), through the drop-in `gaussian_renderer.render()`.
+With N > 1 every rank renders its own mv views (weak scaling, views sharded by rank) and the
+parameter gradients are all-reduced with NCCL.
 
 Printed JSON (one line, rank 0): metric fwd_bwd_ms_per_view (lower is better) = max-over-ranks step
-time / views rendered by all ranks; `e2e` = the same through the public API with host inputs (pinned
-ground-truth images copied H2D every view, loss read back D2H every step); `roofline` for the
-dominant kernel; `cpu_baseline` = the oracle port on the host cores over one view.
+time / views rendered by all ranks, inputs resident in HBM; `e2e` = the same with host inputs (each
+view's ground-truth image copied H2D from pinned memory, the loss read back D2H every step);
+`roofline` for the stage with the largest share; `cpu_baseline` = the oracle port on the host cores
+over one view.
 
-`--impl reference` times the reference's own CPU implementation of the path: the reference rasterizer
-is CUDA-only and absent and its Python decode cannot travel to the GPU box, so this
-arm runs the oracle port (oracle/) on all host threads, one view per step.
+`--impl reference`: the reference's rasterizer is CUDA-only and absent from the mount and its Python
+decode cannot travel to the GPU box, so this arm times the oracle port of the
+same path (oracle/decode_oracle.py on torch CPU threads + oracle/raster_oracle.c on all host
+threads), one view of the workload per step.
 """
 from __future__ import annotations
 
@@ -28,6 +33,7 @@ import subprocess
 import sys
 import tempfile
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -37,38 +43,39 @@ import numpy as np
 import torch
 
 WORKLOADS = {
-    # name: (anchors N, K, W, H, mv)
-    "c1": dict(N=10_000, K=10, W=256, H=256, mv=1, desc="C1 synthetic 10k anchors x10, 256x256, 1 view"),
-    "c2": dict(N=100_000, K=10, W=980, H=545, mv=4, desc="C2 Tanks&Temples-shaped ~1M Gaussians, 980x545, mv=4"),
-    "c3": dict(N=500_000, K=10, W=1152, H=864, mv=4, desc="C3 Mill19-Rubble-shaped ~5M Gaussians, 1152x864, mv=4"),
+    "c1": dict(N=10_000, K=10, W=256, H=256, mv=1, plane_size=512, C=15,
+               desc="C1 synthetic 10k anchors x10 offsets, 256x256, 1 view"),
+    "c2": dict(N=100_000, K=10, W=980, H=545, mv=4, plane_size=2500, C=15,
+               desc="C2 Tanks&Temples-shaped 100k anchors x10 offsets (~1M Gaussians), 980x545, mv=4"),
+    "c3": dict(N=500_000, K=10, W=1152, H=864, mv=4, plane_size=2800, C=15,
+               desc="C3 Mill19-Rubble-shaped 500k anchors x10 (~5M Gaussians), 1152x864, plane_size 2800, mv=4"),
 }
+SCALE_FACTOR = 0.5       # anchor scale = 0.5 / N^(1/3): projected sigma ~0.5-4 px at these resolutions
+LEVEL = 2                # activate_level in steady state (train.py:305-307)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.path = None
+        self.index, self.proc, self.path = index, None, None
 
     def start(self):
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -76,6 +83,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -83,58 +91,47 @@ class ClockSampler:
             self.proc.kill()
         try:
             rows = [r.split(",") for r in open(self.path).read().strip().splitlines() if r.strip()]
-            sm = [float(r[1]) for r in rows if len(r) >= 9]
-            if sm:
-                out["sm_mhz"] = float(np.median(sm))
+            rows = [r for r in rows if len(r) >= 9]
+            if rows:
+                out["sm_mhz"] = float(np.median([float(r[1]) for r in rows]))
                 out["sm_max_mhz"] = float(rows[0][2])
-                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-                for k, n in enumerate(names):
-                    if any("Active" == r[5 + k].strip() for r in rows if len(r) >= 9):
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                for k, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                    if any(r[5 + k].strip() == "Active" for r in rows):
                         out["reasons"].append(n)
-                out["samples"] = len(sm)
+                out["samples"] = len(rows)
             os.unlink(self.path)
         except Exception:
             pass
         return out
 
 
-def build_scene(cfg, seed, device):
-    """Synthetic Gaussians of the workload's shape.  Until the fused decode is wired in, the cloud is
-    the decode's *output* shape: anchors U([-1,1]^3), K offsets each, ~55 % kept (opacity mask)."""
+def build_model(cfg, device, seed=1):
+    from splatco_b200.model import AnchorModel
+    pc = AnchorModel(cfg["N"], n_offsets=cfg["K"], plane_size=cfg["plane_size"], num_channels=cfg["C"],
+                     device=device, seed=20240 + seed, scale_factor=SCALE_FACTOR)
+    pc.feat_planes._feat.activate_level = LEVEL
+    pc.train()
+    return pc
+
+
+def build_views(cfg, rank=0, world=1, seed=1):
     from splatco_b200.synthetic import ring_cameras
-    g = torch.Generator().manual_seed(20240 + seed)
-    N, K = cfg["N"], cfg["K"]
-    anchors = torch.rand(N, 3, generator=g) * 2 - 1
-    s0 = 2.0 / N ** (1.0 / 3.0)
-    ascale = s0 * torch.exp(torch.randn(N, 6, generator=g) * 0.3)
-    offs = torch.randn(N, K, 3, generator=g) * 0.5
-    keep = torch.rand(N * K, generator=g) < 0.55
-    xyz = (anchors[:, None, :] + offs * ascale[:, None, :3]).reshape(-1, 3)[keep]
-    M = xyz.shape[0]
-    scales = (ascale[:, None, 3:].expand(N, K, 3).reshape(-1, 3)[keep] * torch.sigmoid(torch.randn(M, 3, generator=g))) * 0.5
-    q = torch.randn(M, 4, generator=g)
-    rots = q / q.norm(dim=1, keepdim=True)
-    opac = torch.empty(M, 1).uniform_(0.02, 0.95, generator=g)
-    colors = torch.rand(M, 3, generator=g)
-    cams = ring_cameras(cfg["mv"], cfg["W"], cfg["H"])
+    phase = 2 * math.pi * rank / (world * cfg["mv"]) if world > 1 else 0.0
+    cams = ring_cameras(cfg["mv"], cfg["W"], cfg["H"], phase=phase)
+    g = torch.Generator().manual_seed(777 + seed + rank)
     gts = [torch.rand(3, cfg["H"], cfg["W"], generator=g) for _ in cams]
-    t = dict(xyz=xyz, colors=colors, opac=opac, scales=scales.contiguous(), rots=rots)
-    return {k: v.to(device) for k, v in t.items()}, cams, gts
+    return cams, gts
 
 
-def make_settings(cam, bg, device):
-    from splatco_b200.diff_gaussian_rasterization import GaussianRasterizationSettings
-    return GaussianRasterizationSettings(
-        image_height=cam.image_height, image_width=cam.image_width, tanfovx=math.tan(cam.FoVx * 0.5),
-        tanfovy=math.tan(cam.FoVy * 0.5), bg=bg, scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(device),
-        projmatrix=cam.full_proj_transform.to(device), sh_degree=1, campos=cam.camera_center.to(device),
-        prefiltered=False, debug=False)
+PIPE = SimpleNamespace(debug=False, compute_cov3D_python=False, convert_SHs_python=False)
 
 
 def run_ours(args):
     import torch.distributed as dist
     from splatco_b200 import _lib, profiling
-    from splatco_b200.diff_gaussian_rasterization import GaussianRasterizer
+    from splatco_b200.gaussian_renderer import prefilter_voxel, render
+    from splatco_b200.multiview import GradBucket
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -145,37 +142,35 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     cfg = WORKLOADS[args.workload]
     L = _lib.lib()
-    params, cams, gts = build_scene(cfg, seed=1, device=device)
-    # each rank renders its own mv views (weak scaling): rotate the camera ring per rank
-    if world > 1:
-        from splatco_b200.synthetic import ring_cameras
-        cams = ring_cameras(cfg["mv"], cfg["W"], cfg["H"], phase=2 * math.pi * rank / (world * cfg["mv"]))
+    pc = build_model(cfg, device)
+    pc.feat_planes.Q0 = 0.03                       # training-time plane-feature noise (timing config)
+    cams, gts = build_views(cfg, rank, world)
+    cams = [c.to(device) for c in cams]
     bg = torch.ones(3, device=device)
-    leaves = {k: params[k].clone().requires_grad_() for k in ("xyz", "colors", "opac", "scales", "rots")}
-    rasts = [GaussianRasterizer(make_settings(c, bg, device)) for c in cams]
     gts_dev = [g.to(device) for g in gts]
     gts_pinned = [g.pin_memory() for g in gts]
+    params = pc.parameters()
+    bucket = GradBucket(params) if world > 1 else None
     H, W, mv = cfg["H"], cfg["W"], cfg["mv"]
-    M = leaves["xyz"].shape[0]
-    flat_grads = None
+    info = {}
 
     def step(host_inputs: bool):
-        total = None
-        for p in leaves.values():
+        for p in params:
             p.grad = None
+        total = None
+        Ms, Vs = [], []
         for v in range(mv):
             gt = gts_pinned[v].to(device, non_blocking=True) if host_inputs else gts_dev[v]
-            m2d = torch.zeros_like(leaves["xyz"], requires_grad=True)
-            img, radii = rasts[v](means3D=leaves["xyz"], means2D=m2d, shs=None, colors_precomp=leaves["colors"],
-                                  opacities=leaves["opac"], scales=leaves["scales"], rotations=leaves["rots"],
-                                  cov3D_precomp=None)
-            loss = (img - gt).abs().mean()
+            vm = prefilter_voxel(cams[v], pc, PIPE, bg)
+            pkg = render(cams[v], pc, PIPE, bg, visible_mask=vm, retain_grad=True)
+            loss = (pkg["render"] - gt).abs().mean() + 0.01 * pkg["scaling"].prod(dim=1).mean()
             total = loss if total is None else total + loss
+            Ms.append(pkg["radii"].shape[0]); Vs.append(pkg["selection_mask"].shape[0] // cfg["K"])
         total.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in leaves.values()])
-            dist.all_reduce(flat)
-        return total.item() if host_inputs else total
+        if bucket is not None:
+            bucket.allreduce()
+        info["M"], info["V"] = float(np.mean(Ms)), float(np.mean(Vs))
+        return float(total.item()) if host_inputs else total
 
     def timed(n, host_inputs):
         if world > 1:
@@ -187,6 +182,8 @@ def run_ours(args):
             step(host_inputs)
         e1.record()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms], device=device)
@@ -194,7 +191,8 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step(False)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -202,129 +200,166 @@ def run_ours(args):
     launches0 = L.splatco_launch_count()
     with profiling.collect() as prof:
         ms_dev = timed(args.steps, host_inputs=False)
-    launches = (L.splatco_launch_count() - launches0)
+    launches = L.splatco_launch_count() - launches0
     stage_sum = prof.summary()
     ms_e2e = timed(args.steps, host_inputs=True)
     clocks = sampler.stop() if rank == 0 else None
 
     views = mv * world
     ms_step = ms_dev / args.steps
-    value = ms_step / views
-    e2e_value = (ms_e2e / args.steps) / views
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # roofline of the dominant kernel (algorithmic bytes per launch / mean launch time)
+    # instance count R of each view (for the algorithmic-byte roofline figures)
+    from splatco_b200.diff_gaussian_rasterization import rasterize_forward_state
+    from splatco_b200.gaussian_renderer import _settings, generate_neural_gaussians
+    R_list = []
     with torch.no_grad():
-        R_list = []
-        from splatco_b200.diff_gaussian_rasterization import rasterize_forward_state
         for v in range(mv):
-            _, _, st = rasterize_forward_state(leaves["xyz"], leaves["colors"], leaves["opac"], leaves["scales"],
-                                               leaves["rots"], rasts[v].raster_settings)
+            vm = prefilter_voxel(cams[v], pc, PIPE, bg)
+            xyz, color, opacity, scaling, rot, _, _ = generate_neural_gaussians(cams[v], pc, vm, is_training=True)
+            _, _, st = rasterize_forward_state(xyz, color, opacity, scaling, rot, _settings(cams[v], PIPE, bg, 1.0))
             R_list.append(st.R)
-    R_mean = float(np.mean(R_list))
+    R, M, V, N = float(np.mean(R_list)), info["M"], info["V"], cfg["N"]
     HW = H * W
     T = ((W + 15) // 16) * ((H + 15) // 16)
     passes = math.ceil((32 + max(1, (T - 1).bit_length())) / 8)
-    alg_bytes = {
+    dec_bytes = V * (284 + 240 * (LEVEL + 2) + 50) + 56 * M          # SURVEY §8d decode fwd per visible anchor
+    alg_bytes = {                                                      # SURVEY §8d / BASELINE.md §3.4
+        "visible_filter": 48.0 * N,
+        "decode_fwd": dec_bytes, "decode_emit": 56.0 * M, "decode_bwd": 2.0 * dec_bytes,
         "preprocess_fwd": 104.0 * M,
-        "binning": 12.0 * R_mean + passes * 24.0 * R_mean + 8.0 * R_mean + 8.0 * R_mean + 8.0 * T,
-        "blend_fwd": 40.0 * R_mean + 20.0 * HW,
-        "blend_bwd": 76.0 * R_mean + 32.0 * HW,
+        "binning": 12.0 * R + passes * 24.0 * R + 8.0 * R + 8.0 * R + 8.0 * T,
+        "blend_fwd": 40.0 * R + 20.0 * HW,
+        "blend_bwd": 76.0 * R + 32.0 * HW,
         "preprocess_bwd": 200.0 * M,
     }
     peak, peak_src = peaks()
     stages = {}
     for k, (n, tot) in stage_sum.items():
         avg = tot / max(n, 1)
-        stages[k] = {"calls": n, "avg_ms": round(avg, 4), "share": round(tot / ms_dev, 4),
-                     "alg_gbs": round(alg_bytes.get(k, 0.0) / (avg * 1e-3) / 1e9, 1) if avg > 0 else None}
-    dom = max(stage_sum.items(), key=lambda kv: kv[1][1])[0] if stage_sum else None
+        st = {"calls": n, "avg_ms": round(avg, 4), "share": round(tot / ms_dev, 4)}
+        if k in alg_bytes and avg > 0:
+            st["alg_gbs"] = round(alg_bytes[k] / (avg * 1e-3) / 1e9, 1)
+        stages[k] = st
+    timed_k = [k for k in stage_sum if k in alg_bytes]
+    dom = max(timed_k, key=lambda k: stage_sum[k][1]) if timed_k else None
     roof = None
     if dom:
         a = stages[dom]["alg_gbs"]
         roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
                 "frac": round(a / peak, 4), "peak_source": peak_src, "traffic": None,
-                "pairs_per_s": None}
+                "alg_bytes_per_launch": int(alg_bytes[dom])}
+        if dom.startswith("blend"):
+            # the blend is FP32-issue bound, not HBM bound: also report (pixel, splat) pairs/s
+            roof["pairs_per_s"] = round(R * 256 / (stages[dom]["avg_ms"] * 1e-3), 1)
     out = {
-        "metric": "fwd_bwd_ms_per_view", "value": round(value, 4), "unit": "ms/view", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
-        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["desc"], "path": "rasterizer (preprocess+binning+blend fwd/bwd); decode pending",
-                   "gaussians": int(M), "instances_R": int(R_mean), "mv": mv, "views_per_step": views,
-                   "loss": "L1 (torch elementwise)", "l2": "inputs > L2 not guaranteed; L2 not flushed between views",
-                   "parallelism": f"view-sharded dp{world}"},
+        "metric": "fwd_bwd_ms_per_view", "value": round(ms_step / views, 4), "unit": "ms/view", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_step, 4), "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["desc"], "path": "prefilter_voxel + render() drop-in: decode, preprocess, binning, blend, fwd+bwd",
+                   "anchors": N, "visible_anchors": int(V), "gaussians": int(M), "instances_R": int(R),
+                   "activate_level": LEVEL, "plane_size": cfg["plane_size"], "num_channels": cfg["C"], "Q0": 0.03,
+                   "mv": mv, "views_per_step": views, "loss": "L1 + 0.01*mean(prod(scaling)) (torch elementwise)",
+                   "l2": "per-step working set (planes + workspaces) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"view-sharded dp{world}, NCCL grad all-reduce" if world > 1 else "single GPU"},
         "it_per_s": round(1000.0 / ms_step, 3),
-        "e2e": {"value": round(e2e_value, 4), "unit": "ms/view", "h2d_bytes_per_step": int(mv * 3 * HW * 4),
-                "d2h_bytes_per_step": 4 + 4 * mv},
+        "e2e": {"value": round((ms_e2e / args.steps) / views, 4), "unit": "ms/view",
+                "h2d_bytes_per_step": int(mv * 3 * HW * 4), "d2h_bytes_per_step": 4 + 8 * mv},
         "gpu_launches": int(launches),
         "roofline": roof, "stages": stages, "clocks": clocks,
     }
+    if bucket is not None:
+        out["config"]["allreduce_bytes_per_step"] = bucket.nbytes()
     if world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(cfg, params, cams, gts, views=1)
+        out["cpu_baseline"] = cpu_baseline(cfg)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_view(params_np, cam, gt, bg):
-    """One view, forward + backward, on the CPU oracle (all host threads)."""
-    from oracle import raster as R
-    tx, ty = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
-    H, W = cam.image_height, cam.image_width
-    view, proj = cam.world_view_transform.numpy(), cam.full_proj_transform.numpy()
-    fw = R.rasterize_forward(params_np["xyz"], params_np["colors"], params_np["opac"], params_np["scales"],
-                             params_np["rots"], 1.0, view, proj, tx, ty, H, W, bg)
-    dL = (np.sign(fw["image"] - gt) / (3.0 * H * W)).astype(np.float32)
-    R.rasterize_backward(fw, params_np["xyz"], params_np["colors"], params_np["scales"], params_np["rots"], 1.0,
-                         view, proj, tx, ty, H, W, bg, dL)
-    return fw["bn"].R
+# ---- CPU oracle port (cpu_baseline leg and --impl reference) -------------------------------------------
+class _CpuScene:
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.pc = build_model(cfg, "cpu")
+        self.pc.feat_planes.Q0 = 0.0
+        self.cams, self.gts = build_views(cfg)
+        self.p = {"feat." + k: v for k, v in self.pc.feat_planes._feat.state_dict().items()}
+        for name in ("mlp_opacity", "mlp_cov", "mlp_color"):
+            self.p.update({f"{name}.{k}": v for k, v in getattr(self.pc, name).state_dict().items()})
+        for k, v in self.p.items():
+            if v.dtype.is_floating_point and "running" not in k and "xyz_m" not in k:
+                v.requires_grad_(True)
+
+    def view(self, i):
+        """prefilter + decode + rasterize forward, L1 gradient, rasterize + decode backward; returns seconds."""
+        from oracle import decode_oracle as D
+        from oracle import raster as R
+        cfg, pc = self.cfg, self.pc
+        cam, gt = self.cams[i % len(self.cams)], self.gts[i % len(self.gts)].numpy()
+        H, W = cfg["H"], cfg["W"]
+        tx, ty = math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5)
+        view, proj = cam.world_view_transform.numpy(), cam.full_proj_transform.numpy()
+        bg = np.ones(3, np.float32)
+        t0 = time.perf_counter()
+        scaling = torch.exp(pc._scaling)
+        radii = R.visible_filter(pc._anchor.detach().numpy(), scaling.detach().numpy()[:, :3],
+                                 torch.nn.functional.normalize(pc._rotation).numpy(), 1.0, view, proj, tx, ty, H, W)
+        vis = torch.from_numpy(radii > 0)
+        xyz, color, opacity, scl, rot, _, _ = D.decode(self.p, pc._anchor_feat, pc._anchor, pc._offset, scaling, vis,
+                                                       cam.camera_center, LEVEL, cfg["K"])
+        a = [t.detach().numpy() for t in (xyz, color, opacity, scl, rot)]
+        fw = R.rasterize_forward(a[0], a[1], a[2], a[3], a[4], 1.0, view, proj, tx, ty, H, W, bg)
+        dL = (np.sign(fw["image"] - gt) / (3.0 * H * W)).astype(np.float32)
+        g = R.rasterize_backward(fw, a[0], a[1], a[3], a[4], 1.0, view, proj, tx, ty, H, W, bg, dL)
+        outs = [xyz, color, opacity, scl, rot]
+        grads = [torch.from_numpy(g[k]) for k in ("means3D", "colors", "opacities", "scales", "rotations")]
+        torch.autograd.backward(outs, grads)
+        for t in [pc._anchor_feat, pc._anchor, pc._offset, pc._scaling] + list(self.p.values()):
+            t.grad = None
+        return time.perf_counter() - t0
 
 
-def cpu_baseline(cfg, params, cams, gts, views=1):
+def cpu_baseline(cfg):
     from oracle import raster as R
-    pn = {k: v.detach().cpu().numpy() for k, v in params.items()}
-    bg = np.ones(3, np.float32)
-    t0 = time.perf_counter()
-    for v in range(views):
-        cpu_view(pn, cams[v], gts[v].numpy(), bg)
-    dt = (time.perf_counter() - t0) / views
+    torch.set_num_threads(os.cpu_count() or 1)
+    sc = _CpuScene(cfg)
+    dt = sc.view(0)
     return {"value": round(dt * 1e3, 2), "unit": "ms/view", "cores": int(R.lib().oracle_get_threads()),
-            "kind": "port", "sample": f"{views} view(s) of the same workload, fwd+bwd, oracle/raster_oracle.c on all host threads"}
+            "kind": "port", "sample": "1 view of the same workload, fwd+bwd: oracle/decode_oracle.py (torch CPU, "
+                                      "autograd) + oracle/raster_oracle.c on all host threads"}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation of the path = the oracle port (see module doc)."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """Reference arm = the oracle port of the path on the host cores (see module doc)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import raster as R
+    torch.set_num_threads(os.cpu_count() or 1)
     cfg = WORKLOADS[args.workload]
-    params, cams, gts = build_scene(cfg, seed=1, device="cpu")
-    pn = {k: v.numpy() for k, v in params.items()}
-    bg = np.ones(3, np.float32)
-    budget_s = 240.0
-    t_start = time.perf_counter()
-    for i in range(min(args.warmup, 1)):
-        cpu_view(pn, cams[0], gts[0].numpy(), bg)
+    sc = _CpuScene(cfg)
+    budget_s, t_start = 240.0, time.perf_counter()
+    nwarm = min(args.warmup, 1)
+    for i in range(nwarm):
+        sc.view(i)
     times = []
     for i in range(args.steps):
-        t0 = time.perf_counter()
-        cpu_view(pn, cams[i % len(cams)], gts[i % len(cams)].numpy(), bg)
-        times.append(time.perf_counter() - t0)
+        times.append(sc.view(i))
         if time.perf_counter() - t_start > budget_s:
             break
     ms = float(np.mean(times)) * 1e3
     cores = int(R.lib().oracle_get_threads())
     out = {"impl": "reference", "metric": "fwd_bwd_ms_per_view", "value": round(ms, 2), "unit": "ms/view",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(times), "warmup": min(args.warmup, 1),
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(times), "warmup": nwarm,
            "ms_per_step": round(ms, 2), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": cfg["desc"], "path": "rasterizer (preprocess+binning+blend fwd/bwd); decode pending",
-                      "gaussians": int(pn["xyz"].shape[0]), "mv": cfg["mv"]},
+           "config": {"workload": cfg["desc"], "path": "oracle port: prefilter + decode + rasterize, fwd+bwd, one view per step",
+                      "anchors": cfg["N"], "mv": cfg["mv"], "activate_level": LEVEL},
            "cpu_baseline": {"value": round(ms, 2), "unit": "ms/view", "cores": cores, "kind": "port",
-                            "sample": "one view of the workload per step, fwd+bwd, oracle port on all host threads"},
+                            "sample": "one view of the workload per step (the reference's CUDA rasterizer is absent and "
+                                      "has no CPU path; its Python decode cannot travel): oracle port on all host threads"},
            "e2e": {"value": round(ms, 2), "unit": "ms/view", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 

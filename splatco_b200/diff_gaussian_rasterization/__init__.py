@@ -256,7 +256,7 @@ class GaussianRasterizer(nn.Module):
             rotations = _f32c(rotations.detach())
             scales, sstride = _rows_f32(scales.detach(), 3)
             view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
-            with torch.cuda.device(dev):
+            with torch.cuda.device(dev), stage("visible_filter"):
                 check(L.splatco_visible_filter(N, ptr(means3D), ptr(scales), sstride, ptr(rotations),
                                                float(rs.scale_modifier), ptr(view), ptr(proj), float(rs.tanfovx),
                                                float(rs.tanfovy), int(rs.image_height), int(rs.image_width),

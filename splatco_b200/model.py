@@ -110,7 +110,7 @@ class AnchorModel:
 
     def __init__(self, N, n_offsets=10, feat_dim=32, plane_size=256, num_channels=15, appearance_dim=0,
                  num_cameras=1, add_opacity_dist=False, add_cov_dist=False, add_color_dist=False,
-                 device="cuda", seed=0):
+                 device="cuda", seed=0, scale_factor=2.0):
         g = torch.Generator().manual_seed(seed)
         with torch.random.fork_rng(devices=[]):
             torch.manual_seed(seed)
@@ -134,7 +134,7 @@ class AnchorModel:
                 emb.embedding = nn.Embedding(num_cameras, appearance_dim)
                 self.embedding_appearance = emb
         anchor = torch.rand(N, 3, generator=g) * 2 - 1
-        s0 = 2.0 / max(N, 1) ** (1.0 / 3.0)
+        s0 = scale_factor / max(N, 1) ** (1.0 / 3.0)     # scale_factor 2.0 = mean anchor spacing
         self._anchor = nn.Parameter(anchor.to(device))
         self._offset = nn.Parameter((torch.randn(N, n_offsets, 3, generator=g) * 0.5).to(device))
         self._anchor_feat = nn.Parameter((torch.randn(N, feat_dim, generator=g) * 0.3).to(device))
