@@ -222,6 +222,61 @@ def _bn_lin(seq):
     return bn, lin
 
 
+def triplane_attention(x, w_ca1, w_ca2, w_sa):
+    """TriPlaneAttention.forward (scene/grids.py:22-64) evaluated from the module's weights with plain
+    reductions: the module's AdaptiveAvg/MaxPool2d(1) run one thread per channel over the whole plane
+    (14 ms at plane_size 2500), `mean`/`amax` over (H, W) compute the same numbers in microseconds."""
+    avg = x.mean(dim=(2, 3), keepdim=True)
+    mx = x.amax(dim=(2, 3), keepdim=True)
+    F = torch.nn.functional
+    ca = torch.sigmoid(F.conv2d(F.relu(F.conv2d(avg, w_ca1)), w_ca2) + F.conv2d(F.relu(F.conv2d(mx, w_ca1)), w_ca2))
+    x = ca * x
+    s = torch.cat([x.mean(dim=1, keepdim=True), x.amax(dim=1, keepdim=True)], dim=1)
+    sa = torch.sigmoid(F.conv2d(s, w_sa, padding=w_sa.shape[-1] // 2))
+    return sa * x
+
+
+class _TACache:
+    """TriPlaneAttention is view-independent (it only reads the level-0 planes and its own weights) but
+    the reference recomputes it for every view.  Its output is cached here and
+    re-used by all views of an iteration: autograd then sums the views' gradients into the ONE cached
+    node and runs the attention backward once.  The entry is dropped when any input tensor is modified
+    in place (optimizer.step bumps `_version`), replaced (densification swaps Parameters), when the grad
+    mode changes, or as soon as a backward pass has flowed through it (the graph is gone after that)."""
+
+    def __init__(self):
+        self.key = None
+        self.value = None
+
+    def get(self, planes, weights):
+        ts = list(planes) + list(weights)
+        key = (torch.is_grad_enabled(),) + tuple((id(t), t._version, t.data_ptr(), tuple(t.shape)) for t in ts)
+        if self.key == key and self.value is not None:
+            return self.value
+        ta = triplane_attention(torch.cat(planes, dim=1), *weights)
+        att = tuple(t.contiguous() for t in torch.chunk(ta, 3, dim=1))
+        if ta.requires_grad:
+            ta.register_hook(self._invalidate)
+        self.key, self.value = key, att
+        return att
+
+    def _invalidate(self, grad):
+        self.key, self.value = None, None
+        return grad
+
+
+_ta_caches = {}
+
+
+def _ta_cache_for(owner) -> _TACache:
+    c = _ta_caches.get(id(owner))
+    if c is None:
+        if len(_ta_caches) > 8:
+            _ta_caches.clear()
+        c = _ta_caches[id(owner)] = _TACache()
+    return c
+
+
 def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     """Read the reference model's attributes (duck-typed GaussianModel) into
     (cfg, differentiable inputs)."""
@@ -276,8 +331,9 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169), evaluated by the model's own module
     pl0 = k0s[0]
     with stage("triplane_attention_torch"):
-        ta = pl0.TA(torch.cat((pl0.xy_plane, pl0.xz_plane, pl0.yz_plane), dim=1))
-        att = torch.chunk(ta, 3, dim=1)
+        att = _ta_cache_for(pl0).get((pl0.xy_plane, pl0.xz_plane, pl0.yz_plane),
+                                     (pl0.TA.ca.sharedMLP[0].weight, pl0.TA.ca.sharedMLP[2].weight,
+                                      pl0.TA.sa.conv.weight))
     app_vec = None
     if cfg.app_dim > 0:
         app_vec = pc.get_appearance.embedding.weight[int(viewpoint_camera.uid)]
