@@ -443,42 +443,42 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
 // =======================================================================================================
 // Head activations, opacity mask, per-anchor survivor counts (first scan level)
 // =======================================================================================================
+// One thread per Z element (coalesced); a CTA covers 32 rows.  block_sums (one per 256 rows, pre-zeroed)
+// receives the survivor counts for the scan.
+constexpr int ACT_ROWS = 32;
 __global__ void __launch_bounds__(256)
 dec_heads_act_kernel(int V, float *__restrict__ Z, float *__restrict__ neural_opacity, uint8_t *__restrict__ mask_out,
                      uint32_t *__restrict__ maskbits, uint32_t *__restrict__ block_sums) {
-    __shared__ uint32_t s_warp[8];
-    const int v = blockIdx.x * 256 + threadIdx.x;
-    uint32_t cnt = 0;
-    if (v < V) {
-        float *z = Z + (size_t)v * ZD;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int k = 0; k < KO; ++k) {
-            const float t = tanhf(z[k]);
-            z[k] = t;
-            neural_opacity[(size_t)v * KO + k] = t;
-            const bool m = t > 0.f;
-            mask_out[(size_t)v * KO + k] = m ? 1 : 0;
-            bits |= m ? (1u << k) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 3 * KO; ++j) {
-            const float x = z[8 * KO + j];
-            z[8 * KO + j] = 1.f / (1.f + expf(-x));
-        }
-        maskbits[v] = bits;
-        cnt = __popc(bits);
-    }
-    uint32_t s = cnt;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = s;
+    __shared__ uint32_t s_bits[ACT_ROWS];
+    if (threadIdx.x < ACT_ROWS) s_bits[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
+    const int row0 = blockIdx.x * ACT_ROWS;
+    const int nrows = min(ACT_ROWS, V - row0);
+    float *zb = Z + (size_t)row0 * ZD;
+    for (int e = threadIdx.x; e < nrows * ZD; e += 256) {
+        const int r = e / ZD, j = e - r * ZD;
+        const float x = zb[e];
+        if (j < KO) {
+            const float t = tanhf(x);
+            zb[e] = t;
+            const size_t o = (size_t)(row0 + r) * KO + j;
+            neural_opacity[o] = t;
+            const bool m = t > 0.f;
+            mask_out[o] = m ? 1 : 0;
+            if (m) atomicOr(&s_bits[r], 1u << j);
+        } else if (j >= 8 * KO && j < 11 * KO) {
+            zb[e] = 1.f / (1.f + expf(-x));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int r = threadIdx.x;
+        uint32_t bits = 0;
+        if (r < nrows) { bits = s_bits[r]; maskbits[row0 + r] = bits; }
+        uint32_t s = __popc(bits);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += s_warp[w];
-        block_sums[blockIdx.x] = t;
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (r == 0 && s) atomicAdd(&block_sums[row0 / 256], s);
     }
 }
 
@@ -908,7 +908,8 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
     if (sgemm<false, false>(st, V, HD, XI, f.XIN, XI, f.W1T, HD, f.H, HD, f.b1e, 1)) return -2;
     if (sgemm<false, false>(st, V, ZD, HD, f.H, HD, f.W2T, ZD, f.Z, ZD, f.b2)) return -2;
     const int nb = ceil_div(V, 256);
-    dec_heads_act_kernel<<<nb, 256, 0, st>>>(V, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.bsum, 0, (size_t)nb * sizeof(uint32_t), st));
+    dec_heads_act_kernel<<<ceil_div(V, ACT_ROWS), 256, 0, st>>>(V, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
     SPLATCO_CHECK_LAUNCH();
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
     SPLATCO_CHECK_LAUNCH();
@@ -958,7 +959,7 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     }
     gw.app_vec = g->app_vec;
     gi.anchor_feat = g->anchor_feat; gi.anchor = g->anchor; gi.offset = g->offset; gi.scaling = g->scaling;
-    const int KCH = 4096;
+    const int KCH = 512;            // split-K chunk: V/512 slices x (M/64 x N/32) tiles keep all 148 SMs busy
 
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(b.acc_begin, 0, b.acc_bytes, st));
     dec_bwd_uncompact_kernel<<<ceil_div(V, 128), 128, 0, st>>>(V, LDX, DP, f.X, f.Z, f.maskbits, f.offs, d_xyz, d_color,
@@ -967,17 +968,17 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     // dH = (dZ W2) * [H > 0];   gW2T += H^T dZ;   gb2 = colsum(dZ)
     if (sgemm<false, true>(st, V, HD, ZD, b.DZ, ZD, f.W2T, ZD, b.DH, HD, nullptr, 0, f.H, HD)) return -2;
     if (sgemm<true, false>(st, HD, ZD, V, f.H, HD, b.DZ, ZD, b.gW2T, ZD, nullptr, 0, nullptr, 0, KCH)) return -2;
-    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 1024);
+    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 128);
     SPLATCO_CHECK_LAUNCH();
     // dX100 = dH W1;   gW1T += X100^T dH;   gb1 = colsum(dH)
     if (sgemm<false, true>(st, V, XI, HD, b.DH, HD, f.W1T, HD, b.DX, XI)) return -2;
     if (sgemm<true, false>(st, XI, HD, V, f.XIN, XI, b.DH, HD, b.gW1T, HD, nullptr, 0, nullptr, 0, KCH)) return -2;
-    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, HD, b.DH, HD, b.gb1, 1024);
+    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, HD, b.DH, HD, b.gb1, 128);
     SPLATCO_CHECK_LAUNCH();
     // S1raw = dgeo^T X (both branches), S0 = colsum(dgeo)
     if (sgemm<true, false>(st, 32, DP, V, b.DX + 36, XI, f.X, LDX, b.S1, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
     if (sgemm<true, false>(st, 32, GD, V, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
-    colsum_kernel<<<dim3(ceil_div(V, 1024), 1), 128, 0, st>>>(V, 64, b.DX + 36, XI, b.S0, 1024);
+    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, 64, b.DX + 36, XI, b.S0, 128);
     SPLATCO_CHECK_LAUNCH();
     dec_bwd_fold_kernel<<<1, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                            b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
