@@ -2,24 +2,95 @@
 // [SURVEY.md Appendix A.4, A.5; reference call site gaussian_renderer/__init__.py:163-171 and the
 // autograd backward triggered at train.py:240].
 //
-// One CTA per 16x16 tile, one thread per pixel; warps cover 8x4-pixel patches (not 16x2 rows) so
-// that warp-wide skips (__any/__all ballots) fire more often.  Splats are staged through shared
-// memory in batches of 256 (three 16-byte loads of the packed record per splat); a warp leaves the
-// batch loop as soon as all its pixels are saturated and the CTA ends when every warp has.
-// Backward: gradients of the 9 per-splat scalars are reduced across the warp with shuffles, then
-// accumulated per CTA in shared memory, and flushed with ONE global atomic (RED) per scalar per
-// (tile, splat) — 256x fewer global atomics than the per-pixel atomics of the upstream kernel.
+// One CTA per 16x16 tile, one thread per pixel; warps cover 8x4-pixel patches.  ncu showed the first
+// version of these kernels to be instruction-issue bound (81 % issue-active, DRAM < 1 % of peak), so
+// the design goal is the fewest instructions per (pixel, splat) pair:
+//  * splats are staged through shared memory in batches of 256; the staging thread precomputes, once
+//    per (tile, splat), the conic pre-scaled into the log2 domain (P2 = log2(e) * power, evaluated from
+//    (dx, dy) exactly like the reference so threshold decisions keep full fp32 precision) and
+//    log2(opacity), which is folded into the exponent so the alpha >= 1/255 cut is a compare BEFORE the
+//    ex2 (culled pairs never touch the SFU);
+//  * the staging thread also intersects the splat's alpha >= 1/255 bounding box with the 8 warp
+//    patches; ballots turn that into one 32-bit word per (warp, 32 splats) and each warp walks only the
+//    set bits, in list order — semantics per pixel are unchanged (a culled splat has alpha < 1/255 on
+//    every pixel of the patch and would have been skipped);
+//  * a warp leaves as soon as all its pixels are saturated, the CTA when every warp has.
+// Backward: same staging / culling / skip decisions (bit-identical exponent), gradients of the 9
+// per-splat scalars are reduced across the warp with a transposed butterfly (14 shuffles instead of
+// 45), accumulated per CTA in shared memory and flushed with ONE global RED per scalar per
+// (tile, splat) — 256x fewer global atomics than per-pixel atomics.
 #include "common.cuh"
 
 namespace splatco {
 
 constexpr int BLEND_THREADS = TILE * TILE;   // 256
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLog2Inv255 = -7.994353436858858f;     // log2(1/255)
 
-__device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int &px, int &py) {
+__device__ __forceinline__ void pixel_of_thread(int tile_x, int tile_y, int &px, int &py, float &u, float &v) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    px = tile_x * TILE + (warp & 1) * 8 + (lane & 7);
-    py = tile_y * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    px = tile_x * TILE + lx;
+    py = tile_y * TILE + ly;
+    u = (float)lx - 7.5f;      // tile-centred pixel coordinates
+    v = (float)ly - 7.5f;
+}
+
+struct SplatCoef {
+    float4 k0;    // sx, sy, a2, b2        (centre relative to the tile centre; log2-domain conic)
+    float4 k1;    // c2, log2(opacity), r, g
+    uint32_t mask8;
+};
+
+// P2 = log2(e) * power = a2 dx^2 + b2 dx dy + c2 dy^2   (a2 = -0.5 log2e A, b2 = -log2e B, c2 = -0.5 log2e C)
+__device__ __forceinline__ float eval_p2(const float4 &k0, float c2, float u, float v, float &dx, float &dy) {
+    dx = k0.x - u; dy = k0.y - v;
+    const float t = fmaf(k0.z, dx, k0.w * dy);
+    return fmaf(c2 * dy, dy, t * dx);
+}
+
+// sx, sy: splat centre relative to the tile centre.  Returns the log2-domain coefficients and the
+// 8-bit patch mask (bit w = warp w's 8x4 patch may see alpha >= 1/255).
+__device__ __forceinline__ SplatCoef splat_setup(float sx, float sy, float A, float B, float C, float op, float r,
+                                                 float g) {
+    SplatCoef s;
+    const float a2 = -0.5f * kLog2e * A, c2 = -0.5f * kLog2e * C, b2 = -kLog2e * B;
+    const float lo = op > 0.f ? __log2f(op) : -1e30f;
+    s.k0 = make_float4(sx, sy, a2, b2);
+    s.k1 = make_float4(c2, lo, r, g);
+    // bounding box of { d : -P2(d) <= tau2 },  tau2 = log2(255 * opacity)
+    const float tau2 = lo - kLog2Inv255;
+    uint32_t m = 0;
+    const float det = a2 * c2 - 0.25f * b2 * b2;        // > 0 for a valid conic
+    if (tau2 > 0.f && det > 0.f) {
+        const float t = tau2 * 1.002f + 1e-3f;
+        const float inv = t / det;
+        const float ex = sqrtf(fmaxf(-c2 * inv, 0.f)) + 0.02f;
+        const float ey = sqrtf(fmaxf(-a2 * inv, 0.f)) + 0.02f;
+        const float x0 = sx - ex, x1 = sx + ex, y0 = sy - ey, y1 = sy + ey;
+        const uint32_t xb = ((x1 >= -7.5f && x0 <= -0.5f) ? 1u : 0u) | ((x1 >= 0.5f && x0 <= 7.5f) ? 2u : 0u);
+        uint32_t yb = 0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) yb |= (y1 >= -7.5f + 4.f * h && y0 <= -4.5f + 4.f * h) ? (1u << h) : 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) m |= (((xb >> (w & 1)) & 1u) & ((yb >> (w >> 1)) & 1u)) << w;
+    } else if (tau2 > 0.f) {
+        m = 0xffu;                                      // degenerate conic: never cull
+    }
+    s.mask8 = m;
+    return s;
+}
+
+// turn the per-splat 8-bit masks of one staging warp into 8 ballot words s_mask[w][staging_warp]
+__device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)[8]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (mask8 >> w) & 1u);
+        if (lane == w) mine = b;
+    }
+    if (lane < 8) s_mask[lane][warp] = mine;
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS)
@@ -27,49 +98,66 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
                  float *__restrict__ out_color, float *__restrict__ final_T,
                  int32_t *__restrict__ n_contrib) {
-    __shared__ float4 s_a[BLEND_THREADS];   // x, y, conA, conB
-    __shared__ float4 s_b[BLEND_THREADS];   // conC, opacity, r, g
-    __shared__ float s_c[BLEND_THREADS];    // b
+    __shared__ float4 s_k0[BLEND_THREADS];
+    __shared__ float4 s_k1[BLEND_THREADS];
+    __shared__ float s_b[BLEND_THREADS];
+    __shared__ uint32_t s_mask[8][8];          // [patch warp][staging warp]
     const int tile = blockIdx.x;
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
+    float u, v;
+    pixel_of_thread(tile_x, tile_y, px, py, u, v);
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
     const int2 range = ranges[tile];
+    const float cx = (float)(tile_x * TILE) + 7.5f, cy = (float)(tile_y * TILE) + 7.5f;
     int todo = range.y - range.x;
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    int contributor = 0, last_contributor = 0;
+    int last_contributor = 0;
+    const int warp = threadIdx.x >> 5;
 
     for (int base = range.x; todo > 0; base += BLEND_THREADS, todo -= BLEND_THREADS) {
         if (__syncthreads_and(done)) break;
+        uint32_t mask8 = 0;
         if ((int)threadIdx.x < todo) {
             const uint32_t id = point_list[base + threadIdx.x];
             const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-            s_a[threadIdx.x] = r0; s_b[threadIdx.x] = r1; s_c[threadIdx.x] = r2.x;
+            const SplatCoef s = splat_setup(r0.x - cx, r0.y - cy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
+            s_k0[threadIdx.x] = s.k0; s_k1[threadIdx.x] = s.k1; s_b[threadIdx.x] = r2.x;
+            mask8 = s.mask8;
         }
+        publish_masks(mask8, s_mask);
         __syncthreads();
-        const int nb = min(BLEND_THREADS, todo);
-        {
-            for (int j = 0; j < nb; ++j) {
-                // warp-uniform early exit (j is uniform, every lane reaches the vote)
-                if ((j & 3) == 0 && __all_sync(0xffffffffu, done)) break;
-                if (done) continue;
-                contributor = (base - range.x) + j + 1;
-                const float4 a = s_a[j];
-                const float4 b = s_b[j];
-                const float dx = a.x - pxf, dy = a.y - pyf;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                if (power > 0.0f) continue;
-                const float alpha = fminf(0.99f, b.y * ex2_approx(power * kLog2e));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < 0.0001f) { done = true; continue; }
-                const float w = alpha * T;
-                C0 = fmaf(b.z, w, C0); C1 = fmaf(b.w, w, C1); C2 = fmaf(s_c[j], w, C2);
-                T = test_T;
-                last_contributor = contributor;
+        if (__all_sync(0xffffffffu, done)) continue;
+        const int pos0 = base - range.x + 1;
+#pragma unroll 1
+        for (int word = 0; word < 8; ++word) {
+            uint32_t bits = s_mask[warp][word];
+            while (bits) {
+                const int j = word * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4 k0 = s_k0[j];
+                const float4 k1 = s_k1[j];
+                float dx, dy;
+                const float p2 = eval_p2(k0, k1.x, u, v, dx, dy);
+                const float e = p2 + k1.y;
+                // power > 0 (invalid conic) and alpha < 1/255 skips; `done` pixels take no part
+                const bool live = !done && p2 <= 0.f && e >= kLog2Inv255;
+                if (__any_sync(0xffffffffu, live)) {
+                    if (live) {
+                        const float alpha = fminf(0.99f, ex2_approx(e));
+                        const float test_T = T * (1.0f - alpha);
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float w = alpha * T;
+                            C0 = fmaf(k1.z, w, C0); C1 = fmaf(k1.w, w, C1); C2 = fmaf(s_b[j], w, C2);
+                            T = test_T;
+                            last_contributor = pos0 + j;
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, done)) { bits = 0; word = 8; }
+                }
             }
         }
     }
@@ -84,6 +172,29 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
 }
 
 // ---- backward ---------------------------------------------------------------------------------------
+// Transposed butterfly: every lane enters with 8 values g[0..7]; on return lanes with (lane & 3) == 0
+// hold in `r` the warp-wide sum of value index ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float warp_reduce8(const float (&g)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float w4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? g[i] : g[i + 4];
+        const float keep = b4 ? g[i + 4] : g[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float w2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? w4[i] : w4[i + 2];
+        const float keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float r = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -97,18 +208,21 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                  const float *__restrict__ dL_dpix, float *__restrict__ dL_dmean2D,
                  float *__restrict__ dL_dconic, float *__restrict__ dL_dopacity,
                  float *__restrict__ dL_dcolor) {
-    __shared__ float4 s_a[BLEND_THREADS];
-    __shared__ float4 s_b[BLEND_THREADS];
-    __shared__ float s_c[BLEND_THREADS];
+    __shared__ float4 s_k0[BLEND_THREADS];     // sx, sy, a2, b2
+    __shared__ float4 s_k1[BLEND_THREADS];     // c2, log2(op), r, g
+    __shared__ float4 s_g0[BLEND_THREADS];     // conA, conB, conC, opacity
+    __shared__ float s_b[BLEND_THREADS];
     __shared__ uint32_t s_id[BLEND_THREADS];
-    __shared__ float s_acc[9][BLEND_THREADS];      // per-CTA accumulation of the batch's gradients
+    __shared__ float s_acc[9][BLEND_THREADS];  // per-CTA accumulation of the batch's gradients
+    __shared__ uint32_t s_mask[8][8];
     __shared__ int s_max[BLEND_THREADS / 32];
     const int tile = blockIdx.x;
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
+    float u, v;
+    pixel_of_thread(tile_x, tile_y, px, py, u, v);
     const bool inside = px < W && py < H;
-    const float pxf = (float)px, pyf = (float)py;
+    const float cx = (float)(tile_x * TILE) + 7.5f, cy = (float)(tile_y * TILE) + 7.5f;
     const int2 range = ranges[tile];
     const size_t pid = (size_t)py * W + px, HW = (size_t)H * W;
     const float T_final = inside ? final_T[pid] : 0.f;
@@ -119,82 +233,86 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     // deepest contributor over the tile: nothing behind it receives gradient
-    int m = last;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    const int warp_last = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0) s_max[warp] = warp_last;
     __syncthreads();
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_THREADS / 32; ++w) tile_last = max(tile_last, s_max[w]);
-    const int lane = threadIdx.x & 31;
+    // destination of this lane's share of the butterfly result
+    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
 
-    // walk positions tile_last-1 .. 0 in batches of 256, back to front
+    // walk positions tile_last-1 .. 0 in batches of 256, back to front; slot j holds position hi-1-j
     for (int hi = tile_last; hi > 0; hi -= BLEND_THREADS) {
         const int nb = min(BLEND_THREADS, hi);
         __syncthreads();                        // previous batch fully flushed
         {
-            // slot j holds position hi-1-j
             const int j = threadIdx.x;
+            uint32_t mask8 = 0;
             if (j < nb) {
                 const uint32_t id = point_list[range.x + hi - 1 - j];
                 const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-                s_a[j] = r0; s_b[j] = r1; s_c[j] = r2.x; s_id[j] = id;
+                const float sx = r0.x - cx, sy = r0.y - cy;
+                const SplatCoef s = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
+                s_k0[j] = s.k0; s_k1[j] = s.k1;
+                s_g0[j] = make_float4(r0.z, r0.w, r1.x, r1.y);
+                s_b[j] = r2.x;
+                s_id[j] = id;
+                mask8 = s.mask8;
             }
+            publish_masks(mask8, s_mask);
 #pragma unroll
             for (int q = 0; q < 9; ++q) s_acc[q][j] = 0.f;
         }
         __syncthreads();
-        // warp-uniform bound: positions >= warp's deepest contributor cannot contribute
-        const int warp_last = __reduce_max_sync(0xffffffffu, last);
-        for (int j = 0; j < nb; ++j) {
-            const int pos = hi - 1 - j;
-            if (pos >= warp_last) continue;
-            float g[9];
-            bool live = pos < last;
-            float alpha = 0.f, G = 0.f, dx = 0.f, dy = 0.f;
-            const float4 a = s_a[j];
-            const float4 b = s_b[j];
-            if (live) {
-                dx = a.x - pxf; dy = a.y - pyf;
-                const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-                G = ex2_approx(power * kLog2e);
-                alpha = fminf(0.99f, b.y * G);
-                live = (power <= 0.0f) && (alpha >= 1.0f / 255.0f);
-            }
-            if (!__any_sync(0xffffffffu, live)) continue;
-            if (live) {
-                T = T / (1.0f - alpha);
-                const float dch = alpha * T;
-                const float c0 = b.z, c1 = b.w, c2 = s_c[j];
-                ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = c0;
-                ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = c1;
-                ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = c2;
-                float dL_dalpha = ((c0 - ar0) * dp0 + (c1 - ar1) * dp1 + (c2 - ar2) * dp2) * T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = b.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                g[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
-                g[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddely_dy;
-                g[2] = -0.5f * gdx * dx * dL_dG;
-                g[3] = -0.5f * gdx * dy * dL_dG;
-                g[4] = -0.5f * gdy * dy * dL_dG;
-                g[5] = G * dL_dalpha;
-                g[6] = dch * dp0; g[7] = dch * dp1; g[8] = dch * dp2;
-            } else {
+#pragma unroll 1
+        for (int word = 0; word < 8; ++word) {
+            uint32_t bits = s_mask[warp][word];
+            while (bits) {
+                const int j = word * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int pos = hi - 1 - j;
+                if (pos >= warp_last) continue;              // warp-uniform
+                const float4 k0 = s_k0[j];
+                const float4 k1 = s_k1[j];
+                float dx, dy;
+                const float p2 = eval_p2(k0, k1.x, u, v, dx, dy);
+                const float e = p2 + k1.y;
+                const bool live = pos < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
+                if (!__any_sync(0xffffffffu, live)) continue;
+                float g[8], gop = 0.f;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) g[q] = 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < 9; ++q) g[q] = warp_sum(g[q]);
-            if (lane < 9) {
-                float v = g[0];
-#pragma unroll
-                for (int q = 1; q < 9; ++q) v = (lane == q) ? g[q] : v;
-                atomicAdd(&s_acc[lane][j], v);
+                for (int q = 0; q < 8; ++q) g[q] = 0.f;
+                if (live) {
+                    const float4 g0 = s_g0[j];      // A, B, C, opacity
+                    const float G = ex2_approx(p2);
+                    const float alpha = fminf(0.99f, g0.w * G);
+                    T = T / (1.0f - alpha);
+                    const float dch = alpha * T;
+                    const float c0 = k1.z, c1 = k1.w, c2 = s_b[j];
+                    ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = c0;
+                    ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = c1;
+                    ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = c2;
+                    float dL_dalpha = ((c0 - ar0) * dp0 + (c1 - ar1) * dp1 + (c2 - ar2) * dp2) * T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = g0.w * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    g[0] = dL_dG * (-gdx * g0.x - gdy * g0.y) * ddelx_dx;
+                    g[1] = dL_dG * (-gdy * g0.z - gdx * g0.y) * ddely_dy;
+                    g[2] = -0.5f * gdx * dx * dL_dG;
+                    g[3] = -0.5f * gdx * dy * dL_dG;
+                    g[4] = -0.5f * gdy * dy * dL_dG;
+                    g[5] = dch * dp0; g[6] = dch * dp1; g[7] = dch * dp2;
+                    gop = G * dL_dalpha;
+                }
+                const float r8 = warp_reduce8(g, lane);
+                const float r1 = warp_sum(gop);
+                if ((lane & 3) == 0) atomicAdd(&s_acc[ridx][j], r8);
+                if (lane == 1) atomicAdd(&s_acc[8][j], r1);
             }
         }
         __syncthreads();
@@ -202,20 +320,20 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
             const int j = threadIdx.x;
             if (j < nb) {
                 const uint32_t id = s_id[j];
-                float v[9];
+                float a[9];
                 bool any = false;
 #pragma unroll
-                for (int q = 0; q < 9; ++q) { v[q] = s_acc[q][j]; any |= (v[q] != 0.f); }
+                for (int q = 0; q < 9; ++q) { a[q] = s_acc[q][j]; any |= (a[q] != 0.f); }
                 if (any) {
-                    atomicAdd(&dL_dmean2D[3 * (size_t)id], v[0]);
-                    atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], v[1]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id], v[2]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id + 1], v[3]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id + 2], v[4]);
-                    atomicAdd(&dL_dopacity[id], v[5]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id], v[6]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id + 1], v[7]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id + 2], v[8]);
+                    atomicAdd(&dL_dmean2D[3 * (size_t)id], a[0]);
+                    atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], a[1]);
+                    atomicAdd(&dL_dconic[3 * (size_t)id], a[2]);
+                    atomicAdd(&dL_dconic[3 * (size_t)id + 1], a[3]);
+                    atomicAdd(&dL_dconic[3 * (size_t)id + 2], a[4]);
+                    atomicAdd(&dL_dcolor[3 * (size_t)id], a[5]);
+                    atomicAdd(&dL_dcolor[3 * (size_t)id + 1], a[6]);
+                    atomicAdd(&dL_dcolor[3 * (size_t)id + 2], a[7]);
+                    atomicAdd(&dL_dopacity[id], a[8]);
                 }
             }
         }
