@@ -201,6 +201,19 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+
+// Staged splat record of the backward: 64 bytes = 4 x float4
+//   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] conA, conB, conC, opacity   [3] b, id(bits), 0, 0
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
@@ -208,12 +221,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                  const float *__restrict__ dL_dpix, float *__restrict__ dL_dmean2D,
                  float *__restrict__ dL_dconic, float *__restrict__ dL_dopacity,
                  float *__restrict__ dL_dcolor) {
-    __shared__ float4 s_k0[BLEND_THREADS];     // sx, sy, a2, b2
-    __shared__ float4 s_k1[BLEND_THREADS];     // c2, log2(op), r, g
-    __shared__ float4 s_g0[BLEND_THREADS];     // conA, conB, conC, opacity
-    __shared__ float s_b[BLEND_THREADS];
-    __shared__ uint32_t s_id[BLEND_THREADS];
-    __shared__ float s_acc[9][BLEND_THREADS];  // per-CTA accumulation of the batch's gradients
+    __shared__ float4 s_rec[BLEND_THREADS * 4];
     __shared__ uint32_t s_mask[8][8];
     __shared__ int s_max[BLEND_THREADS / 32];
     const int tile = blockIdx.x;
@@ -230,10 +238,11 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     float T = T_final;
     float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
     if (inside) { dp0 = dL_dpix[pid]; dp1 = dL_dpix[HW + pid]; dp2 = dL_dpix[2 * HW + pid]; }
-    const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    const float neg_Tf_bg = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(s_rec);
 
     // deepest contributor over the tile: nothing behind it receives gradient
     const int warp_last = __reduce_max_sync(0xffffffffu, last);
@@ -242,13 +251,15 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_THREADS / 32; ++w) tile_last = max(tile_last, s_max[w]);
-    // destination of this lane's share of the butterfly result
+    // After the butterfly, lanes with (lane & 3) == 0 own one of the 8 reduced scalars; its destination
+    // array has row stride 3: mean2D.x/.y, conic.x/.y/.z, colour.r/.g/.b.  Lane 1 owns the opacity sum.
     const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float *const gdst = ridx < 2 ? dL_dmean2D + ridx : (ridx < 5 ? dL_dconic + (ridx - 2) : dL_dcolor + (ridx - 5));
 
     // walk positions tile_last-1 .. 0 in batches of 256, back to front; slot j holds position hi-1-j
     for (int hi = tile_last; hi > 0; hi -= BLEND_THREADS) {
         const int nb = min(BLEND_THREADS, hi);
-        __syncthreads();                        // previous batch fully flushed
+        __syncthreads();                        // every warp is done with the previous batch
         {
             const int j = threadIdx.x;
             uint32_t mask8 = 0;
@@ -257,84 +268,69 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
                 const float sx = r0.x - cx, sy = r0.y - cy;
                 const SplatCoef s = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
-                s_k0[j] = s.k0; s_k1[j] = s.k1;
-                s_g0[j] = make_float4(r0.z, r0.w, r1.x, r1.y);
-                s_b[j] = r2.x;
-                s_id[j] = id;
+                s_rec[4 * j] = s.k0; s_rec[4 * j + 1] = s.k1;
+                s_rec[4 * j + 2] = make_float4(r0.z, r0.w, r1.x, r1.y);
+                s_rec[4 * j + 3] = make_float4(r2.x, __uint_as_float(id), 0.f, 0.f);
                 mask8 = s.mask8;
             }
             publish_masks(mask8, s_mask);
-#pragma unroll
-            for (int q = 0; q < 9; ++q) s_acc[q][j] = 0.f;
         }
         __syncthreads();
+        // slots whose position is at or behind this warp's deepest contributor cannot receive gradient:
+        // position = hi-1-j >= warp_last  <=>  j < hi - warp_last
+        const int skip = hi - warp_last;
 #pragma unroll 1
         for (int word = 0; word < 8; ++word) {
             uint32_t bits = s_mask[warp][word];
+            const int lo = word * 32;
+            if (skip >= lo + 32) bits = 0;
+            else if (skip > lo) bits &= ~((1u << (skip - lo)) - 1u);
             while (bits) {
-                const int j = word * 32 + __ffs(bits) - 1;
+                const int j = lo + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const int pos = hi - 1 - j;
-                if (pos >= warp_last) continue;              // warp-uniform
-                const float4 k0 = s_k0[j];
-                const float4 k1 = s_k1[j];
+                const uint32_t addr = a_rec + ((uint32_t)j << 6);
+                const float4 k0 = lds128(addr);
+                const float4 k1 = lds128(addr + 16);
                 float dx, dy;
                 const float p2 = eval_p2(k0, k1.x, u, v, dx, dy);
                 const float e = p2 + k1.y;
-                const bool live = pos < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
+                const bool live = (hi - 1 - j) < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
                 if (!__any_sync(0xffffffffu, live)) continue;
+                const float2 bid = lds64(addr + 48);
                 float g[8], gop = 0.f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) g[q] = 0.f;
                 if (live) {
-                    const float4 g0 = s_g0[j];      // A, B, C, opacity
+                    const float4 g0 = lds128(addr + 32);      // A, B, C, opacity
                     const float G = ex2_approx(p2);
                     const float alpha = fminf(0.99f, g0.w * G);
-                    T = T / (1.0f - alpha);
+                    const float rcp = __fdividef(1.0f, 1.0f - alpha);
+                    T *= rcp;
                     const float dch = alpha * T;
-                    const float c0 = k1.z, c1 = k1.w, c2 = s_b[j];
-                    ar0 = last_alpha * lc0 + (1.f - last_alpha) * ar0; lc0 = c0;
-                    ar1 = last_alpha * lc1 + (1.f - last_alpha) * ar1; lc1 = c1;
-                    ar2 = last_alpha * lc2 + (1.f - last_alpha) * ar2; lc2 = c2;
+                    const float c0 = k1.z, c1 = k1.w, c2 = bid.x;
+                    const float om = 1.f - last_alpha;
+                    ar0 = fmaf(last_alpha, lc0, om * ar0); lc0 = c0;
+                    ar1 = fmaf(last_alpha, lc1, om * ar1); lc1 = c1;
+                    ar2 = fmaf(last_alpha, lc2, om * ar2); lc2 = c2;
                     float dL_dalpha = ((c0 - ar0) * dp0 + (c1 - ar1) * dp1 + (c2 - ar2) * dp2) * T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha = fmaf(neg_Tf_bg, rcp, dL_dalpha);
                     const float dL_dG = g0.w * dL_dalpha;
                     const float gdx = G * dx, gdy = G * dy;
                     g[0] = dL_dG * (-gdx * g0.x - gdy * g0.y) * ddelx_dx;
                     g[1] = dL_dG * (-gdy * g0.z - gdx * g0.y) * ddely_dy;
-                    g[2] = -0.5f * gdx * dx * dL_dG;
-                    g[3] = -0.5f * gdx * dy * dL_dG;
-                    g[4] = -0.5f * gdy * dy * dL_dG;
+                    const float h = -0.5f * dL_dG;
+                    g[2] = h * gdx * dx;
+                    g[3] = h * gdx * dy;
+                    g[4] = h * gdy * dy;
                     g[5] = dch * dp0; g[6] = dch * dp1; g[7] = dch * dp2;
                     gop = G * dL_dalpha;
                 }
                 const float r8 = warp_reduce8(g, lane);
                 const float r1 = warp_sum(gop);
-                if ((lane & 3) == 0) atomicAdd(&s_acc[ridx][j], r8);
-                if (lane == 1) atomicAdd(&s_acc[8][j], r1);
-            }
-        }
-        __syncthreads();
-        {
-            const int j = threadIdx.x;
-            if (j < nb) {
-                const uint32_t id = s_id[j];
-                float a[9];
-                bool any = false;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) { a[q] = s_acc[q][j]; any |= (a[q] != 0.f); }
-                if (any) {
-                    atomicAdd(&dL_dmean2D[3 * (size_t)id], a[0]);
-                    atomicAdd(&dL_dmean2D[3 * (size_t)id + 1], a[1]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id], a[2]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id + 1], a[3]);
-                    atomicAdd(&dL_dconic[3 * (size_t)id + 2], a[4]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id], a[5]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id + 1], a[6]);
-                    atomicAdd(&dL_dcolor[3 * (size_t)id + 2], a[7]);
-                    atomicAdd(&dL_dopacity[id], a[8]);
-                }
+                const size_t id = __float_as_uint(bid.y);
+                if ((lane & 3) == 0 && r8 != 0.f) atomicAdd(gdst + 3 * id, r8);
+                if (lane == 1 && r1 != 0.f) atomicAdd(dL_dopacity + id, r1);
             }
         }
     }
