@@ -162,6 +162,13 @@ int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *b
                        const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
                        const splatco_decode_grads *g, void *stream);
 
+/* ---- diagnostics --------------------------------------------------------------------------------
+ * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:
+ * C[M,N] = A[M,K] * B[N,K]^T (row-major fp32, N <= 112, K <= 136).  variant bit0: swapped LBO/SBO
+ * descriptor convention (expected to be wrong), bit1: single-pass TF32.  Used by tests/test_tc_gpu.py. */
+int splatco_tc_gemm_selftest(int M, int N, int K, const float *A, const float *B, float *C, int variant,
+                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,7 @@ SIGNATURES = {
     "splatco_decode_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }
 
 

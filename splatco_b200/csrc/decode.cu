@@ -37,9 +37,13 @@ inline DecDims dec_dims(int V, int rc, int level) {
     return d;
 }
 
+}  // namespace splatco
+#include "decode_tc.cuh"
+namespace splatco {
+
 // ---- forward workspace -------------------------------------------------------------------------------
 enum FwdChunk { F_X, F_STATS, F_MU, F_RSTD, F_WPT, F_WCT, F_BGEO, F_W1T, F_B1E, F_W2T, F_B2, F_WPG, F_WCG,
-                F_XIN, F_H, F_Z, F_MASKBITS, F_OFFS, F_BSUM, F_BOFF, F_TOTAL, F_NCHUNK };
+                F_XIN, F_H, F_Z, F_MASKBITS, F_OFFS, F_BSUM, F_BOFF, F_TOTAL, F_XT, F_BA, F_W1B, F_W2B, F_NCHUNK };
 
 static size_t dec_fwd_offsets(const DecDims &d, size_t off[F_NCHUNK + 1]) {
     const size_t V = (size_t)(d.V > 0 ? d.V : 0);
@@ -55,6 +59,10 @@ static size_t dec_fwd_offsets(const DecDims &d, size_t off[F_NCHUNK + 1]) {
     put(F_WPG, 32 * DEC_MAX_DP * 4); put(F_WCG, 32 * GD * 4);
     put(F_XIN, V * XI * 4); put(F_H, V * HD * 4); put(F_Z, V * ZD * 4);
     put(F_MASKBITS, V * 4); put(F_OFFS, V * 4); put(F_BSUM, nb * 4); put(F_BOFF, nb * 4); put(F_TOTAL, 4);
+    // tensor-core path: X in 128-row tile / 16-byte chunk layout, pre-split weight tiles
+    const size_t ntiles = (V + TC_ROWS - 1) / TC_ROWS;
+    put(F_XT, d.rc <= TC_MAX_RC ? ntiles * tc_tile_chunks(d.DP) * TC_CHUNK : 0);
+    put(F_BA, 2 * TC_BA_HALF); put(F_W1B, 2 * TC_W1_HALF); put(F_W2B, 2 * TC_W2_HALF);
     off[F_NCHUNK] = o;
     return o;
 }
@@ -237,7 +245,7 @@ constexpr int GATHER_WARPS = 8;
 
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
 dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__ X, float *__restrict__ XIN,
-                  double *__restrict__ stats) {
+                  double *__restrict__ stats, float *__restrict__ XT) {
     extern __shared__ float s_red[];     // [GATHER_WARPS][2][LDX]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps_total = gridDim.x * GATHER_WARPS;
@@ -275,7 +283,18 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
                 else val = __ldg(p.scaling + (size_t)i * 6 + (g - FD - 3 - 3 * KO));
             }
             xrow[c] = val;
+            if (XT) {       // tile / chunk layout for the tensor-core kernel: [tile][chunk][row][4]; g starts on a fresh chunk
+                const int cc = c < DP ? c : ((DP + 3) & ~3) + (c - DP);
+                const size_t cell = ((size_t)(v >> 7) * tc_tile_chunks(DP) + (cc >> 2)) * TC_ROWS + (v & 127);
+                XT[cell * 4 + (cc & 3)] = val;
+            }
             sum[j] += val; sq[j] = fmaf(val, val, sq[j]);
+        }
+        if (XT) {           // zero the padding of the last P chunk and the g pad column (garbage * 0 could be NaN)
+            const int npc = (DP + 3) >> 2;
+            const size_t tb = (size_t)(v >> 7) * tc_tile_chunks(DP);
+            if (lane < 4 * npc - DP) XT[((tb + npc - 1) * TC_ROWS + (v & 127)) * 4 + (DP & 3) + lane] = 0.f;
+            if (lane == 0) XT[((tb + npc + 17) * TC_ROWS + (v & 127)) * 4 + 3] = 0.f;
         }
         if (lane < LDX - ncols) xrow[ncols + lane] = 0.f;       // zero the row padding
         // x100 head: feat | dir | dist   (gaussian_renderer/__init__.py:34-38,55)
@@ -284,7 +303,9 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
         if (lane < 4) {
             const float vx = ax - p.cam[0], vy = ay - p.cam[1], vz = az - p.cam[2];
             const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
-            xin[FD + lane] = lane == 0 ? vx / dist : (lane == 1 ? vy / dist : (lane == 2 ? vz / dist : dist));
+            const float dd = lane == 0 ? vx / dist : (lane == 1 ? vy / dist : (lane == 2 ? vz / dist : dist));
+            xin[FD + lane] = dd;
+            if (XT) XT[(((size_t)(v >> 7) * tc_tile_chunks(DP) + ((DP + 3) >> 2) + 18) * TC_ROWS + (v & 127)) * 4 + lane] = dd;
         }
     }
     // CTA reduction of the statistics, then one fp64 atomic per channel per CTA
@@ -784,6 +805,8 @@ struct FwdView {
     float *X, *mu, *rstd, *WpT, *WcT, *bgeo, *W1T, *b1e, *W2T, *b2, *WpG, *WcG, *XIN, *H, *Z;
     double *stats;
     uint32_t *maskbits, *offs, *bsum, *boff, *total;
+    float *XT;
+    uint8_t *BA, *W1B, *W2B;
 };
 FwdView fwd_view(void *ws, const DecDims &d) {
     size_t off[F_NCHUNK + 1];
@@ -800,6 +823,8 @@ FwdView fwd_view(void *ws, const DecDims &d) {
     v.maskbits = (uint32_t *)(b + off[F_MASKBITS]); v.offs = (uint32_t *)(b + off[F_OFFS]);
     v.bsum = (uint32_t *)(b + off[F_BSUM]); v.boff = (uint32_t *)(b + off[F_BOFF]);
     v.total = (uint32_t *)(b + off[F_TOTAL]);
+    v.XT = (float *)(b + off[F_XT]);
+    v.BA = (uint8_t *)(b + off[F_BA]); v.W1B = (uint8_t *)(b + off[F_W1B]); v.W2B = (uint8_t *)(b + off[F_W2B]);
     return v;
 }
 
@@ -896,21 +921,38 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
     const DecPtrs p = make_ptrs(d);
     const DecWeights w = make_weights(d);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.stats, 0, 2 * (size_t)dd.LDX * sizeof(double), st));
+    const bool use_tc = dd.rc <= TC_MAX_RC;     // tensor-core path (3 rc <= 16 plane chunks fit its shared-memory map)
     dec_gather_kernel<<<gather_grid(V), GATHER_WARPS * 32, GATHER_WARPS * 2 * dd.LDX * sizeof(float), st>>>(
-        p, V, dd.rc, dd.DP, dd.LDX, f.X, f.XIN, f.stats);
+        p, V, dd.rc, dd.DP, dd.LDX, f.X, f.XIN, f.stats, use_tc ? f.XT : nullptr);
     SPLATCO_CHECK_LAUNCH();
     dec_fold_kernel<<<1, 256, 0, st>>>(w, V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
                                        f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
     SPLATCO_CHECK_LAUNCH();
-    // geo = [ (P - mu) Wp' | (g - mu) Wc' ] + bias, written straight into x100 columns 36..99
-    if (sgemm<false, false>(st, V, 32, dd.DP, f.X, dd.LDX, f.WpT, 32, f.XIN + 36, XI, f.bgeo)) return -2;
-    if (sgemm<false, false>(st, V, 32, GD, f.X + dd.DP, dd.LDX, f.WcT, 32, f.XIN + 68, XI, f.bgeo + 32)) return -2;
-    if (sgemm<false, false>(st, V, HD, XI, f.XIN, XI, f.W1T, HD, f.H, HD, f.b1e, 1)) return -2;
-    if (sgemm<false, false>(st, V, ZD, HD, f.H, HD, f.W2T, ZD, f.Z, ZD, f.b2)) return -2;
     const int nb = ceil_div(V, 256);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.bsum, 0, (size_t)nb * sizeof(uint32_t), st));
-    dec_heads_act_kernel<<<ceil_div(V, ACT_ROWS), 256, 0, st>>>(V, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
-    SPLATCO_CHECK_LAUNCH();
+    if (use_tc) {
+        // fused tcgen05 path: geo -> hidden -> heads -> activations in one persistent kernel
+        dec_tc_pack_kernel<<<1, 256, 0, st>>>(dd.DP, f.WpT, f.WcT, f.W1T, f.W2T, f.BA, f.W1B, f.W2B);
+        SPLATCO_CHECK_LAUNCH();
+        static bool attr_set = false;
+        if (!attr_set) {
+            SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+            attr_set = true;
+        }
+        const int ntiles = ceil_div(V, TC_ROWS);
+        dec_tc_fwd_kernel<<<min(ntiles, 148), TC_ROWS, TC_SMEM, st>>>(V, dd.DP, f.XT, f.BA, f.W1B, f.W2B, f.bgeo, f.b1e, f.b2,
+                                                                     f.XIN, f.H, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
+        SPLATCO_CHECK_LAUNCH();
+    } else {
+        // SIMT fp32 chain (plane grids with more than 5 channels per plane)
+        // geo = [ (P - mu) Wp' | (g - mu) Wc' ] + bias, written straight into x100 columns 36..99
+        if (sgemm<false, false>(st, V, 32, dd.DP, f.X, dd.LDX, f.WpT, 32, f.XIN + 36, XI, f.bgeo)) return -2;
+        if (sgemm<false, false>(st, V, 32, GD, f.X + dd.DP, dd.LDX, f.WcT, 32, f.XIN + 68, XI, f.bgeo + 32)) return -2;
+        if (sgemm<false, false>(st, V, HD, XI, f.XIN, XI, f.W1T, HD, f.H, HD, f.b1e, 1)) return -2;
+        if (sgemm<false, false>(st, V, ZD, HD, f.H, HD, f.W2T, ZD, f.Z, ZD, f.b2)) return -2;
+        dec_heads_act_kernel<<<ceil_div(V, ACT_ROWS), 256, 0, st>>>(V, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
+        SPLATCO_CHECK_LAUNCH();
+    }
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
     SPLATCO_CHECK_LAUNCH();
     dec_offsets_kernel<<<nb, 256, 0, st>>>(V, f.maskbits, f.boff, f.offs);
