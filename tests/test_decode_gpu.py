@@ -102,7 +102,10 @@ def test_decode_matches_reference_golden(tag):
             assert got is not None, name
             # TA.* weights get their gradient through torch's conv backward (reduction over the whole plane)
             tol = 3e-3 if ".TA." in name else 1e-3
-            assert rel_err(got.cpu().numpy(), d[k]) < tol, (level, name)
+            # 1e-3 relative; entries below 3e-3*max|g| are held to 3e-6*max|g| absolute: the forward runs
+            # on tensor cores as 3xTF32 (~4e-6 relative, tests/test_tc_gpu.py) and the saved activations
+            # carry that into the smallest gradient entries
+            assert rel_err(got.cpu().numpy(), d[k], floor_frac=3e-3) < tol, (level, name)
             checked += 1
         assert checked >= 20
     sd = pc.feat_planes._feat.state_dict()
