@@ -555,36 +555,42 @@ dec_compact_kernel(int V, int LDX, int DP, const float *__restrict__ X, const fl
 // Backward elementwise stages
 // =======================================================================================================
 // un-compaction: upstream gradients of the five compacted outputs -> dZ rows (pre-activation) and the
-// direct (non-MLP) gradients of anchor / offsets / scaling.  One thread per visible anchor.
-__global__ void __launch_bounds__(128)
+// direct (non-MLP) gradients of anchor / offsets / scaling.  One thread per (visible anchor, offset):
+// a CTA covers 32 anchors x 10 offsets, so the 110 dZ entries of a row are written by 10 adjacent
+// threads; the per-anchor sums over offsets (anchor 3 + scaling 6) are reduced in shared memory.
+constexpr int UNC_ROWS = 32;
+__global__ void __launch_bounds__(UNC_ROWS * KO)
 dec_bwd_uncompact_kernel(int V, int LDX, int DP, const float *__restrict__ X, const float *__restrict__ Z,
                          const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ offs,
                          const float *__restrict__ d_xyz, const float *__restrict__ d_color,
                          const float *__restrict__ d_opacity, const float *__restrict__ d_scaling,
                          const float *__restrict__ d_rot, const float *__restrict__ d_nopac,
                          float *__restrict__ DZ, float *__restrict__ DGA) {
-    const int v = blockIdx.x * 128 + threadIdx.x;
-    if (v >= V) return;
-    const uint32_t bits = maskbits[v];
-    const float *g = X + (size_t)v * LDX + DP;
-    const float *z = Z + (size_t)v * ZD;
-    const float *s6 = g + FD + 3 + 3 * KO;
-    float *dz = DZ + (size_t)v * ZD;
-    float *dga = DGA + (size_t)v * 40;          // [anchor 3 | offsets 30 | scaling 6 | pad]
-    float da0 = 0.f, da1 = 0.f, da2 = 0.f, ds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    size_t j = offs[v];
-    for (int k = 0; k < KO; ++k) {
+    __shared__ float s_sum[UNC_ROWS][9];
+    const int tid = threadIdx.x;
+    if (tid < UNC_ROWS * 9) (&s_sum[0][0])[tid] = 0.f;
+    __syncthreads();
+    const int vl = tid / KO, k = tid - vl * KO;
+    const int v = blockIdx.x * UNC_ROWS + vl;
+    if (v < V) {
+        const uint32_t bits = maskbits[v];
+        const float *g = X + (size_t)v * LDX + DP;
+        const float *z = Z + (size_t)v * ZD;
+        const float *s6 = g + FD + 3 + 3 * KO;
+        float *dz = DZ + (size_t)v * ZD;
+        float *dga = DGA + (size_t)v * 40;          // [anchor 3 | offsets 30 | scaling 6 | pad]
         const bool m = (bits >> k) & 1u;
         const float no = z[k];
         float dno = d_nopac ? d_nopac[(size_t)v * KO + k] : 0.f;
         float dof[3] = {0.f, 0.f, 0.f}, dc[3] = {0.f, 0.f, 0.f}, dsr[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (m) {
+            const size_t j = offs[v] + __popc(bits & ((1u << k) - 1u));
             dno += d_opacity[j];
             const float gx = d_xyz[3 * j], gy = d_xyz[3 * j + 1], gz = d_xyz[3 * j + 2];
             const float *of = g + FD + 3 + 3 * k;
-            da0 += gx; da1 += gy; da2 += gz;
             dof[0] = gx * s6[0]; dof[1] = gy * s6[1]; dof[2] = gz * s6[2];
-            ds[0] += gx * of[0]; ds[1] += gy * of[1]; ds[2] += gz * of[2];
+            atomicAdd(&s_sum[vl][0], gx); atomicAdd(&s_sum[vl][1], gy); atomicAdd(&s_sum[vl][2], gz);
+            atomicAdd(&s_sum[vl][3], gx * of[0]); atomicAdd(&s_sum[vl][4], gy * of[1]); atomicAdd(&s_sum[vl][5], gz * of[2]);
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const float c = z[8 * KO + 3 * k + q];
@@ -596,7 +602,7 @@ dec_bwd_uncompact_kernel(int V, int LDX, int DP, const float *__restrict__ X, co
                 const float sg = 1.f / (1.f + expf(-sr[q]));
                 const float gsc = d_scaling[3 * j + q];
                 dsr[q] = gsc * s6[3 + q] * sg * (1.f - sg);
-                ds[3 + q] += gsc * sg;
+                atomicAdd(&s_sum[vl][6 + q], gsc * sg);
             }
             const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
             const float n = fmaxf(nrm, 1e-12f);
@@ -609,19 +615,21 @@ dec_bwd_uncompact_kernel(int V, int LDX, int DP, const float *__restrict__ X, co
             } else {
                 dsr[3] = g0 / n; dsr[4] = g1 / n; dsr[5] = g2 / n; dsr[6] = g3 / n;
             }
-            ++j;
         }
         dz[k] = dno * (1.f - no * no);
 #pragma unroll
         for (int q = 0; q < 7; ++q) dz[KO + 7 * k + q] = dsr[q];
 #pragma unroll
         for (int q = 0; q < 3; ++q) { dz[8 * KO + 3 * k + q] = dc[q]; dga[3 + 3 * k + q] = dof[q]; }
+        if (k == 0) { dz[11 * KO] = 0.f; dz[11 * KO + 1] = 0.f; dga[39] = 0.f; }
     }
-    dz[11 * KO] = 0.f; dz[11 * KO + 1] = 0.f;
-    dga[0] = da0; dga[1] = da1; dga[2] = da2;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) dga[33 + q] = ds[q];
-    dga[39] = 0.f;
+    __syncthreads();
+    if (v < V && k < 9) {
+        // s_sum: [0..2] anchor, [3..5] scaling[0..2] (from xyz), [6..8] scaling[3..5]
+        float *dga = DGA + (size_t)v * 40;
+        const float val = s_sum[vl][k];
+        if (k < 3) dga[k] = val; else dga[33 + (k - 3)] = val;
+    }
 }
 
 // S0/S1 -> parameter gradients of the BN+Linear branches and the per-channel BN-backward constants m1, m2.
@@ -1004,12 +1012,19 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     const int KCH = 512;            // split-K chunk: V/512 slices x (M/64 x N/32) tiles keep all 148 SMs busy
 
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(b.acc_begin, 0, b.acc_bytes, st));
-    dec_bwd_uncompact_kernel<<<ceil_div(V, 128), 128, 0, st>>>(V, LDX, DP, f.X, f.Z, f.maskbits, f.offs, d_xyz, d_color,
+    dec_bwd_uncompact_kernel<<<ceil_div(V, UNC_ROWS), UNC_ROWS * KO, 0, st>>>(V, LDX, DP, f.X, f.Z, f.maskbits, f.offs, d_xyz, d_color,
                                                               d_opacity, d_scaling, d_rot, d_neural_opacity, b.DZ, b.DGA);
     SPLATCO_CHECK_LAUNCH();
     // dH = (dZ W2) * [H > 0];   gW2T += H^T dZ;   gb2 = colsum(dZ)
-    if (sgemm<false, true>(st, V, HD, ZD, b.DZ, ZD, f.W2T, ZD, b.DH, HD, nullptr, 0, f.H, HD)) return -2;
-    if (sgemm<true, false>(st, HD, ZD, V, f.H, HD, b.DZ, ZD, b.gW2T, ZD, nullptr, 0, nullptr, 0, KCH)) return -2;
+    // (W2 is block-diagonal: head h maps hidden 32h..32h+31 to its own output columns, so each product is
+    //  three narrow GEMMs instead of one dense 96 x 112)
+    for (int hd = 0; hd < 3; ++hd) {
+        const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
+        if (sgemm<false, true>(st, V, 32, nj, b.DZ + j0, ZD, f.W2T + (size_t)i0 * ZD + j0, ZD, b.DH + i0, HD, nullptr, 0,
+                               f.H + i0, HD)) return -2;
+        if (sgemm<true, false>(st, 32, nj, V, f.H + i0, HD, b.DZ + j0, ZD, b.gW2T + (size_t)i0 * ZD + j0, ZD, nullptr, 0,
+                               nullptr, 0, KCH)) return -2;
+    }
     colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 128);
     SPLATCO_CHECK_LAUNCH();
     // dX100 = dH W1;   gW1T += X100^T dH;   gb1 = colsum(dH)
