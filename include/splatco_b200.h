@@ -117,7 +117,8 @@ typedef struct splatco_decode_desc {
     int32_t E[3];                          /* plane edge of k0s[0] (TA level), k0s[1], k0s[2]           */
     int32_t use_dist[3];                   /* add_opacity_dist, add_cov_dist, add_color_dist            */
     int32_t update_running;                /* 1: update BatchNorm running stats in place (train mode)   */
-    float xyz_min[3], xyz_max[3], cam[3];
+    const float *xyz_min, *xyz_max, *cam;  /* DEVICE pointers to 3 floats each: plane bbox (PlaneGrid.xyz_min/max)
+                                              and camera_center — read on the device, no host sync needed  */
     float bn_eps, bn_momentum;
     const float *anchor_feat, *anchor, *offset, *scaling;   /* [N,32] [N,3] [N,K,3] [N,6] (activated)   */
     const int32_t *vis;                    /* [V] ascending indices of the visible anchors              */

@@ -187,7 +187,7 @@ struct DecPtrs {
     const float *plane[3][3];
     const float *att[3];
     int E[3];
-    float mn[3], mx[3], cam[3];
+    const float *mn, *mx, *cam;      // device pointers (3 floats each)
     const float *noise;
 };
 
@@ -231,9 +231,10 @@ __device__ __forceinline__ void plane_channel(int c, int rc, int &lvl, int &pl, 
 }
 
 __device__ __forceinline__ void norm_coords(const DecPtrs &p, float ax, float ay, float az, float ind[3]) {
-    ind[0] = (ax - p.mn[0]) / (p.mx[0] - p.mn[0]) * 2.f - 1.f;
-    ind[1] = (ay - p.mn[1]) / (p.mx[1] - p.mn[1]) * 2.f - 1.f;
-    ind[2] = (az - p.mn[2]) / (p.mx[2] - p.mn[2]) * 2.f - 1.f;
+    const float m0 = __ldg(p.mn), m1 = __ldg(p.mn + 1), m2 = __ldg(p.mn + 2);
+    ind[0] = (ax - m0) / (__ldg(p.mx) - m0) * 2.f - 1.f;
+    ind[1] = (ay - m1) / (__ldg(p.mx + 1) - m1) * 2.f - 1.f;
+    ind[2] = (az - m2) / (__ldg(p.mx + 2) - m2) * 2.f - 1.f;
 }
 // plane 0 = xy (rows X, cols Y), 1 = xz (rows X, cols Z), 2 = yz (rows Y, cols Z)   [grids.py:148-150]
 __device__ __forceinline__ void plane_axes(int pl, const float ind[3], float &u, float &v) {
@@ -301,7 +302,7 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
         float *xin = XIN + (size_t)v * XI;
         xin[lane] = __ldg(p.anchor_feat + (size_t)i * FD + lane);
         if (lane < 4) {
-            const float vx = ax - p.cam[0], vy = ay - p.cam[1], vz = az - p.cam[2];
+            const float vx = ax - __ldg(p.cam), vy = ay - __ldg(p.cam + 1), vz = az - __ldg(p.cam + 2);
             const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
             const float dd = lane == 0 ? vx / dist : (lane == 1 ? vy / dist : (lane == 2 ? vz / dist : dist));
             xin[FD + lane] = dd;
@@ -864,6 +865,7 @@ int check_desc(const splatco_decode_desc *d) {
     SPLATCO_REQUIRE(d->app_dim >= 0 && (d->app_dim == 0 || d->app_vec), "decode: appearance vector missing");
     if (d->V == 0) return 0;
     SPLATCO_REQUIRE(d->anchor_feat && d->anchor && d->offset && d->scaling && d->vis, "decode: null input");
+    SPLATCO_REQUIRE(d->xyz_min && d->xyz_max && d->cam, "decode: null bbox / camera pointer");
     for (int l = 0; l <= d->level; ++l) {
         SPLATCO_REQUIRE(d->E[l] >= 2, "decode: plane edge %d too small", d->E[l]);
         for (int p = 0; p < 3; ++p) SPLATCO_REQUIRE(d->plane[3 * l + p], "decode: null plane (level %d)", l);
@@ -884,7 +886,8 @@ DecPtrs make_ptrs(const splatco_decode_desc *d) {
         p.E[l] = d->E[l];
         for (int q = 0; q < 3; ++q) p.plane[l][q] = d->plane[3 * l + q];
     }
-    for (int q = 0; q < 3; ++q) { p.att[q] = d->att[q]; p.mn[q] = d->xyz_min[q]; p.mx[q] = d->xyz_max[q]; p.cam[q] = d->cam[q]; }
+    for (int q = 0; q < 3; ++q) p.att[q] = d->att[q];
+    p.mn = d->xyz_min; p.mx = d->xyz_max; p.cam = d->cam;
     p.noise = d->noise;
     return p;
 }

@@ -27,7 +27,7 @@ class DecodeDesc(C.Structure):
         ("N", C.c_int32), ("V", C.c_int32), ("K", C.c_int32), ("rc", C.c_int32), ("level", C.c_int32),
         ("app_dim", C.c_int32),
         ("E", C.c_int32 * 3), ("use_dist", C.c_int32 * 3), ("update_running", C.c_int32),
-        ("xyz_min", C.c_float * 3), ("xyz_max", C.c_float * 3), ("cam", C.c_float * 3),
+        ("xyz_min", _vp), ("xyz_max", _vp), ("cam", _vp),
         ("bn_eps", C.c_float), ("bn_momentum", C.c_float),
         ("anchor_feat", _vp), ("anchor", _vp), ("offset", _vp), ("scaling", _vp), ("vis", _vp),
         ("plane", _vp * 9), ("att", _vp * 3),
@@ -99,7 +99,7 @@ def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, 
     for q in range(3):
         d.E[q] = cfg.E[q]
         d.use_dist[q] = int(cfg.use_dist[q])
-        d.xyz_min[q], d.xyz_max[q], d.cam[q] = cfg.xyz_min[q], cfg.xyz_max[q], cfg.cam[q]
+    d.xyz_min, d.xyz_max, d.cam = cfg.xyz_min.data_ptr(), cfg.xyz_max.data_ptr(), cfg.cam.data_ptr()
     d.update_running = int(cfg.update_running)
     d.bn_eps, d.bn_momentum = cfg.bn_eps, cfg.bn_momentum
     d.anchor_feat, d.anchor, d.offset, d.scaling = (t.data_ptr() for t in (anchor_feat, anchor, offset, scaling))
@@ -159,7 +159,7 @@ class _FusedDecode(torch.autograd.Function):
                 check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
                                             stream), "splatco_decode_emit")
         ctx.cfg, ctx.desc, ctx.ws, ctx.M, ctx.V = cfg, desc, ws, M, V
-        ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise)           # keeps every pointer in desc alive
+        ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise, cfg.xyz_min, cfg.xyz_max, cfg.cam)           # keeps every pointer in desc alive
         ctx.shapes = [t.shape for t in (anchor_feat, anchor, offset, scaling)]
         ctx.has_app = app_vec is not None
         ctx.mark_non_differentiable(mask)
@@ -304,10 +304,9 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
             raise NotImplementedError("splatco_b200 decode supports cubic plane grids only (world_size = [s, s, s])")
     cfg.use_dist = [bool(pc.add_opacity_dist), bool(pc.add_cov_dist), bool(pc.add_color_dist)]
     cfg.app_dim = int(pc.appearance_dim) if pc.appearance_dim else 0
-    mn = k0s[0].xyz_min.detach().float().cpu().tolist()
-    mx = k0s[0].xyz_max.detach().float().cpu().tolist()
-    cfg.xyz_min, cfg.xyz_max = mn, mx
-    cfg.cam = viewpoint_camera.camera_center.detach().float().cpu().tolist()
+    # bbox and camera centre stay on the device (the kernels read them there): no host sync
+    cfg.xyz_min, cfg.xyz_max = _c(k0s[0].xyz_min), _c(k0s[0].xyz_max)
+    cfg.cam = _c(viewpoint_camera.camera_center)
     bn0 = feat.models[0][0]
     cfg.bn_eps, cfg.bn_momentum = float(bn0.eps), float(bn0.momentum if bn0.momentum is not None else 0.1)
     cfg.update_running = bool(update_running)
