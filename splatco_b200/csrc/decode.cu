@@ -39,11 +39,12 @@ inline DecDims dec_dims(int V, int rc, int level) {
 
 }  // namespace splatco
 #include "decode_tc.cuh"
+#include "decode_tc_bwd.cuh"
 namespace splatco {
 
 // ---- forward workspace -------------------------------------------------------------------------------
 enum FwdChunk { F_X, F_STATS, F_MU, F_RSTD, F_WPT, F_WCT, F_BGEO, F_W1T, F_B1E, F_W2T, F_B2, F_WPG, F_WCG,
-                F_XIN, F_H, F_Z, F_MASKBITS, F_OFFS, F_BSUM, F_BOFF, F_TOTAL, F_XT, F_BA, F_W1B, F_W2B, F_NCHUNK };
+                F_XIN, F_H, F_Z, F_MASKBITS, F_OFFS, F_BSUM, F_BOFF, F_TOTAL, F_XT, F_BA, F_W1B, F_W2B, F_W2R, F_W1R, F_WPCR, F_NCHUNK };
 
 static size_t dec_fwd_offsets(const DecDims &d, size_t off[F_NCHUNK + 1]) {
     const size_t V = (size_t)(d.V > 0 ? d.V : 0);
@@ -63,6 +64,7 @@ static size_t dec_fwd_offsets(const DecDims &d, size_t off[F_NCHUNK + 1]) {
     const size_t ntiles = (V + TC_ROWS - 1) / TC_ROWS;
     put(F_XT, d.rc <= TC_MAX_RC ? ntiles * tc_tile_chunks(d.DP) * TC_CHUNK : 0);
     put(F_BA, 2 * TC_BA_HALF); put(F_W1B, 2 * TC_W1_HALF); put(F_W2B, 2 * TC_W2_HALF);
+    put(F_W2R, 2 * TCB_W2R_HALF); put(F_W1R, 2 * TCB_W1R_HALF); put(F_WPCR, 2 * TCB_WPC_HALF);   // backward-chain weight tiles
     off[F_NCHUNK] = o;
     return o;
 }
@@ -815,7 +817,7 @@ struct FwdView {
     double *stats;
     uint32_t *maskbits, *offs, *bsum, *boff, *total;
     float *XT;
-    uint8_t *BA, *W1B, *W2B;
+    uint8_t *BA, *W1B, *W2B, *W2R, *W1R, *WPCR;
 };
 FwdView fwd_view(void *ws, const DecDims &d) {
     size_t off[F_NCHUNK + 1];
@@ -834,6 +836,7 @@ FwdView fwd_view(void *ws, const DecDims &d) {
     v.total = (uint32_t *)(b + off[F_TOTAL]);
     v.XT = (float *)(b + off[F_XT]);
     v.BA = (uint8_t *)(b + off[F_BA]); v.W1B = (uint8_t *)(b + off[F_W1B]); v.W2B = (uint8_t *)(b + off[F_W2B]);
+    v.W2R = (uint8_t *)(b + off[F_W2R]); v.W1R = (uint8_t *)(b + off[F_W1R]); v.WPCR = (uint8_t *)(b + off[F_WPCR]);
     return v;
 }
 
@@ -945,6 +948,8 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
         // fused tcgen05 path: geo -> hidden -> heads -> activations in one persistent kernel
         dec_tc_pack_kernel<<<1, 256, 0, st>>>(dd.DP, f.WpT, f.WcT, f.W1T, f.W2T, f.BA, f.W1B, f.W2B);
         SPLATCO_CHECK_LAUNCH();
+        dec_tc_pack_bwd_kernel<<<1, 256, 0, st>>>(dd.DP, f.W2T, f.W1T, f.WpG, f.WcG, f.W2R, f.W1R, f.WPCR);   // for the backward
+        SPLATCO_CHECK_LAUNCH();
         static bool attr_set = false;
         if (!attr_set) {
             SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
@@ -1018,34 +1023,52 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     dec_bwd_uncompact_kernel<<<ceil_div(V, UNC_ROWS), UNC_ROWS * KO, 0, st>>>(V, LDX, DP, f.X, f.Z, f.maskbits, f.offs, d_xyz, d_color,
                                                               d_opacity, d_scaling, d_rot, d_neural_opacity, b.DZ, b.DGA);
     SPLATCO_CHECK_LAUNCH();
-    // dH = (dZ W2) * [H > 0];   gW2T += H^T dZ;   gb2 = colsum(dZ)
-    // (W2 is block-diagonal: head h maps hidden 32h..32h+31 to its own output columns, so each product is
-    //  three narrow GEMMs instead of one dense 96 x 112)
+    const bool use_tc = dd.rc <= TC_MAX_RC;
+    // split-K reduction over anchors  C[M,N] += A^T B  (weight gradients, S1)
+    auto tn64 = [&](int M, int N, const float *A, int lda, const float *B, int ldb, float *C, int ldc) -> int {
+        dim3 grid(ceil_div(M, 64), ceil_div(N, 64), ceil_div(V, KCH));
+        sgemm_tn64_kernel<<<grid, 256, 0, st>>>(M, N, V, A, lda, B, ldb, C, ldc, KCH);
+        SPLATCO_CHECK_LAUNCH();
+        return 0;
+    };
+    if (use_tc) {
+        // row chain on tensor cores: dH = (dZ W2).[H>0], dX = dH W1, dxhat = dgeo (gamma W); gb2, gb1, S0 in its epilogues
+        static bool attr_set = false;
+        if (!attr_set) {
+            SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCB_SMEM));
+            attr_set = true;
+        }
+        dec_tc_bwd_kernel<<<min(ceil_div(V, TC_ROWS), 148), TC_ROWS, TCB_SMEM, st>>>(V, DP, LDX, b.DZ, f.H, f.W2R, f.W1R, f.WPCR,
+                                                                                    b.DH, b.DX, b.DXH, b.gb2, b.gb1, b.S0);
+        SPLATCO_CHECK_LAUNCH();
+    } else {
+        // SIMT chain.  W2 is block-diagonal: three narrow GEMMs instead of one dense 96 x 112.
+        for (int hd = 0; hd < 3; ++hd) {
+            const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
+            if (sgemm<false, true>(st, V, 32, nj, b.DZ + j0, ZD, f.W2T + (size_t)i0 * ZD + j0, ZD, b.DH + i0, HD, nullptr, 0,
+                                   f.H + i0, HD)) return -2;
+        }
+        if (sgemm<false, true>(st, V, XI, HD, b.DH, HD, f.W1T, HD, b.DX, XI)) return -2;
+        if (sgemm<false, false>(st, V, DP, 32, b.DX + 36, XI, f.WpG, DP, b.DXH, LDX)) return -2;
+        if (sgemm<false, false>(st, V, GD, 32, b.DX + 68, XI, f.WcG, GD, b.DXH + DP, LDX)) return -2;
+        colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 128);
+        SPLATCO_CHECK_LAUNCH();
+        colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, HD, b.DH, HD, b.gb1, 128);
+        SPLATCO_CHECK_LAUNCH();
+        colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, 64, b.DX + 36, XI, b.S0, 128);
+        SPLATCO_CHECK_LAUNCH();
+    }
+    // weight gradients: gW2T += H^T dZ (block-diagonal), gW1T += X100^T dH, S1raw = dgeo^T X (both branches)
     for (int hd = 0; hd < 3; ++hd) {
         const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
-        if (sgemm<false, true>(st, V, 32, nj, b.DZ + j0, ZD, f.W2T + (size_t)i0 * ZD + j0, ZD, b.DH + i0, HD, nullptr, 0,
-                               f.H + i0, HD)) return -2;
-        if (sgemm<true, false>(st, 32, nj, V, f.H + i0, HD, b.DZ + j0, ZD, b.gW2T + (size_t)i0 * ZD + j0, ZD, nullptr, 0,
-                               nullptr, 0, KCH)) return -2;
+        if (tn64(32, nj, f.H + i0, HD, b.DZ + j0, ZD, b.gW2T + (size_t)i0 * ZD + j0, ZD)) return -2;
     }
-    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, ZD, b.DZ, ZD, b.gb2, 128);
-    SPLATCO_CHECK_LAUNCH();
-    // dX100 = dH W1;   gW1T += X100^T dH;   gb1 = colsum(dH)
-    if (sgemm<false, true>(st, V, XI, HD, b.DH, HD, f.W1T, HD, b.DX, XI)) return -2;
-    if (sgemm<true, false>(st, XI, HD, V, f.XIN, XI, b.DH, HD, b.gW1T, HD, nullptr, 0, nullptr, 0, KCH)) return -2;
-    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, HD, b.DH, HD, b.gb1, 128);
-    SPLATCO_CHECK_LAUNCH();
-    // S1raw = dgeo^T X (both branches), S0 = colsum(dgeo)
-    if (sgemm<true, false>(st, 32, DP, V, b.DX + 36, XI, f.X, LDX, b.S1, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
-    if (sgemm<true, false>(st, 32, GD, V, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX, nullptr, 0, nullptr, 0, KCH)) return -2;
-    colsum_kernel<<<dim3(ceil_div(V, 128), 1), 128, 0, st>>>(V, 64, b.DX + 36, XI, b.S0, 128);
-    SPLATCO_CHECK_LAUNCH();
+    if (tn64(XI, HD, f.XIN, XI, b.DH, HD, b.gW1T, HD)) return -2;
+    if (tn64(32, DP, b.DX + 36, XI, f.X, LDX, b.S1, LDX)) return -2;
+    if (tn64(32, GD, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX)) return -2;
     dec_bwd_fold_kernel<<<1, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                            b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();
-    // dxhat = dgeo (gamma W)  for both branches
-    if (sgemm<false, false>(st, V, DP, 32, b.DX + 36, XI, f.WpG, DP, b.DXH, LDX)) return -2;
-    if (sgemm<false, false>(st, V, GD, 32, b.DX + 68, XI, f.WcG, GD, b.DXH + DP, LDX)) return -2;
     dec_bwd_inputs_kernel<<<gather_grid(V), GATHER_WARPS * 32, 0, st>>>(p, gi, V, dd.rc, DP, LDX, f.X, f.XIN, f.mu, f.rstd,
                                                                         b.m1, b.m2, b.DXH, b.DX, b.DGA);
     SPLATCO_CHECK_LAUNCH();
