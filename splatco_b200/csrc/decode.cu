@@ -1024,13 +1024,6 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
                                                               d_opacity, d_scaling, d_rot, d_neural_opacity, b.DZ, b.DGA);
     SPLATCO_CHECK_LAUNCH();
     const bool use_tc = dd.rc <= TC_MAX_RC;
-    // split-K reduction over anchors  C[M,N] += A^T B  (weight gradients, S1)
-    auto tn64 = [&](int M, int N, const float *A, int lda, const float *B, int ldb, float *C, int ldc) -> int {
-        dim3 grid(ceil_div(M, 64), ceil_div(N, 64), ceil_div(V, KCH));
-        sgemm_tn64_kernel<<<grid, 256, 0, st>>>(M, N, V, A, lda, B, ldb, C, ldc, KCH);
-        SPLATCO_CHECK_LAUNCH();
-        return 0;
-    };
     if (use_tc) {
         // row chain on tensor cores: dH = (dZ W2).[H>0], dX = dH W1, dxhat = dgeo (gamma W); gb2, gb1, S0 in its epilogues
         static bool attr_set = false;
@@ -1059,13 +1052,26 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
         SPLATCO_CHECK_LAUNCH();
     }
     // weight gradients: gW2T += H^T dZ (block-diagonal), gW1T += X100^T dH, S1raw = dgeo^T X (both branches)
-    for (int hd = 0; hd < 3; ++hd) {
-        const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
-        if (tn64(32, nj, f.H + i0, HD, b.DZ + j0, ZD, b.gW2T + (size_t)i0 * ZD + j0, ZD)) return -2;
+    {
+        TnGroup grp;
+        grp.count = 0;
+        int tiles = 0;
+        auto add = [&](int M, int N, const float *A, int lda, const float *B, int ldb, float *C, int ldc) {
+            TnProblem &q = grp.p[grp.count++];
+            q.A = A; q.B = B; q.C = C; q.M = M; q.N = N; q.lda = lda; q.ldb = ldb; q.ldc = ldc;
+            q.tile0 = tiles; q.tiles_n = ceil_div(N, 64);
+            tiles += ceil_div(M, 64) * q.tiles_n;
+        };
+        for (int hd = 0; hd < 3; ++hd) {
+            const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
+            add(32, nj, f.H + i0, HD, b.DZ + j0, ZD, b.gW2T + (size_t)i0 * ZD + j0, ZD);
+        }
+        add(XI, HD, f.XIN, XI, b.DH, HD, b.gW1T, HD);
+        add(32, DP, b.DX + 36, XI, f.X, LDX, b.S1, LDX);
+        add(32, GD, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX);
+        sgemm_tn64_grouped_kernel<<<dim3(ceil_div(V, KCH), tiles), 256, 0, st>>>(grp, V, KCH);
+        SPLATCO_CHECK_LAUNCH();
     }
-    if (tn64(XI, HD, f.XIN, XI, b.DH, HD, b.gW1T, HD)) return -2;
-    if (tn64(32, DP, b.DX + 36, XI, f.X, LDX, b.S1, LDX)) return -2;
-    if (tn64(32, GD, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX)) return -2;
     dec_bwd_fold_kernel<<<1, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                            b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();

@@ -247,15 +247,30 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
-// ---- split-K  C[M,N] += A^T B  with 64x64 tiles and 4x4 register blocks (weight-gradient reductions over anchors) ----
+// ---- grouped split-K  C_p[M,N] += A_p^T B_p  (weight-gradient reductions over anchors) ------------------------
+// All products of one backward pass share K = V, so they are launched as ONE grid: blockIdx.y walks the
+// 64x64 output tiles of every problem, blockIdx.x the K slices.  Each problem alone is a single wave of
+// latency-bound CTAs; together they keep ~10 CTAs per SM in flight.  4x4 register blocks.
+struct TnProblem { const float *A; const float *B; float *C; int M, N, lda, ldb, ldc, tile0, tiles_n; };
+constexpr int TN_MAX_PROBLEMS = 8;
+struct TnGroup { TnProblem p[TN_MAX_PROBLEMS]; int count; };
+
 __global__ void __launch_bounds__(256)
-sgemm_tn64_kernel(int M, int N, int K, const float *__restrict__ A, int lda, const float *__restrict__ B, int ldb,
-                  float *__restrict__ C, int ldc, int kchunk) {
+sgemm_tn64_grouped_kernel(TnGroup g, int K, int kchunk) {
     __shared__ __align__(16) float As[16][68];
     __shared__ __align__(16) float Bs[16][68];
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < TN_MAX_PROBLEMS; ++i)
+        if (i < g.count && (int)blockIdx.y >= g.p[i].tile0) pi = i;
+    const TnProblem &pr = g.p[pi];
+    const int t = blockIdx.y - pr.tile0;
+    const int m0 = (t / pr.tiles_n) * 64, n0 = (t % pr.tiles_n) * 64;
+    const int M = pr.M, N = pr.N, lda = pr.lda, ldb = pr.ldb;
+    const float *__restrict__ A = pr.A;
+    const float *__restrict__ B = pr.B;
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    const int kbeg = blockIdx.x * kchunk, kend = min(K, kbeg + kchunk);
     const int ty = tid >> 4, tx = tid & 15;
     float acc[4][4] = {};
     for (int k0 = kbeg; k0 < kend; k0 += 16) {
@@ -279,6 +294,8 @@ sgemm_tn64_kernel(int M, int N, int K, const float *__restrict__ A, int lda, con
         }
         __syncthreads();
     }
+    float *__restrict__ C = pr.C;
+    const int ldc = pr.ldc;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + ty * 4 + i;
