@@ -226,10 +226,13 @@ def triplane_attention(x, w_ca1, w_ca2, w_sa):
     """TriPlaneAttention.forward (scene/grids.py:22-64) evaluated from the module's weights with plain
     reductions: the module's AdaptiveAvg/MaxPool2d(1) run one thread per channel over the whole plane
     (14 ms at plane_size 2500), `mean`/`amax` over (H, W) compute the same numbers in microseconds."""
-    avg = x.mean(dim=(2, 3), keepdim=True)
-    mx = x.amax(dim=(2, 3), keepdim=True)
     F = torch.nn.functional
-    ca = torch.sigmoid(F.conv2d(F.relu(F.conv2d(avg, w_ca1)), w_ca2) + F.conv2d(F.relu(F.conv2d(mx, w_ca1)), w_ca2))
+    C = x.shape[1]
+    # channel attention: the two 1x1 convolutions act on the pooled [C] vectors -> two tiny matmuls
+    # (each F.conv2d call costs ~1 ms of host time in cuDNN's plan lookup, which starved the GPU)
+    pooled = torch.stack([x.mean(dim=(2, 3)).reshape(C), x.amax(dim=(2, 3)).reshape(C)], dim=1)      # [C, 2]
+    w1, w2 = w_ca1.reshape(w_ca1.shape[0], C), w_ca2.reshape(C, w_ca2.shape[1])
+    ca = torch.sigmoid((w2 @ F.relu(w1 @ pooled)).sum(dim=1)).reshape(1, C, 1, 1)
     x = ca * x
     s = torch.cat([x.mean(dim=1, keepdim=True), x.amax(dim=1, keepdim=True)], dim=1)
     sa = torch.sigmoid(F.conv2d(s, w_sa, padding=w_sa.shape[-1] // 2))
