@@ -134,9 +134,12 @@ typedef struct splatco_decode_desc {
                                               levels >= 1 (scene/grids.py:159-164), or NULL (Q = 0)     */
 } splatco_decode_desc;
 
-/* Gradient destinations (same shapes as the inputs).  anchor_feat/anchor/offset/scaling must be
- * zero-filled [N,*] arrays (visible rows are overwritten); plane/att must be zero-filled (atomics
- * accumulate); the parameter gradients are overwritten.  NULL entries are skipped. */
+/* Gradient destinations (same shapes as the inputs).  EVERY destination is ACCUMULATED into (+=):
+ * the caller zero-fills a buffer once and may hand the same buffer to the decode backward of every
+ * view of an iteration (train.py:171-240 sums the mv views' losses before one backward), which
+ * removes the per-view N-row / plane-sized temporaries and the autograd additions between them.
+ * anchor_feat/anchor/offset/scaling are [N,*] (only visible rows are touched); plane/att receive
+ * bilinear scatter atomics.  NULL plane/att/parameter entries are skipped. */
 typedef struct splatco_decode_grads {
     float *anchor_feat, *anchor, *offset, *scaling;
     float *plane[9];

@@ -1,0 +1,76 @@
+"""Gradient buffers shared by the decode nodes of ONE backward pass.
+
+The reference sums the losses of the `--mv` views and calls backward once (train.py:199,240); its
+autograd then materialises, per view, N-row gradients for `_anchor_feat/_anchor/_offset`, plane-sized
+gradients and ~50 small weight gradients, and adds them pairwise (SURVEY.md §7 "dense-grad hidden
+cost").  `splatco_decode_bwd` accumulates (+=) into its destinations, so all decode nodes of a
+backward pass that were fed the SAME input tensor can write into ONE zero-filled buffer: the first
+node that runs hands the buffer to autograd, the later ones add into it in place and return None.
+
+Why this is safe: a consumer of that gradient (AccumulateGrad of a leaf, or the grad_fn of a non-leaf
+such as the cached TriPlaneAttention output) has one incoming edge per decode node that used the
+tensor, and the engine runs it only after all of them have run — i.e. after the last in-place add.
+Buffers are keyed on the identity of the forward input objects (kept alive by the nodes), inputs that
+do not require grad are never shared, and the table is dropped by a callback the engine runs at the
+end of the backward pass (`queue_callback`), so nothing leaks into the next pass.
+"""
+from __future__ import annotations
+
+import threading
+
+import torch
+from torch.autograd import Variable
+
+_lock = threading.Lock()
+_passes = {}          # device index -> {key: (flat buffer, offset in floats)}
+_ALIGN = 64           # floats (256 bytes): every carved buffer keeps the alignment of a fresh allocation
+
+
+def _end_of_pass(index):
+    with _lock:
+        _passes.pop(index, None)
+
+
+def acquire(device, requests, want_views=False):
+    """requests: list of (key or None, shape).  Returns a list of (pointer, ret): the address to
+    accumulate into and what to return to autograd for that input (None when an earlier node of this
+    backward pass already returned the buffer; do not keep `ret`: autograd adopts it as .grad without a
+    copy only while nobody else holds it).  key None = private buffer, never shared.  With
+    want_views=True the entries are (pointer, ret, buffer-as-tensor) (host-logic tests)."""
+    device = torch.device(device)
+    index = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
+    with _lock:
+        table = _passes.get(index)
+        fresh_pass = table is None
+        if fresh_pass:
+            table = _passes[index] = {}
+    if fresh_pass:
+        try:
+            Variable._execution_engine.queue_callback(lambda: _end_of_pass(index))
+        except RuntimeError:
+            # not inside an engine run (direct call of backward in a test): nothing may be shared
+            _end_of_pass(index)
+            table = {}
+    out = [None] * len(requests)
+    todo, total = [], 0
+    for n, (key, shape) in enumerate(requests):
+        hit = table.get(key) if key is not None else None
+        if hit is not None:
+            flat, off, numel = hit
+            out[n] = (flat.data_ptr() + 4 * off, None, flat[off:off + numel].view(shape)) if want_views else \
+                     (flat.data_ptr() + 4 * off, None)
+        else:
+            numel = 1
+            for s in shape:
+                numel *= int(s)
+            todo.append((n, key, shape, total, numel))
+            total += (numel + _ALIGN - 1) // _ALIGN * _ALIGN
+    if todo:
+        flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)      # ONE fill kernel
+        base = flat.data_ptr()
+        for n, key, shape, off, numel in todo:
+            buf = flat[off:off + numel].view(shape)
+            out[n] = (base + 4 * off, buf, buf) if want_views else (base + 4 * off, buf)
+            if key is not None:
+                table[key] = (flat, off, numel)
+    return out

@@ -675,7 +675,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
         for (int e = tid; e < 32 * d; e += 256) {
             const int o = e / d, cl = e - o * d, c = base + cl;
             const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[o]);
-            if (gw.lin_w[l]) gw.lin_w[l][o * d + cl] = w.bn_w[l][cl] * s1 + w.bn_b[l][cl] * S0[o];
+            if (gw.lin_w[l]) gw.lin_w[l][o * d + cl] += w.bn_w[l][cl] * s1 + w.bn_b[l][cl] * S0[o];
         }
         for (int cl = tid; cl < d; cl += 256) {
             const int c = base + cl;
@@ -685,15 +685,15 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
                 gg = fmaf(w.lin_w[l][o * d + cl], s1, gg);
                 gb = fmaf(w.lin_w[l][o * d + cl], S0[o], gb);
             }
-            if (gw.bn_w[l]) gw.bn_w[l][cl] = gg;
-            if (gw.bn_b[l]) gw.bn_b[l][cl] = gb;
+            if (gw.bn_w[l]) gw.bn_w[l][cl] += gg;
+            if (gw.bn_b[l]) gw.bn_b[l][cl] += gb;
         }
-        if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] = S0[tid];
+        if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] += S0[tid];
         // context branch
         for (int e = tid; e < 32 * GD; e += 256) {
             const int o = e / GD, g = e - o * GD, c = DP + g;
             const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[32 + o]);
-            if (gw.clin_w[l]) gw.clin_w[l][o * GD + g] = w.cbn_w[l][g] * s1 + w.cbn_b[l][g] * S0[32 + o];
+            if (gw.clin_w[l]) gw.clin_w[l][o * GD + g] += w.cbn_w[l][g] * s1 + w.cbn_b[l][g] * S0[32 + o];
         }
         for (int g = tid; g < GD; g += 256) {
             const int c = DP + g;
@@ -703,10 +703,10 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
                 gg = fmaf(w.clin_w[l][o * GD + g], s1, gg);
                 gb = fmaf(w.clin_w[l][o * GD + g], S0[32 + o], gb);
             }
-            if (gw.cbn_w[l]) gw.cbn_w[l][g] = gg;
-            if (gw.cbn_b[l]) gw.cbn_b[l][g] = gb;
+            if (gw.cbn_w[l]) gw.cbn_w[l][g] += gg;
+            if (gw.cbn_b[l]) gw.cbn_b[l][g] += gb;
         }
-        if (tid < 32 && gw.clin_b[l]) gw.clin_b[l][tid] = S0[32 + tid];
+        if (tid < 32 && gw.clin_b[l]) gw.clin_b[l][tid] += S0[32 + tid];
     }
     // heads: un-fold gW1T[k][n] / gW2T[i][j] into torch layouts
     for (int hd = 0; hd < 3; ++hd) {
@@ -722,18 +722,18 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
                 else if (dd && col == 35) v = gW1T[35 * HD + n];
                 else if (col < 35 + dd + 64) v = gW1T[(36 + col - 35 - dd) * HD + n];
                 else v = gb1[n] * w.app_vec[col - 35 - dd - 64];
-                gw.w1[hd][e] = v;
+                gw.w1[hd][e] += v;
             }
-        if (gw.b1[hd] && tid < 32) gw.b1[hd][tid] = gb1[hd * 32 + tid];
+        if (gw.b1[hd] && tid < 32) gw.b1[hd][tid] += gb1[hd * 32 + tid];
         const int nout = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO);
         const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO);
         if (gw.w2[hd])
             for (int e = tid; e < nout * 32; e += 256) {
                 const int j = e >> 5, ii = e & 31;
-                gw.w2[hd][e] = gW2T[(hd * 32 + ii) * ZD + j0 + j];
+                gw.w2[hd][e] += gW2T[(hd * 32 + ii) * ZD + j0 + j];
             }
         if (gw.b2[hd])
-            for (int j = tid; j < nout; j += 256) gw.b2[hd][j] = gb2[j0 + j];
+            for (int j = tid; j < nout; j += 256) gw.b2[hd][j] += gb2[j0 + j];
     }
     if (gw.app_vec && w.app_dim > 0) {
         const int dd = w.use_dist[2];
@@ -741,7 +741,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
         for (int a = tid; a < w.app_dim; a += 256) {
             float s = 0.f;
             for (int o = 0; o < 32; ++o) s = fmaf(w.w1[2][o * in_h + 35 + dd + 64 + a], gb1[64 + o], s);
-            gw.app_vec[a] = s;
+            gw.app_vec[a] += s;
         }
     }
 }
@@ -750,7 +750,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
 // bilinear scatter into the plane gradients, and the per-anchor rows of the N-row gradient tensors.
 // One warp per visible anchor (same mapping as the gather).
 struct DecInputGrads {
-    float *anchor_feat, *anchor, *offset, *scaling;     // [N,*], visible rows overwritten
+    float *anchor_feat, *anchor, *offset, *scaling;     // [N,*], visible rows accumulated (+=)
     float *plane[3][3];
     float *att[3];
 };
@@ -794,13 +794,13 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
                 if (base) bilin_scatter(base + (size_t)ch * E * E, b, dx);
             } else {
                 const int g = c - DP;
-                if (g < FD) gi.anchor_feat[(size_t)i * FD + g] = dx + dx100[g];
+                if (g < FD) gi.anchor_feat[(size_t)i * FD + g] += dx + dx100[g];
                 else if (g < FD + 3) {
                     const int q = g - FD;
-                    gi.anchor[3 * (size_t)i + q] = dx + dga[q] + (q == 0 ? dv0 : (q == 1 ? dv1 : dv2));
+                    gi.anchor[3 * (size_t)i + q] += dx + dga[q] + (q == 0 ? dv0 : (q == 1 ? dv1 : dv2));
                 }
-                else if (g < FD + 3 + 3 * KO) gi.offset[(size_t)i * 3 * KO + (g - FD - 3)] = dx + dga[3 + (g - FD - 3)];
-                else gi.scaling[(size_t)i * 6 + (g - FD - 3 - 3 * KO)] = dx + dga[33 + (g - FD - 3 - 3 * KO)];
+                else if (g < FD + 3 + 3 * KO) gi.offset[(size_t)i * 3 * KO + (g - FD - 3)] += dx + dga[3 + (g - FD - 3)];
+                else gi.scaling[(size_t)i * 6 + (g - FD - 3 - 3 * KO)] += dx + dga[33 + (g - FD - 3 - 3 * KO)];
             }
         }
     }

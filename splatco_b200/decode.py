@@ -11,10 +11,11 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 
 import torch
 
-from . import _lib
+from . import _gradacc, _lib
 from ._lib import check
 from .profiling import stage
 
@@ -85,7 +86,7 @@ def _c(t):
 class DecodeConfig:
     """Everything that is not a differentiable tensor input."""
     __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
-                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise")
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan")
 
 
 # order of the differentiable parameter list handed to the autograd Function
@@ -93,29 +94,65 @@ PER_LEVEL = ("xy", "xz", "yz", "bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b
 PER_HEAD = ("w1", "b1", "w2", "b2")
 
 
-def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, app_vec, level_params, head_params):
-    d = DecodeDesc()
-    d.N, d.V, d.K, d.rc, d.level, d.app_dim = cfg.N, V, cfg.K, cfg.rc, cfg.level, cfg.app_dim
-    for q in range(3):
-        d.E[q] = cfg.E[q]
-        d.use_dist[q] = int(cfg.use_dist[q])
-    d.xyz_min, d.xyz_max, d.cam = cfg.xyz_min.data_ptr(), cfg.xyz_max.data_ptr(), cfg.cam.data_ptr()
+_NGRAD = 53
+_GradPtrs = C.c_void_p * _NGRAD
+assert C.sizeof(_GradPtrs) == C.sizeof(DecodeGrads)
+_slot_cache = {}
+
+
+def _grad_slots(nl):
+    """forward-argument index (anchor_feat, anchor, offset, scaling, att x3, app_vec, per-level x11, heads x4)
+    -> pointer slot of splatco_decode_grads."""
+    m = _slot_cache.get(nl)
+    if m is None:
+        m = [0, 1, 2, 3, 13, 14, 15, 52]
+        for l in range(nl):
+            m += [4 + 3 * l, 5 + 3 * l, 6 + 3 * l] + [16 + 3 * j + l for j in range(8)]
+        for h in range(3):
+            m += [40 + 3 * j + h for j in range(4)]
+        _slot_cache[nl] = m
+    return m
+
+
+def _plain(t):
+    return t.dtype == torch.float32 and t.is_contiguous()
+
+
+def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, app_vec, params):
+    """Descriptor for one view.  The ~100 parameter / buffer pointers only change when the optimizer or
+    densification swaps tensors, so a filled template is cached on the config's plan and copied."""
+    plan = cfg.plan
+    key = (tuple([t.data_ptr() for t in params]), tuple(cfg.use_dist), cfg.app_dim, cfg.level, cfg.N)
+    if plan.desc_key != key:
+        d = DecodeDesc()
+        d.N, d.K, d.rc, d.level, d.app_dim = cfg.N, cfg.K, cfg.rc, cfg.level, cfg.app_dim
+        for q in range(3):
+            d.E[q] = cfg.E[q]
+            d.use_dist[q] = int(cfg.use_dist[q])
+        d.xyz_min, d.xyz_max = cfg.xyz_min.data_ptr(), cfg.xyz_max.data_ptr()
+        d.bn_eps, d.bn_momentum = cfg.bn_eps, cfg.bn_momentum
+        nl = cfg.level + 1
+        for l in range(nl):
+            lp = dict(zip(PER_LEVEL, params[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)]))
+            d.plane[3 * l], d.plane[3 * l + 1], d.plane[3 * l + 2] = (lp[k].data_ptr() for k in ("xy", "xz", "yz"))
+            for k in ("bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b"):
+                getattr(d, k)[l] = lp[k].data_ptr()
+            bufs = cfg.buffers[l]
+            for k in ("bn_rm", "bn_rv", "cbn_rm", "cbn_rv", "bn_nbt", "cbn_nbt"):
+                getattr(d, k)[l] = bufs[k].data_ptr() if bufs.get(k) is not None else None
+        base = nl * len(PER_LEVEL)
+        for h in range(3):
+            for n, k in enumerate(PER_HEAD):
+                getattr(d, k)[h] = params[base + h * 4 + n].data_ptr()
+        plan.desc_key, plan.desc = key, d
+    d = DecodeDesc.from_buffer_copy(plan.desc)
+    d.N, d.V = cfg.N, V
     d.update_running = int(cfg.update_running)
-    d.bn_eps, d.bn_momentum = cfg.bn_eps, cfg.bn_momentum
-    d.anchor_feat, d.anchor, d.offset, d.scaling = (t.data_ptr() for t in (anchor_feat, anchor, offset, scaling))
+    d.cam = cfg.cam.data_ptr()
+    d.anchor_feat, d.anchor, d.offset, d.scaling = (anchor_feat.data_ptr(), anchor.data_ptr(), offset.data_ptr(),
+                                                    scaling.data_ptr())
     d.vis = cfg.vis_idx.data_ptr()
-    for l, lp in enumerate(level_params):
-        d.plane[3 * l], d.plane[3 * l + 1], d.plane[3 * l + 2] = (lp[k].data_ptr() for k in ("xy", "xz", "yz"))
-        for k in ("bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b"):
-            getattr(d, k)[l] = lp[k].data_ptr()
-        bufs = cfg.buffers[l]
-        for k in ("bn_rm", "bn_rv", "cbn_rm", "cbn_rv", "bn_nbt", "cbn_nbt"):
-            getattr(d, k)[l] = bufs[k].data_ptr() if bufs.get(k) is not None else None
-    for q in range(3):
-        d.att[q] = att[q].data_ptr()
-    for h, hp in enumerate(head_params):
-        for k in PER_HEAD:
-            getattr(d, k)[h] = hp[k].data_ptr()
+    d.att[0], d.att[1], d.att[2] = att[0].data_ptr(), att[1].data_ptr(), att[2].data_ptr()
     d.app_vec = app_vec.data_ptr() if app_vec is not None else None
     d.noise = cfg.noise.data_ptr() if cfg.noise is not None else None
     return d
@@ -127,18 +164,14 @@ class _FusedDecode(torch.autograd.Function):
                 *params):
         L = _register()
         dev = anchor.device
-        nl = cfg.level + 1
-        tensors = [_c(t) for t in (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz)]
+        # kernels read fp32 contiguous memory; tensors that already are (the normal case) are used in place
+        tensors = [t if _plain(t) else _c(t) for t in (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz)]
         anchor_feat_c, anchor_c, offset_c, scaling_c, a_xy, a_xz, a_yz = tensors
-        app_c = _c(app_vec) if app_vec is not None else None
-        pc = [_c(t) for t in params]
-        level_params = [dict(zip(PER_LEVEL, pc[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)])) for l in range(nl)]
-        base = nl * len(PER_LEVEL)
-        head_params = [dict(zip(PER_HEAD, pc[base + h * 4: base + h * 4 + 4])) for h in range(3)]
+        app_c = None if app_vec is None else (app_vec if _plain(app_vec) else _c(app_vec))
+        pc = [t if _plain(t) else _c(t) for t in params]
         V = int(cfg.vis_idx.shape[0])
         K = cfg.K
-        desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c,
-                          level_params, head_params)
+        desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c, pc)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             ws = torch.empty(max(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
@@ -149,7 +182,7 @@ class _FusedDecode(torch.autograd.Function):
                 check(L.splatco_decode_fwd(C.byref(desc), _p(ws), _p(nopac), _p(mask), counter.data_ptr(), stream),
                       "splatco_decode_fwd")
             torch.cuda.current_stream(dev).synchronize()      # M sizes the outputs (the reference syncs here too: boolean indexing)
-            M = int(counter.item()) if V > 0 else 0
+            M = int(counter[0]) if V > 0 else 0
             xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
             color = torch.empty((M, 3), dtype=torch.float32, device=dev)
             opacity = torch.empty((M, 1), dtype=torch.float32, device=dev)
@@ -159,9 +192,10 @@ class _FusedDecode(torch.autograd.Function):
                 check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
                                             stream), "splatco_decode_emit")
         ctx.cfg, ctx.desc, ctx.ws, ctx.M, ctx.V = cfg, desc, ws, M, V
-        ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise, cfg.xyz_min, cfg.xyz_max, cfg.cam)           # keeps every pointer in desc alive
-        ctx.shapes = [t.shape for t in (anchor_feat, anchor, offset, scaling)]
-        ctx.has_app = app_vec is not None
+        # everything a pointer in desc refers to stays alive with the node
+        ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise, cfg.xyz_min, cfg.xyz_max, cfg.cam)
+        # the forward input OBJECTS: their identity keys the shared gradient buffers of a backward pass
+        ctx.origs = (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz, app_vec) + tuple(params)
         ctx.mark_non_differentiable(mask)
         return xyz, color, opacity, scl, rot, nopac, mask
 
@@ -172,49 +206,40 @@ class _FusedDecode(torch.autograd.Function):
         tensors, app_c, pc = ctx.keep[:3]
         dev = tensors[1].device
         nl = cfg.level + 1
-        N, K = cfg.N, cfg.K
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        g_feat, g_anchor, g_offset, g_scaling = z(N, 32), z(N, 3), z(N, K, 3), z(N, 6)
-        g_att = [torch.zeros_like(t) for t in tensors[4:7]]
-        g_params = []
-        for l in range(nl):
-            for k, t in zip(PER_LEVEL, pc[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)]):
-                g_params.append(torch.zeros_like(t) if k in ("xy", "xz", "yz") else torch.empty_like(t))
-        base = nl * len(PER_LEVEL)
-        for t in pc[base:]:
-            g_params.append(torch.empty_like(t))
-        g_app = torch.empty_like(app_c) if app_c is not None else None
-        gd = DecodeGrads()
-        gd.anchor_feat, gd.anchor, gd.offset, gd.scaling = (t.data_ptr() for t in (g_feat, g_anchor, g_offset, g_scaling))
-        for l in range(nl):
-            lp = dict(zip(PER_LEVEL, g_params[l * len(PER_LEVEL):(l + 1) * len(PER_LEVEL)]))
-            gd.plane[3 * l], gd.plane[3 * l + 1], gd.plane[3 * l + 2] = (lp[k].data_ptr() for k in ("xy", "xz", "yz"))
-            for k in ("bn_w", "bn_b", "lin_w", "lin_b", "cbn_w", "cbn_b", "clin_w", "clin_b"):
-                getattr(gd, k)[l] = lp[k].data_ptr()
-        for q in range(3):
-            gd.att[q] = g_att[q].data_ptr()
-        for h in range(3):
-            hp = dict(zip(PER_HEAD, g_params[base + h * 4: base + h * 4 + 4]))
-            for k in PER_HEAD:
-                getattr(gd, k)[h] = hp[k].data_ptr()
-        gd.app_vec = g_app.data_ptr() if g_app is not None else None
+        # One destination per differentiable input, in forward-argument order.  splatco_decode_bwd
+        # accumulates, so nodes of the same backward pass that were fed the same tensor share one
+        # zero-filled buffer (_gradacc): no per-view N-row / plane-sized temporaries, no autograd adds.
+        origs = ctx.origs                      # forward inputs 1.. (anchor_feat, ..., app_vec, *params)
+        need = ctx.needs_input_grad[1:]
+        shapes = [t.shape for t in tensors] + [app_c.shape if app_c is not None else None] + [t.shape for t in pc]
+        reqs, where = [], []
+        for n, (o, shp) in enumerate(zip(origs, shapes)):
+            if shp is None:
+                continue
+            reqs.append((id(o) if need[n] else None, shp))
+            where.append(n)
+        with torch.cuda.device(dev):
+            got = _gradacc.acquire(dev, reqs)
+        slots = _grad_slots(nl)
+        vals = [None] * _NGRAD
+        rets = [None] * len(origs)
+        for n, (ptr_n, ret) in zip(where, got):
+            vals[slots[n]] = ptr_n
+            rets[n] = ret if need[n] else None
+        del got
+        gd = _GradPtrs(*vals)                  # same memory layout as splatco_decode_grads (all pointers)
         if V > 0:
             ups = [_c(t) if t is not None else None for t in (g_xyz, g_color, g_opacity, g_scl, g_rot, g_nopac)]
             if M > 0:
+                z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
                 ups = [u if u is not None else z(*s) for u, s in zip(ups[:5], ((M, 3), (M, 3), (M, 1), (M, 3), (M, 4)))] + [ups[5]]
             stream = torch.cuda.current_stream(dev).cuda_stream
             with torch.cuda.device(dev):
                 bws = torch.empty(max(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
                 with stage("decode_bwd"):
                     check(L.splatco_decode_bwd(C.byref(desc), _p(ctx.ws), _p(bws), M, *[_p(u) for u in ups],
-                                               C.byref(gd), stream), "splatco_decode_bwd")
-        else:
-            for t in g_params:
-                t.zero_()
-            if g_app is not None:
-                g_app.zero_()
-        return (None, g_feat, g_anchor, g_offset, g_scaling, g_att[0], g_att[1], g_att[2],
-                g_app if ctx.has_app else None, *g_params)
+                                               gd, stream), "splatco_decode_bwd")
+        return (None, *rets)
 
 
 def _bn_lin(seq):
@@ -280,6 +305,58 @@ def _ta_cache_for(owner) -> _TACache:
     return c
 
 
+class _ModelPlan:
+    """Per-model state that survives between views: handles of the modules the decode reads (so the ~50
+    parameter tensors are fetched with dict lookups instead of nn.Module attribute resolution), the
+    static sizes, and the descriptor template (_fill_desc)."""
+    __slots__ = ("feat_ref", "level", "heads", "levels", "rc", "E", "xyz_min", "xyz_max", "bn_eps", "bn_momentum",
+                 "buffers", "ta_weights", "desc_key", "desc")
+
+
+_plans = {}
+
+
+def _par(module, name):
+    try:
+        return module._parameters[name]
+    except (AttributeError, KeyError):
+        return getattr(module, name)
+
+
+def _plan_for(pc, feat, level, heads) -> _ModelPlan:
+    plan = _plans.get(id(pc))
+    if (plan is not None and plan.feat_ref() is feat and plan.level == level
+            and all(a is b for a, b in zip(plan.heads, heads))):
+        return plan
+    k0s = feat.k0s
+    for l in range(level + 1):
+        pl = k0s[l]
+        if not (pl.xy_plane.shape[2] == pl.xy_plane.shape[3] == pl.xz_plane.shape[3] == pl.yz_plane.shape[2]):
+            raise NotImplementedError("splatco_b200 decode supports cubic plane grids only (world_size = [s, s, s])")
+    plan = _ModelPlan()
+    plan.feat_ref, plan.level, plan.heads = weakref.ref(feat), level, tuple(heads)
+    plan.rc = int(k0s[0].xy_plane.shape[1])
+    plan.E = [int(k0s[min(l, len(k0s) - 1)].xy_plane.shape[2]) for l in range(3)]
+    plan.xyz_min, plan.xyz_max = _c(k0s[0].xyz_min), _c(k0s[0].xyz_max)      # stay on the device: no host sync
+    bn0 = feat.models[0][0]
+    plan.bn_eps, plan.bn_momentum = float(bn0.eps), float(bn0.momentum if bn0.momentum is not None else 0.1)
+    plan.levels, plan.buffers = [], []
+    for l in range(level + 1):
+        bn, lin = _bn_lin(feat.models[l])
+        cbn, clin = _bn_lin(feat.CTX_models[l])
+        plan.levels.append((k0s[l], bn, lin, cbn, clin))
+        plan.buffers.append(dict(bn_rm=bn.running_mean, bn_rv=bn.running_var, cbn_rm=cbn.running_mean,
+                                 cbn_rv=cbn.running_var, bn_nbt=bn.num_batches_tracked,
+                                 cbn_nbt=cbn.num_batches_tracked))
+    ta = k0s[0].TA
+    plan.ta_weights = (ta.ca.sharedMLP[0], ta.ca.sharedMLP[2], ta.sa.conv)
+    plan.desc_key = plan.desc = None
+    if len(_plans) > 8:
+        _plans.clear()
+    _plans[id(pc)] = plan
+    return plan
+
+
 def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     """Read the reference model's attributes (duck-typed GaussianModel) into
     (cfg, differentiable inputs)."""
@@ -291,51 +368,38 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     dev = anchor.device
     if not anchor.is_cuda:
         raise RuntimeError("splatco_b200 decode needs CUDA tensors (no CPU fallback)")
-    fp = pc.feat_planes
-    feat = fp._feat
+    feat = pc.feat_planes._feat
     level = int(feat.activate_level)
-    k0s = feat.k0s
+    heads = (pc.get_opacity_mlp, pc.get_cov_mlp, pc.get_color_mlp)
+    plan = _plan_for(pc, feat, level, heads)
     cfg = DecodeConfig()
+    cfg.plan = plan
     cfg.N = int(anchor.shape[0])
     cfg.K = int(pc.n_offsets)
-    cfg.level = level
-    cfg.rc = int(k0s[0].xy_plane.shape[1])
-    cfg.E = [int(k0s[min(l, len(k0s) - 1)].xy_plane.shape[2]) for l in range(3)]
-    for l in range(level + 1):
-        pl = k0s[l]
-        if not (pl.xy_plane.shape[2] == pl.xy_plane.shape[3] == pl.xz_plane.shape[3] == pl.yz_plane.shape[2]):
-            raise NotImplementedError("splatco_b200 decode supports cubic plane grids only (world_size = [s, s, s])")
+    cfg.level, cfg.rc, cfg.E = level, plan.rc, plan.E
     cfg.use_dist = [bool(pc.add_opacity_dist), bool(pc.add_cov_dist), bool(pc.add_color_dist)]
     cfg.app_dim = int(pc.appearance_dim) if pc.appearance_dim else 0
-    # bbox and camera centre stay on the device (the kernels read them there): no host sync
-    cfg.xyz_min, cfg.xyz_max = _c(k0s[0].xyz_min), _c(k0s[0].xyz_max)
-    cfg.cam = _c(viewpoint_camera.camera_center)
-    bn0 = feat.models[0][0]
-    cfg.bn_eps, cfg.bn_momentum = float(bn0.eps), float(bn0.momentum if bn0.momentum is not None else 0.1)
+    cfg.xyz_min, cfg.xyz_max = plan.xyz_min, plan.xyz_max
+    cam = viewpoint_camera.camera_center
+    cfg.cam = cam if _plain(cam) else _c(cam)
+    cfg.bn_eps, cfg.bn_momentum = plan.bn_eps, plan.bn_momentum
     cfg.update_running = bool(update_running)
     if visible_mask is None:
         cfg.vis_idx = torch.arange(cfg.N, dtype=torch.int32, device=dev)
     else:
         cfg.vis_idx = torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
-    cfg.buffers = []
+    cfg.buffers = plan.buffers
     params = []
-    for l in range(level + 1):
-        bn, lin = _bn_lin(feat.models[l])
-        cbn, clin = _bn_lin(feat.CTX_models[l])
-        pl = k0s[l]
-        params += [pl.xy_plane, pl.xz_plane, pl.yz_plane, bn.weight, bn.bias, lin.weight, lin.bias,
-                   cbn.weight, cbn.bias, clin.weight, clin.bias]
-        cfg.buffers.append(dict(bn_rm=bn.running_mean, bn_rv=bn.running_var, cbn_rm=cbn.running_mean,
-                                cbn_rv=cbn.running_var, bn_nbt=bn.num_batches_tracked,
-                                cbn_nbt=cbn.num_batches_tracked))
-    for mlp in (pc.get_opacity_mlp, pc.get_cov_mlp, pc.get_color_mlp):
-        params += [mlp[0].weight, mlp[0].bias, mlp[2].weight, mlp[2].bias]
-    # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169), evaluated by the model's own module
-    pl0 = k0s[0]
+    for pl, bn, lin, cbn, clin in plan.levels:
+        params += [_par(pl, "xy_plane"), _par(pl, "xz_plane"), _par(pl, "yz_plane"), _par(bn, "weight"), _par(bn, "bias"),
+                   _par(lin, "weight"), _par(lin, "bias"), _par(cbn, "weight"), _par(cbn, "bias"),
+                   _par(clin, "weight"), _par(clin, "bias")]
+    for mlp in heads:
+        m0, m2 = mlp[0], mlp[2]
+        params += [_par(m0, "weight"), _par(m0, "bias"), _par(m2, "weight"), _par(m2, "bias")]
+    # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169)
     with stage("triplane_attention_torch"):
-        att = _ta_cache_for(pl0).get((pl0.xy_plane, pl0.xz_plane, pl0.yz_plane),
-                                     (pl0.TA.ca.sharedMLP[0].weight, pl0.TA.ca.sharedMLP[2].weight,
-                                      pl0.TA.sa.conv.weight))
+        att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
     app_vec = None
     if cfg.app_dim > 0:
         app_vec = pc.get_appearance.embedding.weight[int(viewpoint_camera.uid)]
