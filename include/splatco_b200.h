@@ -74,6 +74,16 @@ int splatco_preprocess_fwd(int P, const float *means3D, const float *scales, int
                            float scale_mod, const float *view, const float *proj, float tanfovx,
                            float tanfovy, int H, int W, int32_t *radii_out, void *geom,
                            int32_t *num_rendered_host, void *stream);
+/* Same, for callers whose live row count is still on the device: the input arrays (and geom, radii_out)
+ * are sized for P_max rows, *P_dev (device, e.g. splatco_decode_count_ptr) holds the number of valid
+ * rows; rows beyond it get radii 0 / no tiles.  Every later stage is then called with P = P_max.  Lets
+ * render() read the decode's survivor count M and the instance count R with ONE host sync. */
+int splatco_preprocess_fwd_counted(int P_max, const int32_t *P_dev, const float *means3D,
+                                   const float *scales, int scale_stride, const float *rots,
+                                   const float *opacities, const float *colors, float scale_mod,
+                                   const float *view, const float *proj, float tanfovx, float tanfovy,
+                                   int H, int W, int32_t *radii_out, void *geom,
+                                   int32_t *num_rendered_host, void *stream);
 
 /* ---- forward, stage 2: duplicateWithKeys + 64-bit radix sort + identifyTileRanges ------------
  * R must be the value produced by stage 1.  The stages are also exported individually so parity
@@ -157,7 +167,10 @@ size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level);
  * M_host (pinned) asynchronously if not NULL). */
 int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
                        int32_t *M_host, void *stream);
-/* Stage 2: stable compaction + post-processing into the M surviving Gaussians. */
+/* Device address (inside ws) of the survivor count M that splatco_decode_fwd leaves behind. */
+const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level);
+/* Stage 2: stable compaction + post-processing into the M surviving Gaussians.  M is only tested for
+ * zero: a caller that has not read M back yet passes output arrays with V*K rows and M = V*K. */
 int splatco_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
                         float *opacity, float *scaling, float *rot, void *stream);
 /* Backward of both stages.  d_neural_opacity ([V*K]) may be NULL. */
@@ -165,6 +178,25 @@ int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *b
                        const float *d_xyz, const float *d_color, const float *d_opacity,
                        const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
                        const splatco_decode_grads *g, void *stream);
+
+/* ---- TriPlaneAttention over the TA-level planes ---------------------------
+ * Replaces TriPlaneAttention.forward (scene/grids.py:22-64) as applied at scene/grids.py:166-169 to
+ * cat(xy_plane, xz_plane, yz_plane) of k0s[0]: channel attention (global avg + max pool -> 1x1 conv
+ * C -> hidden -> ReLU -> 1x1 conv -> sigmoid) then spatial attention (channel mean / max -> ksize x ksize
+ * conv, zero padding, no bias -> sigmoid).  Planes are [rc, E, E] each, C = 3*rc <= 32, hidden <= 8,
+ * ksize must be 7 (what the reference constructs).  w_ca1 [hidden, C], w_ca2 [C, hidden],
+ * w_sa [1, 2, 7, 7] are the Conv2d weights in torch layout.  fwd_ws keeps what the backward needs.
+ * splatco_ta_bwd ACCUMULATES (+=) into g_xy/g_xz/g_yz and the three weight gradients (NULL weight
+ * gradients are skipped), like splatco_decode_bwd. */
+size_t splatco_ta_fwd_ws_bytes(int rc, int E);
+size_t splatco_ta_bwd_ws_bytes(int rc, int E);
+int splatco_ta_fwd(int rc, int E, int hidden, int ksize, const float *xy, const float *xz, const float *yz,
+                   const float *w_ca1, const float *w_ca2, const float *w_sa, void *fwd_ws, float *out_xy,
+                   float *out_xz, float *out_yz, void *stream);
+int splatco_ta_bwd(int rc, int E, int hidden, int ksize, const float *xy, const float *xz, const float *yz,
+                   const float *w_ca1, const float *w_ca2, const float *w_sa, void *fwd_ws, void *bwd_ws,
+                   const float *g_out_xy, const float *g_out_xz, const float *g_out_yz, float *g_xy,
+                   float *g_xz, float *g_yz, float *g_w_ca1, float *g_w_ca2, float *g_w_sa, void *stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:

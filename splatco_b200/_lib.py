@@ -30,6 +30,7 @@ SIGNATURES = {
     "splatco_sorted_buffer_index": (_i, [_i, _i]),
     "splatco_visible_filter": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp]),
     "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
+    "splatco_preprocess_fwd_counted": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_binning": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "splatco_duplicate_with_keys": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_sort_pairs": (_i, [_i64, _i, _i, _vp, _vp]),
@@ -40,9 +41,14 @@ SIGNATURES = {
     # decode: descriptor / gradient structs are passed with ctypes.byref (see decode.py)
     "splatco_decode_fwd_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_decode_bwd_ws_bytes": (_sz, [_i, _i, _i]),
+    "splatco_decode_count_ptr": (_vp, [_vp, _i, _i, _i]),
     "splatco_decode_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_ta_fwd_ws_bytes": (_sz, [_i, _i]),
+    "splatco_ta_bwd_ws_bytes": (_sz, [_i, _i]),
+    "splatco_ta_fwd": (_i, [_i, _i, _i, _i] + [_vp] * 11),
+    "splatco_ta_bwd": (_i, [_i, _i, _i, _i] + [_vp] * 18),
     "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }
 

@@ -922,6 +922,11 @@ extern "C" size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level) {
     return dec_bwd_offsets(dec_dims(V, rc, level), off);
 }
 
+extern "C" const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level) {
+    if (!ws) return nullptr;
+    return reinterpret_cast<const int32_t *>(fwd_view(const_cast<void *>(ws), dec_dims(V, rc, level)).total);
+}
+
 extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
                                   int32_t *M_host, void *stream) {
     if (check_desc(d)) return -1;

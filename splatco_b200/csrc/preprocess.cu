@@ -156,7 +156,7 @@ visible_filter_kernel(int N, const float *__restrict__ means3D, const float *__r
 
 // ---- preprocess forward: also emits per-block tile-count sums (first level of the scan) ---------
 __global__ void __launch_bounds__(PRE_THREADS)
-preprocess_fwd_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ scales,
+preprocess_fwd_kernel(int P, const uint32_t *__restrict__ P_dev, const float *__restrict__ means3D, const float *__restrict__ scales,
                       int scale_stride, const float *__restrict__ rots,
                       const float *__restrict__ opacities, const float *__restrict__ colors, float mod,
                       const float *__restrict__ view, const float *__restrict__ proj, float tanfovx,
@@ -169,7 +169,11 @@ preprocess_fwd_kernel(int P, const float *__restrict__ means3D, const float *__r
     stage_cam(s_cam, view, proj);
     const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
     uint32_t t = 0;
-    if (i < P) {
+    // counted variant: the live row count is still on the device (decode's survivor count); rows in
+    // [count, P) of the caller's upper-bound buffers are uninitialised and become invisible Gaussians
+    const int live = P_dev ? min(P, (int)__ldg(P_dev)) : P;
+    if (i >= live && i < P) { radii[i] = 0; tiles[i] = 0; }
+    if (i < live) {
         const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
         const float *sp = scales + (size_t)scale_stride * i;
         const float4 q = *reinterpret_cast<const float4 *>(rots + 4 * (size_t)i);
@@ -349,11 +353,11 @@ extern "C" int splatco_visible_filter(int N, const float *means3D, const float *
     return 0;
 }
 
-extern "C" int splatco_preprocess_fwd(int P, const float *means3D, const float *scales, int scale_stride,
-                                      const float *rots, const float *opacities, const float *colors,
-                                      float scale_mod, const float *view, const float *proj,
-                                      float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
-                                      void *geom, int32_t *num_rendered_host, void *stream) {
+static int preprocess_fwd_impl(int P, const uint32_t *P_dev, const float *means3D, const float *scales, int scale_stride,
+                               const float *rots, const float *opacities, const float *colors,
+                               float scale_mod, const float *view, const float *proj,
+                               float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
+                               void *geom, int32_t *num_rendered_host, void *stream) {
     SPLATCO_REQUIRE(P >= 0 && H > 0 && W > 0, "preprocess_fwd: bad sizes P=%d H=%d W=%d", P, H, W);
     cudaStream_t st = (cudaStream_t)stream;
     if (P == 0) {
@@ -369,7 +373,7 @@ extern "C" int splatco_preprocess_fwd(int P, const float *means3D, const float *
     const float fx = (float)W / (2.0f * tanfovx), fy = (float)H / (2.0f * tanfovy);
     const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
     const int nb = ceil_div(P, PRE_THREADS);
-    preprocess_fwd_kernel<<<nb, PRE_THREADS, 0, st>>>(P, means3D, scales, scale_stride, rots, opacities, colors,
+    preprocess_fwd_kernel<<<nb, PRE_THREADS, 0, st>>>(P, P_dev, means3D, scales, scale_stride, rots, opacities, colors,
                                                       scale_mod, view, proj, tanfovx, tanfovy, fx, fy, H, W,
                                                       gx, gy, radii_out, g.rec, g.depths, g.tiles, g.block_sums);
     SPLATCO_CHECK_LAUNCH();
@@ -378,6 +382,27 @@ extern "C" int splatco_preprocess_fwd(int P, const float *means3D, const float *
     if (num_rendered_host)
         SPLATCO_CHECK_CUDA(cudaMemcpyAsync(num_rendered_host, g.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return 0;
+}
+
+extern "C" int splatco_preprocess_fwd(int P, const float *means3D, const float *scales, int scale_stride,
+                                      const float *rots, const float *opacities, const float *colors,
+                                      float scale_mod, const float *view, const float *proj,
+                                      float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
+                                      void *geom, int32_t *num_rendered_host, void *stream) {
+    return preprocess_fwd_impl(P, nullptr, means3D, scales, scale_stride, rots, opacities, colors, scale_mod, view, proj,
+                               tanfovx, tanfovy, H, W, radii_out, geom, num_rendered_host, stream);
+}
+
+extern "C" int splatco_preprocess_fwd_counted(int P_max, const int32_t *P_dev, const float *means3D,
+                                              const float *scales, int scale_stride, const float *rots,
+                                              const float *opacities, const float *colors, float scale_mod,
+                                              const float *view, const float *proj, float tanfovx,
+                                              float tanfovy, int H, int W, int32_t *radii_out, void *geom,
+                                              int32_t *num_rendered_host, void *stream) {
+    SPLATCO_REQUIRE(P_dev, "preprocess_fwd_counted: null device count");
+    return preprocess_fwd_impl(P_max, reinterpret_cast<const uint32_t *>(P_dev), means3D, scales, scale_stride, rots,
+                               opacities, colors, scale_mod, view, proj, tanfovx, tanfovy, H, W, radii_out, geom,
+                               num_rendered_host, stream);
 }
 
 extern "C" int splatco_preprocess_bwd(int P, const float *means3D, const float *scales, int scale_stride,

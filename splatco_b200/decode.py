@@ -86,7 +86,7 @@ def _c(t):
 class DecodeConfig:
     """Everything that is not a differentiable tensor input."""
     __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
-                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan")
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan", "raster")
 
 
 # order of the differentiable parameter list handed to the autograd Function
@@ -181,16 +181,29 @@ class _FusedDecode(torch.autograd.Function):
             with stage("decode_fwd"):
                 check(L.splatco_decode_fwd(C.byref(desc), _p(ws), _p(nopac), _p(mask), counter.data_ptr(), stream),
                       "splatco_decode_fwd")
-            torch.cuda.current_stream(dev).synchronize()      # M sizes the outputs (the reference syncs here too: boolean indexing)
-            M = int(counter[0]) if V > 0 else 0
-            xyz = torch.empty((M, 3), dtype=torch.float32, device=dev)
-            color = torch.empty((M, 3), dtype=torch.float32, device=dev)
-            opacity = torch.empty((M, 1), dtype=torch.float32, device=dev)
-            scl = torch.empty((M, 3), dtype=torch.float32, device=dev)
-            rot = torch.empty((M, 4), dtype=torch.float32, device=dev)
-            with stage("decode_emit"):
-                check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
-                                            stream), "splatco_decode_emit")
+            f32 = dict(dtype=torch.float32, device=dev)
+            if cfg.raster is not None and V > 0:
+                # render() path: compaction and the rasterizer's preprocess are queued on VK-row buffers with the
+                # survivor count still on the device, then ONE sync returns both M and the instance count R
+                # (the reference syncs twice here: boolean indexing, then num_rendered)
+                from . import diff_gaussian_rasterization as _dgr
+                VK = V * K
+                bufs = [torch.empty((VK, c), **f32) for c in (3, 3, 1, 3, 4)]
+                with stage("decode_emit"):
+                    check(L.splatco_decode_emit(C.byref(desc), _p(ws), VK, *[_p(b) for b in bufs], stream),
+                          "splatco_decode_emit")
+                sp = _dgr.preprocess_speculative(*bufs, L.splatco_decode_count_ptr(_p(ws), V, cfg.rc, cfg.level), cfg.raster)
+                torch.cuda.current_stream(dev).synchronize()
+                M = int(counter[0])
+                xyz, color, opacity, scl, rot = [b[:M] for b in bufs]
+                _dgr.publish_speculated(sp, M, (xyz, color, opacity, scl, rot))
+            else:
+                torch.cuda.current_stream(dev).synchronize()      # M sizes the outputs (the reference syncs here too: boolean indexing)
+                M = int(counter[0]) if V > 0 else 0
+                xyz, color, opacity, scl, rot = [torch.empty((M, c), **f32) for c in (3, 3, 1, 3, 4)]
+                with stage("decode_emit"):
+                    check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
+                                                stream), "splatco_decode_emit")
         ctx.cfg, ctx.desc, ctx.ws, ctx.M, ctx.V = cfg, desc, ws, M, V
         # everything a pointer in desc refers to stays alive with the node
         ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise, cfg.xyz_min, cfg.xyz_max, cfg.cam)
@@ -247,21 +260,54 @@ def _bn_lin(seq):
     return bn, lin
 
 
-def triplane_attention(x, w_ca1, w_ca2, w_sa):
-    """TriPlaneAttention.forward (scene/grids.py:22-64) evaluated from the module's weights with plain
-    reductions: the module's AdaptiveAvg/MaxPool2d(1) run one thread per channel over the whole plane
-    (14 ms at plane_size 2500), `mean`/`amax` over (H, W) compute the same numbers in microseconds."""
-    F = torch.nn.functional
-    C = x.shape[1]
-    # channel attention: the two 1x1 convolutions act on the pooled [C] vectors -> two tiny matmuls
-    # (each F.conv2d call costs ~1 ms of host time in cuDNN's plan lookup, which starved the GPU)
-    pooled = torch.stack([x.mean(dim=(2, 3)).reshape(C), x.amax(dim=(2, 3)).reshape(C)], dim=1)      # [C, 2]
-    w1, w2 = w_ca1.reshape(w_ca1.shape[0], C), w_ca2.reshape(C, w_ca2.shape[1])
-    ca = torch.sigmoid((w2 @ F.relu(w1 @ pooled)).sum(dim=1)).reshape(1, C, 1, 1)
-    x = ca * x
-    s = torch.cat([x.mean(dim=1, keepdim=True), x.amax(dim=1, keepdim=True)], dim=1)
-    sa = torch.sigmoid(F.conv2d(s, w_sa, padding=w_sa.shape[-1] // 2))
-    return sa * x
+class _TriPlaneAttention(torch.autograd.Function):
+    """TriPlaneAttention.forward (scene/grids.py:22-64) on the three TA-level planes, in
+    libsplatco_b200.so (csrc/triplane_attention.cu).  Inputs: xy/xz/yz planes [1, rc, E, E] and the
+    three Conv2d weights of the module; outputs: the three attended planes."""
+
+    @staticmethod
+    def forward(ctx, xy, xz, yz, w_ca1, w_ca2, w_sa):
+        L = _register()
+        if not xy.is_cuda:
+            raise RuntimeError("splatco_b200 TriPlaneAttention needs CUDA tensors (no CPU fallback)")
+        dev = xy.device
+        ins = [t if _plain(t) else _c(t) for t in (xy, xz, yz, w_ca1, w_ca2, w_sa)]
+        rc, E = int(xy.shape[1]), int(xy.shape[2])
+        hidden, ksize = int(w_ca1.shape[0]), int(w_sa.shape[-1])
+        if not (xy.shape == xz.shape == yz.shape and xy.shape[2] == xy.shape[3]):
+            raise NotImplementedError("splatco_b200 TriPlaneAttention supports equal square planes only")
+        with torch.cuda.device(dev):
+            ws = torch.empty(L.splatco_ta_fwd_ws_bytes(rc, E), dtype=torch.uint8, device=dev)
+            outs = [torch.empty_like(ins[q]) for q in range(3)]
+            with stage("triplane_attention_fwd"):
+                check(L.splatco_ta_fwd(rc, E, hidden, ksize, *[_p(t) for t in ins], _p(ws), *[_p(t) for t in outs],
+                                       torch.cuda.current_stream(dev).cuda_stream), "splatco_ta_fwd")
+        ctx.ins, ctx.ws, ctx.dims = ins, ws, (rc, E, hidden, ksize)
+        ctx.origs = (xy, xz, yz, w_ca1, w_ca2, w_sa)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_xy, g_xz, g_yz):
+        L = _register()
+        rc, E, hidden, ksize = ctx.dims
+        ins = ctx.ins
+        dev = ins[0].device
+        need = ctx.needs_input_grad
+        # plane gradients go into the same per-backward-pass buffers the decode nodes scatter their
+        # direct (un-attended) level-0 plane gradients into (_gradacc)
+        with torch.cuda.device(dev):
+            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, t.shape) for n, (o, t) in enumerate(zip(ctx.origs, ins))])
+            ptrs = [g[0] for g in got]
+            rets = [g[1] if need[n] else None for n, g in enumerate(got)]
+            del got
+            gs = [g if g is not None else torch.zeros_like(ins[q]) for q, g in enumerate((g_xy, g_xz, g_yz))]
+            gs = [g if _plain(g) else _c(g) for g in gs]
+            bws = torch.empty(L.splatco_ta_bwd_ws_bytes(rc, E), dtype=torch.uint8, device=dev)
+            with stage("triplane_attention_bwd"):
+                check(L.splatco_ta_bwd(rc, E, hidden, ksize, *[_p(t) for t in ins], _p(ctx.ws), _p(bws),
+                                       *[_p(g) for g in gs], *ptrs,
+                                       torch.cuda.current_stream(dev).cuda_stream), "splatco_ta_bwd")
+        return tuple(rets)
 
 
 class _TACache:
@@ -281,10 +327,9 @@ class _TACache:
         key = (torch.is_grad_enabled(),) + tuple((id(t), t._version, t.data_ptr(), tuple(t.shape)) for t in ts)
         if self.key == key and self.value is not None:
             return self.value
-        ta = triplane_attention(torch.cat(planes, dim=1), *weights)
-        att = tuple(t.contiguous() for t in torch.chunk(ta, 3, dim=1))
-        if ta.requires_grad:
-            ta.register_hook(self._invalidate)
+        att = _TriPlaneAttention.apply(*planes, *weights)
+        if att[0].requires_grad:
+            att[0].register_hook(self._invalidate)
         self.key, self.value = key, att
         return att
 
@@ -398,17 +443,19 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
         m0, m2 = mlp[0], mlp[2]
         params += [_par(m0, "weight"), _par(m0, "bias"), _par(m2, "weight"), _par(m2, "bias")]
     # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169)
-    with stage("triplane_attention_torch"):
-        att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
+    att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
     app_vec = None
     if cfg.app_dim > 0:
         app_vec = pc.get_appearance.embedding.weight[int(viewpoint_camera.uid)]
     return cfg, att, app_vec, params
 
 
-def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False):
-    """Drop-in for gaussian_renderer.generate_neural_gaussians (reference :18-116)."""
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, _raster_settings=None):
+    """Drop-in for gaussian_renderer.generate_neural_gaussians (reference :18-116).  `_raster_settings`
+    is render()'s private hint: the GaussianRasterizationSettings it is about to rasterize the result
+    with, which lets the decode queue the rasterizer's preprocess before its own row count is known."""
     cfg, att, app_vec, params = collect_model(pc, viewpoint_camera, visible_mask)
+    cfg.raster = _raster_settings
     # GaussianLearner.inference always passes Q = self.Q0 (0.03 while training, 0 in render.py):
     # U(-.5,.5)*Q is added to the plane features of the non-TA levels (scene/grids.py:159-164)
     Q = float(getattr(pc.feat_planes, "Q0", 0.0) or 0.0)

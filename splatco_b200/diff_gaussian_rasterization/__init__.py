@@ -43,12 +43,12 @@ class GaussianRasterizationSettings(NamedTuple):
 _tls = threading.local()
 
 
-def _pinned_counter(device: torch.device) -> torch.Tensor:
-    """One pinned int32 per (thread, device) for the num_rendered read-back."""
+def _pinned_counter(device: torch.device, slot: int = 0) -> torch.Tensor:
+    """One pinned int32 per (thread, device, slot) for the num_rendered read-back."""
     cache = getattr(_tls, "counters", None)
     if cache is None:
         cache = _tls.counters = {}
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
     buf = cache.get(key)
     if buf is None:
         buf = cache[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
@@ -88,7 +88,62 @@ def _debug_sync(settings, what):
 
 class RasterState:
     """What forward leaves behind for backward and for the stage-wise parity tests."""
-    __slots__ = ("P", "R", "H", "W", "geom", "binning", "image", "radii")
+    __slots__ = ("P", "PL", "R", "H", "W", "geom", "binning", "image", "radii", "radii_full")
+
+
+class _Speculated:
+    """preprocess_fwd launched by the decode on its own outputs before their row count M was known on
+    the host (splatco_preprocess_fwd_counted), so that M and R come back in ONE sync."""
+    __slots__ = ("tensors", "versions", "settings", "M", "PL", "R", "geom", "radii_full", "counter")
+
+
+_spec_slot = threading.local()
+
+
+def preprocess_speculative(xyz_b, color_b, opacity_b, scaling_b, rot_b, count_ptr, settings):
+    """Called by the decode forward with its VK-row output buffers (row count still on the device at
+    `count_ptr`).  Launches the counted preprocess and returns the pending record; the caller syncs,
+    then `publish_speculated` makes it available to the next rasterizer forward on these tensors."""
+    L = _lib.lib()
+    dev = xyz_b.device
+    H, W = int(settings.image_height), int(settings.image_width)
+    PL = int(xyz_b.shape[0])
+    sp = _Speculated()
+    sp.settings, sp.PL = settings, PL
+    sp.radii_full = torch.empty(PL, dtype=torch.int32, device=dev)
+    sp.geom = torch.empty(L.splatco_geom_bytes(PL), dtype=torch.uint8, device=dev)
+    sp.counter = _pinned_counter(dev, 1)
+    view, proj = _f32c(settings.viewmatrix), _f32c(settings.projmatrix)
+    with stage("preprocess_fwd"):
+        check(L.splatco_preprocess_fwd_counted(PL, count_ptr, ptr(xyz_b), ptr(scaling_b), 3, ptr(rot_b), ptr(opacity_b),
+                                               ptr(color_b), float(settings.scale_modifier), ptr(view), ptr(proj),
+                                               float(settings.tanfovx), float(settings.tanfovy), H, W,
+                                               ptr(sp.radii_full), ptr(sp.geom), sp.counter.data_ptr(),
+                                               _stream_ptr(dev)), "splatco_preprocess_fwd_counted")
+    return sp
+
+
+def publish_speculated(sp, M, outs):
+    """After the sync: `outs` = the M-row tensors (xyz, color, opacity, scaling, rot) the decode returns."""
+    sp.M, sp.R = M, int(sp.counter[0])
+    sp.tensors = tuple(outs)
+    sp.versions = tuple(t._version for t in outs)
+    _spec_slot.sp = sp
+
+
+def _take_speculated(means3D, colors, opacities, scales, rotations, settings):
+    sp = getattr(_spec_slot, "sp", None)
+    if sp is None:
+        return None
+    _spec_slot.sp = None
+    ins = (means3D, colors, opacities, scales, rotations)
+    if sp.settings is not settings or sp.M != int(means3D.shape[0]):
+        return None
+    for t, u, v in zip(ins, sp.tensors, sp.versions):
+        # same memory, same shape, not written to since the decode produced it
+        if t.data_ptr() != u.data_ptr() or t.shape != u.shape or t._version != v or not t.is_contiguous():
+            return None
+    return sp
 
 
 def rasterize_forward_state(means3D, colors, opacities, scales, rotations, settings) -> tuple:
@@ -101,39 +156,45 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
     P = int(means3D.shape[0])
     bg = _f32c(settings.bg)
     st = RasterState()
-    st.P, st.H, st.W = P, H, W
+    st.P, st.PL, st.H, st.W = P, P, H, W
+    sp = _take_speculated(means3D, colors, opacities, scales, rotations, settings)
     if P == 0:
         st.R = 0
         st.geom = st.binning = None
         st.image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
-        st.radii = torch.empty(0, dtype=torch.int32, device=dev)
+        st.radii = st.radii_full = torch.empty(0, dtype=torch.int32, device=dev)
         color = bg.reshape(3, 1, 1).expand(3, H, W).contiguous()
         return color, st.radii, st
-    means3D = _f32c(means3D)
-    colors = _f32c(colors)
-    opacities = _f32c(opacities)
-    rotations = _f32c(rotations)
-    scales, sstride = _rows_f32(scales, 3)
-    view = _f32c(settings.viewmatrix)
-    proj = _f32c(settings.projmatrix)
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
-        radii = torch.empty(P, dtype=torch.int32, device=dev)
-        geom = torch.empty(L.splatco_geom_bytes(P), dtype=torch.uint8, device=dev)
-        counter = _pinned_counter(dev)
-        with stage("preprocess_fwd"):
-          check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
-                                       ptr(colors), float(settings.scale_modifier), ptr(view), ptr(proj),
-                                       float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(radii),
-                                       ptr(geom), counter.data_ptr(), stream), "splatco_preprocess_fwd")
-        # the one device->host sync of the forward (the reference has the same one)
-        torch.cuda.current_stream(dev).synchronize()
-        R = int(counter.item())
+        if sp is not None:
+            # preprocess already ran (and was synced) inside the decode forward
+            radii_full, geom, R, st.PL = sp.radii_full, sp.geom, sp.R, sp.PL
+            radii = radii_full[:P]
+        else:
+            means3D = _f32c(means3D)
+            colors = _f32c(colors)
+            opacities = _f32c(opacities)
+            rotations = _f32c(rotations)
+            scales, sstride = _rows_f32(scales, 3)
+            view = _f32c(settings.viewmatrix)
+            proj = _f32c(settings.projmatrix)
+            radii = radii_full = torch.empty(P, dtype=torch.int32, device=dev)
+            geom = torch.empty(L.splatco_geom_bytes(P), dtype=torch.uint8, device=dev)
+            counter = _pinned_counter(dev)
+            with stage("preprocess_fwd"):
+                check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
+                                               ptr(colors), float(settings.scale_modifier), ptr(view), ptr(proj),
+                                               float(settings.tanfovx), float(settings.tanfovy), H, W, ptr(radii),
+                                               ptr(geom), counter.data_ptr(), stream), "splatco_preprocess_fwd")
+            # the one device->host sync of the forward (the reference has the same one)
+            torch.cuda.current_stream(dev).synchronize()
+            R = int(counter[0])
         _debug_sync(settings, "preprocess")
         binning = torch.empty(max(L.splatco_binning_bytes(R), 256), dtype=torch.uint8, device=dev)
         image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
         with stage("binning"):
-            check(L.splatco_binning(P, R, H, W, ptr(radii), ptr(geom), ptr(binning), ptr(image), stream),
+            check(L.splatco_binning(st.PL, R, H, W, ptr(radii_full), ptr(geom), ptr(binning), ptr(image), stream),
                   "splatco_binning")
         _debug_sync(settings, "binning")
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
@@ -141,7 +202,7 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
             check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(color), stream),
                   "splatco_blend_fwd")
         _debug_sync(settings, "blend_fwd")
-    st.R, st.geom, st.binning, st.image, st.radii = R, geom, binning, image, radii
+    st.R, st.geom, st.binning, st.image, st.radii, st.radii_full = R, geom, binning, image, radii, radii_full
     return color, radii, st
 
 

@@ -50,12 +50,13 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
            retain_grad=False):
     """Render the scene.  Background tensor (bg_color) must be on GPU!"""
     is_training = pc.get_color_mlp.training
+    settings = _settings(viewpoint_camera, pipe, bg_color, scaling_modifier)
     if is_training:
         xyz, color, opacity, scaling, rot, neural_opacity, mask = generate_neural_gaussians(
-            viewpoint_camera, pc, visible_mask, is_training=is_training)
+            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings)
     else:
         xyz, color, opacity, scaling, rot = generate_neural_gaussians(
-            viewpoint_camera, pc, visible_mask, is_training=is_training)
+            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings)
 
     # zero tensor whose .grad receives the 2D (screen-space) mean gradients (reference :133-138)
     screenspace_points = torch.zeros_like(xyz, dtype=pc.get_anchor.dtype, requires_grad=True, device="cuda") + 0
@@ -65,7 +66,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         except Exception:
             pass
 
-    rasterizer = GaussianRasterizer(raster_settings=_settings(viewpoint_camera, pipe, bg_color, scaling_modifier))
+    rasterizer = GaussianRasterizer(raster_settings=settings)
     rendered_image, radii = rasterizer(
         means3D=xyz,
         means2D=screenspace_points,

@@ -70,6 +70,24 @@ def main():
         else:
             c = cpu[e.name[:60]]; c[0] += 1; c[1] += e.self_cpu_time_total
     n = a.steps
+    # GPU idle gaps: sort device events by start time, report what ran before/after the large gaps
+    dev_ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+    gaps = defaultdict(lambda: [0, 0.0])
+    idle = 0.0
+    end = None
+    prev = None
+    for e in dev_ev:
+        st, en = e.time_range.start, e.time_range.end
+        if end is not None and st > end:
+            g = st - end
+            idle += g
+            if g > 15:
+                k = gaps[(prev.name.split("(")[0][-40:], e.name.split("(")[0][-40:])]; k[0] += 1; k[1] += g
+        if end is None or en > end:
+            end, prev = en, e
+    print(f"GPU idle between kernels: {idle / n / 1e3:.2f} ms/step; gaps > 15 us by (previous kernel -> next kernel):")
+    for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+        print(f"  {v[1] / n:8.1f} us/step n/step={v[0] / n:5.1f}  {k[0]}  ->  {k[1]}")
     tot = sum(v[1] for v in kern.values())
     ours = sum(v[1] for k, v in kern.items() if "splatco" in k or k.startswith(("dec_", "blend_", "sort_", "preprocess", "visible_filter", "duplicate", "identify", "scan_block", "sgemm", "ta_", "loss_", "stat")))
     print(f"GPU kernel time {tot / n / 1e3:.2f} ms/step: library {ours / n / 1e3:.2f}, other {(tot - ours) / n / 1e3:.2f}")
