@@ -85,11 +85,18 @@ int splatco_preprocess_fwd_counted(int P_max, const int32_t *P_dev, const float 
                                    int H, int W, int32_t *radii_out, void *geom,
                                    int32_t *num_rendered_host, void *stream);
 
-/* ---- forward, stage 2: duplicateWithKeys + 64-bit radix sort + identifyTileRanges ------------
- * R must be the value produced by stage 1.  The stages are also exported individually so parity
- * tests can check keys, permutation and ranges one by one. */
+/* ---- forward, stage 2: the sorted per-tile instance lists ------------------------------------
+ * Produces what upstream's duplicateWithKeys + stable 64-bit SortPairs + identifyTileRanges produce:
+ * sorted keys (tile << 32 | depth bits), the sorted Gaussian-id list and the per-tile ranges, bit for
+ * bit.  splatco_binning is tile-segmented (count per tile, scan, scatter into segments, per-tile sort
+ * in shared memory; see csrc/binning.cu); R is the capacity of the binning buffers and must be >= the
+ * value produced by stage 1.  splatco_binning_radix is the literal composition of the three upstream
+ * stages (global LSD radix sort), which are also exported individually so parity tests can check
+ * keys, permutation and ranges one by one. */
 int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
                     void *binning, void *image, void *stream);
+int splatco_binning_radix(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
+                          void *binning, void *image, void *stream);
 int splatco_duplicate_with_keys(int P, int64_t R, int H, int W, const int32_t *radii,
                                 const void *geom, void *binning, void *stream);
 int splatco_sort_pairs(int64_t R, int H, int W, void *binning, void *stream);

@@ -32,6 +32,7 @@ SIGNATURES = {
     "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd_counted": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_binning": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_binning_radix": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "splatco_duplicate_with_keys": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_sort_pairs": (_i, [_i64, _i, _i, _vp, _vp]),
     "splatco_identify_tile_ranges": (_i, [_i64, _i, _i, _vp, _vp, _vp]),

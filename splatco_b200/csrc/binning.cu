@@ -207,6 +207,310 @@ identify_tile_ranges_kernel(uint32_t n, const uint64_t *__restrict__ keys, int2 
     if (i == n - 1) ranges[t].y = (int)n;
 }
 
+
+// =====================================================================================================
+// Tile-segmented binning (the path splatco_binning takes).  The 64-bit key is (tile << 32 | depth): the
+// tile part only says WHICH segment of the list an instance belongs to.  So instead of six global radix
+// passes over all R pairs, ONE multi-way partition by tile and a per-tile sort in shared memory:
+//   tile_hist     chunks of 4096 Gaussians, one CTA each: per-tile instance counts in a shared-memory
+//                 histogram, written out as one row per chunk (no global atomics)
+//   tile_colscan  per tile: exclusive prefix over the chunks (each chunk's base inside the tile's segment)
+//   tile_scan     one CTA: exclusive scan of the T totals -> ranges
+//   tile_scatter  same chunks: slot = range start + chunk base + shared-memory atomic; stores (depth << 32 | id)
+//   tile_sort_*   one CTA per tile: LSD radix sort of the segment on the depth bits in shared memory
+//                 (constant digits skipped), equal-depth runs then ordered by Gaussian id
+// The arrival order inside a segment is arbitrary, but (depth, id) is unique within a tile, so the
+// result is exactly what a stable sort of (tile | depth) keys in emission order produces: ties in depth
+// keep ascending Gaussian id, the reference's emission order [SURVEY.md Appendix A.3].
+// Traffic: 8 B*R scattered + 8 B*R read + 12 B*R written, L2-resident at the BASELINE sizes.
+// =====================================================================================================
+constexpr int TCHUNK = 4096;                       // Gaussians per CTA of tile_hist / tile_scatter
+constexpr int TCHUNK_THREADS = 512;
+
+__device__ __forceinline__ bool tile_rect(int i, int P, const int32_t *__restrict__ radii, const float4 *__restrict__ rec,
+                                          int gx, int gy, int &r0x, int &r0y, int &r1x, int &r1y) {
+    if (i >= P) return false;
+    const int radius = radii[i];
+    if (radius <= 0) return false;
+    const float4 r0 = rec[3 * (size_t)i];
+    rect_from_rec(r0.x, r0.y, radius, gx, gy, r0x, r0y, r1x, r1y);
+    return true;
+}
+
+__global__ void __launch_bounds__(TCHUNK_THREADS)
+tile_hist_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
+                 uint32_t *__restrict__ chunk_hist /*[nchunks][T]*/) {
+    extern __shared__ uint32_t s_hist[];
+    for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) s_hist[t] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * TCHUNK;
+#pragma unroll 1
+    for (int k = 0; k < TCHUNK / TCHUNK_THREADS; ++k) {
+        const int i = base + k * TCHUNK_THREADS + threadIdx.x;
+        int r0x, r0y, r1x, r1y;
+        if (!tile_rect(i, P, radii, rec, gx, gy, r0x, r0y, r1x, r1y)) continue;
+        for (int y = r0y; y < r1y; ++y)
+            for (int x = r0x; x < r1x; ++x) atomicAdd(&s_hist[y * gx + x], 1u);
+    }
+    __syncthreads();
+    uint32_t *row = chunk_hist + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) row[t] = s_hist[t];
+}
+
+// thread per tile: chunk_hist[c][t] <- exclusive prefix over c; tile_count[t] = total
+__global__ void __launch_bounds__(256)
+tile_colscan_kernel(int T, int nchunks, uint32_t *__restrict__ chunk_hist, uint32_t *__restrict__ tile_count,
+                    uint32_t *__restrict__ work /*[8]: list lengths [0..2], queue heads [4..6]*/) {
+    if (blockIdx.x == 0 && threadIdx.x < 8) work[threadIdx.x] = 0;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= T) return;
+    uint32_t run = 0;
+#pragma unroll 4
+    for (int c = 0; c < nchunks; ++c) {
+        const uint32_t v = chunk_hist[(size_t)c * T + t];
+        chunk_hist[(size_t)c * T + t] = run;
+        run += v;
+    }
+    tile_count[t] = run;
+}
+
+// one CTA; ranges[t] = [start, end) (zero for empty tiles, as identifyTileRanges leaves them), cursor[t] = start
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, const uint32_t *__restrict__ tile_count, int2 *__restrict__ ranges, uint32_t *__restrict__ cursor,
+                 uint32_t capacity, uint32_t *__restrict__ work, uint32_t *__restrict__ lists /*[3][T]*/, uint32_t lim_s,
+                 uint32_t lim_l) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + threadIdx.x;
+        const uint32_t v = t < T ? tile_count[t] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += n; }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= (uint32_t)d) winc += n; }
+            s_warp[lane] = winc - w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + s_warp[warp] + inc - v;
+        if (t < T) {
+            // clamped to the buffers' capacity: a caller that sized them from a guess gets a truncated but
+            // in-bounds list and re-runs the stage once it knows R
+            const uint32_t s0 = min(excl, capacity), e0 = min(excl + v, capacity);
+            ranges[t] = e0 > s0 ? make_int2((int)s0, (int)e0) : make_int2(0, 0);
+            cursor[t] = excl;
+            // work list of the sort kernel that handles this segment length (order inside a list is irrelevant)
+            const uint32_t n = e0 - s0;
+            if (n > 1) {
+                const int cls = n <= lim_s ? 0 : (n <= lim_l ? 1 : 2);
+                lists[(size_t)cls * T + atomicAdd(&work[cls], 1u)] = (uint32_t)t;
+            } else if (n == 1) {
+                lists[(size_t)0 * T + atomicAdd(&work[0], 1u)] = (uint32_t)t;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(TCHUNK_THREADS)
+tile_scatter_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
+                    const uint32_t *__restrict__ chunk_base /*[nchunks][T]*/, const uint32_t *__restrict__ tile_start,
+                    uint64_t *__restrict__ entries, uint32_t capacity) {
+    extern __shared__ uint32_t s_next[];
+    const uint32_t *row = chunk_base + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) s_next[t] = tile_start[t] + row[t];
+    __syncthreads();
+    const int base = blockIdx.x * TCHUNK;
+#pragma unroll 1
+    for (int k = 0; k < TCHUNK / TCHUNK_THREADS; ++k) {
+        const int i = base + k * TCHUNK_THREADS + threadIdx.x;
+        int r0x, r0y, r1x, r1y;
+        if (!tile_rect(i, P, radii, rec, gx, gy, r0x, r0y, r1x, r1y)) continue;
+        const uint64_t e = ((uint64_t)__float_as_uint(rec[3 * (size_t)i + 2].y) << 32) | (uint32_t)i;
+        for (int y = r0y; y < r1y; ++y)
+            for (int x = r0x; x < r1x; ++x) {
+                const uint32_t slot = atomicAdd(&s_next[y * gx + x], 1u);
+                if (slot < capacity) entries[slot] = e;
+            }
+    }
+}
+
+// ---- per-tile sort, segments that fit in shared memory: LSD radix on the 32 depth bits ----------------------
+// ITEMS consecutive-by-32 elements per lane, warp w owns the contiguous slice [w*32*ITEMS, (w+1)*32*ITEMS): the
+// usual stable ranking (match_any inside the warp, running per-(warp, digit) counters across its items).
+template <int ITEMS>
+__global__ void __launch_bounds__(512)
+tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restrict__ entries,
+                       uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ list,
+                       uint32_t *__restrict__ work, int cls) {
+    constexpr int NT = 512, NW = NT / 32, CAP = NT * ITEMS;
+    extern __shared__ uint32_t s_dyn[];
+    uint32_t *s_cnt = s_dyn + 4 * CAP;                         // [NW][256]; before it: [key CAP | val CAP] x 2
+    __shared__ uint32_t s_scan[NW];
+    __shared__ int s_skip;
+    __shared__ uint32_t s_item;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t count = work[cls];
+  for (;;) {                                                   // persistent CTA: next tile of this size class
+    __syncthreads();
+    if (tid == 0) s_item = atomicAdd(&work[4 + cls], 1u);
+    __syncthreads();
+    if (s_item >= count) break;
+    const uint32_t tile = list[s_item];
+    const int2 rg = ranges[tile];
+    const uint32_t n = (uint32_t)(rg.y - rg.x);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < n; i += NT) {
+        const uint64_t e = entries[rg.x + i];
+        s_dyn[i] = (uint32_t)(e >> 32);
+        s_dyn[CAP + i] = (uint32_t)e;
+    }
+    int cur = 0;
+    const uint32_t wbase = warp * 32 * ITEMS;
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        __syncthreads();                                       // the previous scatter (or the load) is complete
+        for (uint32_t i = tid; i < NW * 256; i += NT) s_cnt[i] = 0;
+        __syncthreads();
+        const uint32_t *key = s_dyn + cur * 2 * CAP, *val = key + CAP;
+        uint32_t k[ITEMS], rank[ITEMS];
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const uint32_t idx = wbase + it * 32 + lane;
+            const bool valid = idx < n;
+            k[it] = valid ? key[idx] : 0xffffffffu;
+            const uint32_t digit = valid ? (k[it] >> shift) & 255u : 256u;
+            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+            const uint32_t r = __popc(peers & lanemask_lt());
+            uint32_t pre = 0;
+            if (valid) pre = s_cnt[warp * 256 + digit];
+            rank[it] = pre + r;
+            __syncwarp();
+            if (valid && r == 0) s_cnt[warp * 256 + digit] = pre + __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // digit d = tid (< 256): exclusive scan over warps, then over digits
+        uint32_t dsum = 0, dinc = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { const uint32_t c = s_cnt[w * 256 + tid]; s_cnt[w * 256 + tid] = dsum; dsum += c; }
+            dinc = dsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, dinc, d); if (lane >= (uint32_t)d) dinc += v; }
+            if (lane == 31) s_scan[warp] = dinc;
+            if (tid == 0) s_skip = 0;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t doff = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) doff += (w < (int)warp) ? s_scan[w] : 0u;
+            const uint32_t dstart = doff + dinc - dsum;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s_cnt[w * 256 + tid] += dstart;
+            if (dsum == n) s_skip = 1;                         // every key has this digit: the pass is the identity
+        }
+        __syncthreads();
+        if (s_skip) continue;
+        uint32_t *okey = s_dyn + (cur ^ 1) * 2 * CAP, *oval = okey + CAP;
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            const uint32_t idx = wbase + it * 32 + lane;
+            if (idx < n) {
+                const uint32_t pos = s_cnt[warp * 256 + ((k[it] >> shift) & 255u)] + rank[it];
+                okey[pos] = k[it];
+                oval[pos] = val[idx];
+            }
+        }
+        cur ^= 1;
+    }
+    __syncthreads();
+    // equal-depth runs (rare): order by Gaussian id; the thread at the head of a run sorts it
+    uint32_t *key = s_dyn + cur * 2 * CAP, *val = key + CAP;
+    for (uint32_t i = tid; i + 1 < n; i += NT) {
+        if (key[i] == key[i + 1] && (i == 0 || key[i - 1] != key[i])) {
+            uint32_t e = i + 1;
+            while (e + 1 < n && key[e + 1] == key[i]) ++e;
+            for (uint32_t a = i + 1; a <= e; ++a) {            // insertion sort of val[i..e]
+                const uint32_t v = val[a];
+                uint32_t b = a;
+                while (b > i && val[b - 1] > v) { val[b] = val[b - 1]; --b; }
+                val[b] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t hi = (uint64_t)tile << 32;
+    for (uint32_t i = tid; i < n; i += NT) {
+        keys_out[rg.x + i] = hi | key[i];
+        vals_out[rg.x + i] = val[i];
+    }
+  }
+}
+
+// ---- per-tile sort, segments larger than shared memory: in-place sorting network in global memory -----------
+// Every comparator ascending (first step of each merge mirrors, the rest are half-cleaners), so a segment of any
+// length n behaves as if padded with +inf: comparators touching an index >= n are no-ops and are skipped.
+constexpr int TSORT_THREADS = 512;
+
+__device__ __forceinline__ void tile_sort_network(uint64_t *buf, uint32_t n) {
+    for (uint32_t k = 2; (k >> 1) < n; k <<= 1) {
+        for (uint32_t p = threadIdx.x;; p += TSORT_THREADS) {
+            const uint32_t blk = p / (k >> 1), r = p - blk * (k >> 1);
+            const uint32_t i = blk * k + r, l = blk * k + k - 1 - r;
+            if (i >= n) break;
+            if (l < n) { const uint64_t a = buf[i], b = buf[l]; if (a > b) { buf[i] = b; buf[l] = a; } }
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t p = threadIdx.x;; p += TSORT_THREADS) {
+                const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), l = i + j;
+                if (i >= n) break;
+                if (l < n) { const uint64_t a = buf[i], b = buf[l]; if (a > b) { buf[i] = b; buf[l] = a; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TSORT_THREADS)
+tile_sort_global_kernel(const int2 *__restrict__ ranges, uint64_t *__restrict__ entries, uint64_t *__restrict__ keys_out,
+                        uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ list, uint32_t *__restrict__ work) {
+    __shared__ uint32_t s_item;
+    const uint32_t count = work[2];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(&work[6], 1u);
+        __syncthreads();
+        if (s_item >= count) break;
+        const uint32_t tile = list[s_item];
+        const int2 rg = ranges[tile];
+        const uint32_t n = (uint32_t)(rg.y - rg.x);
+        uint64_t *seg = entries + rg.x;
+        tile_sort_network(seg, n);
+        const uint64_t hi = (uint64_t)tile << 32;
+        for (uint32_t i = threadIdx.x; i < n; i += TSORT_THREADS) {
+            const uint64_t e = seg[i];
+            keys_out[rg.x + i] = hi | (e >> 32);
+            vals_out[rg.x + i] = (uint32_t)e;
+        }
+    }
+}
+
+constexpr int TSORT_ITEMS_S = 4, TSORT_ITEMS_L = 16;          // 2048 / 8192 elements per CTA
+constexpr size_t tsort_smem(int items) { return (size_t)(4 * 512 * items + 16 * 256) * sizeof(uint32_t); }
+
 }  // namespace splatco
 
 using namespace splatco;
@@ -276,11 +580,68 @@ extern "C" int splatco_identify_tile_ranges(int64_t R, int H, int W, const void 
     return 0;
 }
 
-extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
-                               void *binning, void *image, void *stream) {
+// Legacy composition of the three upstream stages (global LSD radix sort); kept for stage-level parity checks.
+extern "C" int splatco_binning_radix(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
+                                     void *binning, void *image, void *stream) {
     int rc = splatco_duplicate_with_keys(P, R, H, W, radii, geom, binning, stream);
     if (rc) return rc;
     rc = splatco_sort_pairs(R, H, W, binning, stream);
     if (rc) return rc;
     return splatco_identify_tile_ranges(R, H, W, binning, image, stream);
+}
+
+extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
+                               void *binning, void *image, void *stream) {
+    if (check_R(R)) return -1;
+    SPLATCO_REQUIRE(image && H > 0 && W > 0 && P >= 0, "binning: bad arguments");
+    ImgWs im = img_view(image, H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
+    const int T = gx * gy;
+    if (P == 0 || R == 0) {
+        SPLATCO_CHECK_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(int2) * (size_t)T, st));
+        return 0;
+    }
+    SPLATCO_REQUIRE(radii && geom && binning, "binning: null pointer");
+    const int nchunks = ceil_div(P, TCHUNK);
+    const size_t hist_bytes = (size_t)T * sizeof(uint32_t);
+    BinWs b = bin_view(binning, R);
+    const int s = splatco_sorted_buffer_index(H, W);
+    // the per-chunk histogram rows live in the value buffer that is not the sorted output (4 B*R): fall back to the
+    // radix composition when they do not fit there or the tile histogram does not fit in shared memory
+    if ((size_t)nchunks * hist_bytes > (size_t)R * sizeof(uint32_t) || hist_bytes > 200 * 1024)
+        return splatco_binning_radix(P, R, H, W, radii, geom, binning, image, stream);
+    GeomWs g = geom_view(const_cast<void *>(geom), P);
+    uint32_t *chunk_hist = b.vals[s ^ 1];
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_ITEMS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tsort_smem(TSORT_ITEMS_S)));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_ITEMS_L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tsort_smem(TSORT_ITEMS_L)));
+        attr_set = true;
+    }
+    tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist);
+    SPLATCO_CHECK_LAUNCH();
+    tile_colscan_kernel<<<ceil_div(T, 256), 256, 0, st>>>(T, nchunks, chunk_hist, im.tile_count, im.work);
+    SPLATCO_CHECK_LAUNCH();
+    tile_scan_kernel<<<1, 1024, 0, st>>>(T, im.tile_count, im.ranges, im.cursor, (uint32_t)R, im.work, im.lists,
+                                         512u * TSORT_ITEMS_S, 512u * TSORT_ITEMS_L);
+    SPLATCO_CHECK_LAUNCH();
+    tile_scatter_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist, im.cursor,
+                                                                    b.keys[s ^ 1], (uint32_t)R);
+    SPLATCO_CHECK_LAUNCH();
+    // persistent sort CTAs pull tiles of their size class from the lists tile_scan built
+    tile_sort_radix_kernel<TSORT_ITEMS_S><<<min(T, 148 * 4), 512, tsort_smem(TSORT_ITEMS_S), st>>>(
+        im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s], im.lists, im.work, 0);
+    SPLATCO_CHECK_LAUNCH();
+    tile_sort_radix_kernel<TSORT_ITEMS_L><<<min(T, 148), 512, tsort_smem(TSORT_ITEMS_L), st>>>(
+        im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s], im.lists + T, im.work, 1);
+    SPLATCO_CHECK_LAUNCH();
+    tile_sort_global_kernel<<<min(T, 148), TSORT_THREADS, 0, st>>>(im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s],
+                                                                   im.lists + 2 * (size_t)T, im.work);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
 }

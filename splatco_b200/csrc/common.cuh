@@ -60,11 +60,15 @@ struct ImgWs {
     int2 *ranges;             // [T]
     float *final_T;           // [HW]
     int32_t *n_contrib;       // [HW]
+    uint32_t *tile_count;     // [T]  instances per tile (tile-segmented binning)
+    uint32_t *cursor;         // [T]  start of each tile's segment
+    uint32_t *lists;          // [3][T] tiles by segment-length class (per-tile sort work lists)
+    uint32_t *work;           // [8]  list lengths [0..2], queue heads [4..6]
 };
 
 size_t geom_offsets(int P, size_t off[7]);
 size_t bin_offsets(int64_t R, size_t off[7]);
-size_t img_offsets(int H, int W, size_t off[4]);
+size_t img_offsets(int H, int W, size_t off[8]);
 GeomWs geom_view(void *base, int P);
 BinWs bin_view(void *base, int64_t R);
 ImgWs img_view(void *base, int H, int W);

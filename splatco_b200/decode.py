@@ -193,7 +193,7 @@ class _FusedDecode(torch.autograd.Function):
                     check(L.splatco_decode_emit(C.byref(desc), _p(ws), VK, *[_p(b) for b in bufs], stream),
                           "splatco_decode_emit")
                 sp = _dgr.preprocess_speculative(*bufs, L.splatco_decode_count_ptr(_p(ws), V, cfg.rc, cfg.level), cfg.raster)
-                torch.cuda.current_stream(dev).synchronize()
+                sp.event.synchronize()             # M, R have landed; binning + blend keep running behind it
                 M = int(counter[0])
                 xyz, color, opacity, scl, rot = [b[:M] for b in bufs]
                 _dgr.publish_speculated(sp, M, (xyz, color, opacity, scl, rot))

@@ -88,13 +88,16 @@ def _debug_sync(settings, what):
 
 class RasterState:
     """What forward leaves behind for backward and for the stage-wise parity tests."""
-    __slots__ = ("P", "PL", "R", "H", "W", "geom", "binning", "image", "radii", "radii_full")
+    __slots__ = ("P", "PL", "R", "RL", "H", "W", "geom", "binning", "image", "radii", "radii_full")
+    # P / R: Gaussians and instances of this view; PL / RL: the row counts the geometry / binning
+    # workspaces were laid out for (>= P, R when the forward was queued before the counts were known)
 
 
 class _Speculated:
     """preprocess_fwd launched by the decode on its own outputs before their row count M was known on
     the host (splatco_preprocess_fwd_counted), so that M and R come back in ONE sync."""
-    __slots__ = ("tensors", "versions", "settings", "M", "PL", "R", "geom", "radii_full", "counter")
+    __slots__ = ("tensors", "versions", "settings", "M", "PL", "R", "RL", "geom", "radii_full", "counter", "binning",
+                 "image", "color", "event")
 
 
 _spec_slot = threading.local()
@@ -120,12 +123,51 @@ def preprocess_speculative(xyz_b, color_b, opacity_b, scaling_b, rot_b, count_pt
                                                float(settings.tanfovx), float(settings.tanfovy), H, W,
                                                ptr(sp.radii_full), ptr(sp.geom), sp.counter.data_ptr(),
                                                _stream_ptr(dev)), "splatco_preprocess_fwd_counted")
+    # M and R are complete once this event has passed; the caller waits for IT, not for the stream
+    sp.event = torch.cuda.Event()
+    sp.event.record(torch.cuda.current_stream(dev))
+    # binning + blend are queued too, on buffers sized from the last view of this resolution: when the
+    # host learns M and R the GPU is already working on them instead of idling through the host-side
+    # bookkeeping that follows the sync.  A wrong guess (R larger than the buffers) is detected after the
+    # sync and the two stages are simply re-run (publish_speculated).
+    sp.binning = sp.image = sp.color = None
+    sp.RL = 0
+    guess = _r_guess.get((H, W))
+    if guess:
+        sp.RL = int(guess * 1.25) + 4096
+        _queue_binning_blend(sp, dev, H, W)
     return sp
+
+
+_r_guess = {}
+
+
+def _queue_binning_blend(sp, dev, H, W):
+    L = _lib.lib()
+    settings = sp.settings
+    stream = _stream_ptr(dev)
+    sp.binning = torch.empty(max(L.splatco_binning_bytes(sp.RL), 256), dtype=torch.uint8, device=dev)
+    sp.image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
+    sp.color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    with stage("binning"):
+        check(L.splatco_binning(sp.PL, sp.RL, H, W, ptr(sp.radii_full), ptr(sp.geom), ptr(sp.binning), ptr(sp.image),
+                                stream), "splatco_binning")
+    with stage("blend_fwd"):
+        check(L.splatco_blend_fwd(sp.RL, H, W, ptr(_f32c(settings.bg)), ptr(sp.geom), ptr(sp.binning), ptr(sp.image),
+                                  ptr(sp.color), stream), "splatco_blend_fwd")
 
 
 def publish_speculated(sp, M, outs):
     """After the sync: `outs` = the M-row tensors (xyz, color, opacity, scaling, rot) the decode returns."""
     sp.M, sp.R = M, int(sp.counter[0])
+    H, W = int(sp.settings.image_height), int(sp.settings.image_width)
+    _r_guess[(H, W)] = max(sp.R, 1)
+    if sp.binning is None or sp.R > sp.RL:
+        if M > 0 and sp.R > 0:
+            sp.RL = sp.R
+            _queue_binning_blend(sp, outs[0].device, H, W)
+        else:
+            sp.binning = None
     sp.tensors = tuple(outs)
     sp.versions = tuple(t._version for t in outs)
     _spec_slot.sp = sp
@@ -159,7 +201,7 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
     st.P, st.PL, st.H, st.W = P, P, H, W
     sp = _take_speculated(means3D, colors, opacities, scales, rotations, settings)
     if P == 0:
-        st.R = 0
+        st.R = st.RL = 0
         st.geom = st.binning = None
         st.image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
         st.radii = st.radii_full = torch.empty(0, dtype=torch.int32, device=dev)
@@ -167,8 +209,14 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
         return color, st.radii, st
     stream = _stream_ptr(dev)
     with torch.cuda.device(dev):
+        if sp is not None and sp.binning is not None:
+            # the whole forward already ran (queued inside the decode forward)
+            st.PL, st.R, st.RL = sp.PL, sp.R, sp.RL
+            st.geom, st.binning, st.image, st.radii_full = sp.geom, sp.binning, sp.image, sp.radii_full
+            st.radii = sp.radii_full[:P]
+            _debug_sync(settings, "forward")
+            return sp.color, st.radii, st
         if sp is not None:
-            # preprocess already ran (and was synced) inside the decode forward
             radii_full, geom, R, st.PL = sp.radii_full, sp.geom, sp.R, sp.PL
             radii = radii_full[:P]
         else:
@@ -202,7 +250,7 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
             check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(color), stream),
                   "splatco_blend_fwd")
         _debug_sync(settings, "blend_fwd")
-    st.R, st.geom, st.binning, st.image, st.radii, st.radii_full = R, geom, binning, image, radii, radii_full
+    st.R, st.RL, st.geom, st.binning, st.image, st.radii, st.radii_full = R, R, geom, binning, image, radii, radii_full
     return color, radii, st
 
 
@@ -210,7 +258,7 @@ def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotat
     """Backward pass; returns dict of gradients (all fp32, same row count as the inputs)."""
     L = _lib.lib()
     dev = means3D.device
-    P, R, H, W = st.P, st.R, st.H, st.W
+    P, R, H, W = st.P, st.RL, st.H, st.W          # RL: the binning workspace's layout size
     flat = torch.zeros(10 * P, dtype=torch.float32, device=dev)
     g_mean2D = flat[: 3 * P].view(P, 3)
     g_conic = flat[3 * P: 6 * P].view(P, 3)

@@ -46,7 +46,7 @@ def test_workspace_sizing_monotone_and_aligned():
     offs = (C.c_size_t * 8)()
     assert L.splatco_geom_layout(1000, offs, 8) == 6 and list(offs)[:6] == sorted(list(offs)[:6])
     assert L.splatco_binning_layout(5000, offs, 8) == 6
-    assert L.splatco_image_layout(545, 980, offs, 8) == 3
+    assert L.splatco_image_layout(545, 980, offs, 8) == 7
 
 
 def test_sort_pass_parity_matches_key_width():

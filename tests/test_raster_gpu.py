@@ -90,6 +90,37 @@ def test_forward_parity(seed, W, H, M, sig):
     assert_forward_parity(fw, color, radii, state)
 
 
+def test_binning_long_tiles_and_radix_composition_agree():
+    """Tiles with more instances than the shared-memory sort holds (8192) take the in-place global path;
+    the tile-segmented binning and the literal upstream composition (duplicateWithKeys + radix sort +
+    identifyTileRanges) must both reproduce the oracle's keys / permutation / ranges bit for bit."""
+    from splatco_b200 import _lib
+    from splatco_b200._lib import check, ptr
+    W, H, M = 64, 48, 70000
+    cam, means, colors, opac, scales, rots = scene(M, W, H, 77, sigma_px=(0.5, 3.0))
+    fw = oracle_forward(cam, means, colors, opac, scales, rots, [1.0, 1.0, 1.0])
+    bn = fw["bn"]
+    counts = bn.ranges[:, 1] - bn.ranges[:, 0]
+    assert counts.max() > 8192, f"scene does not exercise the long-tile path (max {counts.max()})"
+    color, radii, state, _ = gpu_forward(cam, means, colors, opac, scales, rots, [1.0, 1.0, 1.0])
+    g = assert_forward_parity(fw, color, radii, state)
+    # the radix composition on fresh workspaces
+    L = _lib.lib()
+    binning = torch.zeros_like(state.binning)
+    image = torch.zeros_like(state.image)
+    check(L.splatco_binning_radix(state.P, state.R, H, W, ptr(state.radii_full), ptr(state.geom), ptr(binning), ptr(image),
+                                  torch.cuda.current_stream().cuda_stream), "splatco_binning_radix")
+    torch.cuda.synchronize()
+    bo = layout("binning", state.R)
+    sidx = L.splatco_sorted_buffer_index(H, W)
+    keys = chunk(binning, bo[0 + sidx], torch.int64, state.R).cpu().numpy().view(np.uint64)
+    plist = chunk(binning, bo[2 + sidx], torch.int32, state.R).cpu().numpy().view(np.uint32)
+    io = layout("image", H, W)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    ranges = chunk(image, io[0], torch.int32, 2 * T).view(T, 2).cpu().numpy()
+    assert np.array_equal(keys, g["keys"]) and np.array_equal(plist, g["point_list"]) and np.array_equal(ranges, g["ranges"])
+
+
 def test_forward_parity_scale_modifier_and_debug():
     cam, means, colors, opac, scales, rots = scene(3000, 160, 120, 21)
     fw = oracle_forward(cam, means, colors, opac, scales, rots, [0, 0, 0], scale_mod=1.7)
