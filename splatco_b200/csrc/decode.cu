@@ -347,20 +347,29 @@ struct DecWeights {
 __device__ __forceinline__ int level_dim(int l, int rc) { return l == 0 ? 6 * rc : 3 * rc; }
 __device__ __forceinline__ int level_base(int l, int rc) { return l == 0 ? 0 : (l == 1 ? 6 * rc : 9 * rc); }
 
+// Launched with several CTAs: every output depends only on the batch statistics and the source weights, so
+// each CTA first derives mean / rstd of all channels into shared memory and then takes a grid-stride share of
+// every table; the BatchNorm running statistics are updated by CTA 0 alone.
+constexpr int FOLD_CTAS = 16;
 __global__ void __launch_bounds__(256)
 dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const double *__restrict__ stats,
                 float *__restrict__ mu, float *__restrict__ rstd, float *__restrict__ WpT, float *__restrict__ WcT,
                 float *__restrict__ bgeo, float *__restrict__ W1T, float *__restrict__ b1e, float *__restrict__ W2T,
                 float *__restrict__ b2, float *__restrict__ WpG, float *__restrict__ WcG, int update_running) {
+    __shared__ float s_mu[DEC_MAX_DP + GD + 4], s_rstd[DEC_MAX_DP + GD + 4];
     const int tid = threadIdx.x;
+    const int gtid = blockIdx.x * 256 + tid, nthr = gridDim.x * 256;
     const int ncols = DP + GD;
+    const bool first = blockIdx.x == 0;
     for (int c = tid; c < LDX; c += 256) {
-        if (c >= ncols) { mu[c] = 0.f; rstd[c] = 0.f; continue; }
+        if (c >= ncols) { s_mu[c] = 0.f; s_rstd[c] = 0.f; if (first) { mu[c] = 0.f; rstd[c] = 0.f; } continue; }
         const double mean = stats[c] / (double)V;
         double var = stats[LDX + c] / (double)V - mean * mean;
         if (var < 0.0) var = 0.0;
-        mu[c] = (float)mean;
-        rstd[c] = (float)(1.0 / sqrt(var + (double)w.eps));
+        s_mu[c] = (float)mean;
+        s_rstd[c] = (float)(1.0 / sqrt(var + (double)w.eps));
+        if (!first) continue;
+        mu[c] = s_mu[c]; rstd[c] = s_rstd[c];
         if (update_running) {
             const float unb = (float)(V > 1 ? var * (double)V / (double)(V - 1) : var);
             const float m = w.momentum;
@@ -378,53 +387,68 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
             }
         }
     }
-    if (update_running && tid == 0)
+    if (first && update_running && tid == 0)
         for (int l = 0; l <= level; ++l) {
             if (w.bn_nbt[l]) *w.bn_nbt[l] += 1;
             if (w.cbn_nbt[l]) *w.cbn_nbt[l] += 1;
         }
     __syncthreads();
     // plane branch
-    for (int e = tid; e < DP * 32; e += 256) {
+    for (int e = gtid; e < DP * 32; e += nthr) {
         const int c = e >> 5, o = e & 31;
         const int l = c < 6 * rc ? 0 : (c < 9 * rc ? 1 : 2);
         const int d = level_dim(l, rc), cl = c - level_base(l, rc);
         const float gw = w.bn_w[l][cl] * w.lin_w[l][o * d + cl];
         WpG[o * DP + c] = gw;
-        WpT[c * 32 + o] = gw * rstd[c];
+        WpT[c * 32 + o] = gw * s_rstd[c];
     }
     // context branch (all active levels normalise the same g with the same batch statistics)
-    for (int e = tid; e < GD * 32; e += 256) {
+    for (int e = gtid; e < GD * 32; e += nthr) {
         const int g = e >> 5, o = e & 31;
         float gw = 0.f;
         for (int l = 0; l <= level; ++l) gw = fmaf(w.cbn_w[l][g], w.clin_w[l][o * GD + g], gw);
         WcG[o * GD + g] = gw;
-        WcT[g * 32 + o] = gw * rstd[DP + g];
+        WcT[g * 32 + o] = gw * s_rstd[DP + g];
     }
-    __syncthreads();
-    // geo bias: Linear bias + beta through the Linear - mean through the folded weights
-    if (tid < 64) {
-        const int o = tid & 31;
-        float b = 0.f;
-        if (tid < 32) {
-            for (int l = 0; l <= level; ++l) {
-                const int d = level_dim(l, rc), base = level_base(l, rc);
-                b += w.lin_b[l][o];
-                for (int cl = 0; cl < d; ++cl) b = fmaf(w.bn_b[l][cl], w.lin_w[l][o * d + cl], b);
-                for (int cl = 0; cl < d; ++cl) b = fmaf(-mu[base + cl], WpT[(base + cl) * 32 + o], b);
+    // geo bias: Linear bias + beta through the Linear - mean through the folded weights; one warp per output,
+    // the warps of the whole grid share the 64 outputs
+    {
+        const int lane = tid & 31, gw_id = gtid >> 5, nwarps = nthr >> 5;
+        for (int out = gw_id; out < 64; out += nwarps) {
+            const int o = out & 31;
+            float b = 0.f;
+            if (out < 32) {
+                for (int l = 0; l <= level; ++l) {
+                    const int d = level_dim(l, rc), base = level_base(l, rc);
+                    for (int cl = lane; cl < d; cl += 32) {
+                        const float lw = w.lin_w[l][o * d + cl];
+                        b = fmaf(w.bn_b[l][cl], lw, b);
+                        b = fmaf(-s_mu[base + cl], w.bn_w[l][cl] * lw * s_rstd[base + cl], b);
+                    }
+                }
+            } else {
+                for (int g = lane; g < GD; g += 32) {
+                    float gwsum = 0.f;
+                    for (int l = 0; l <= level; ++l) {
+                        const float lw = w.clin_w[l][o * GD + g];
+                        b = fmaf(w.cbn_b[l][g], lw, b);
+                        gwsum = fmaf(w.cbn_w[l][g], lw, gwsum);
+                    }
+                    b = fmaf(-s_mu[DP + g], gwsum * s_rstd[DP + g], b);
+                }
             }
-        } else {
-            for (int l = 0; l <= level; ++l) {
-                b += w.clin_b[l][o];
-                for (int g = 0; g < GD; ++g) b = fmaf(w.cbn_b[l][g], w.clin_w[l][o * GD + g], b);
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) b += __shfl_xor_sync(0xffffffffu, b, dd);
+            if (lane == 0) {
+                float bias = 0.f;
+                for (int l = 0; l <= level; ++l) bias += out < 32 ? w.lin_b[l][o] : w.clin_b[l][o];
+                bgeo[out] = b + bias;
             }
-            for (int g = 0; g < GD; ++g) b = fmaf(-mu[DP + g], WcT[g * 32 + o], b);
         }
-        bgeo[tid] = b;
     }
     // hidden layer: x100 = [feat 32 | dir 3 | dist 1 | geo 64]; per-head torch layout is
     // [feat | dir | (dist) | geo | (appearance, colour head only)]
-    for (int e = tid; e < XI * HD; e += 256) {
+    for (int e = gtid; e < XI * HD; e += nthr) {
         const int k = e / HD, n = e - k * HD;
         const int hd = n >> 5, o = n & 31;
         const int dd = w.use_dist[hd];
@@ -435,18 +459,18 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
         else v = w.w1[hd][o * in_h + 35 + dd + (k - 36)];
         W1T[e] = v;
     }
-    if (tid < HD) {
-        const int hd = tid >> 5, o = tid & 31;
+    for (int n = gtid; n < HD; n += nthr) {
+        const int hd = n >> 5, o = n & 31;
         float b = w.b1[hd][o];
         if (hd == 2 && w.app_dim > 0) {
             const int dd = w.use_dist[2];
             const int in_h = 35 + dd + 64 + w.app_dim;
             for (int a = 0; a < w.app_dim; ++a) b = fmaf(w.w1[2][o * in_h + 35 + dd + 64 + a], w.app_vec[a], b);
         }
-        b1e[tid] = b;
+        b1e[n] = b;
     }
     // output layer as one block-diagonal [96][112] operand: cols [opacity 0..9 | cov 10..79 | colour 80..109]
-    for (int e = tid; e < HD * ZD; e += 256) {
+    for (int e = gtid; e < HD * ZD; e += nthr) {
         const int i = e / ZD, j = e - i * ZD;
         const int hd_i = i >> 5, ii = i & 31;
         float v = 0.f;
@@ -455,12 +479,12 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
         else if (j < 11 * KO) { if (hd_i == 2) v = w.w2[2][(j - 8 * KO) * 32 + ii]; }
         W2T[e] = v;
     }
-    if (tid < ZD) {
+    for (int j = gtid; j < ZD; j += nthr) {
         float v = 0.f;
-        if (tid < KO) v = w.b2[0][tid];
-        else if (tid < 8 * KO) v = w.b2[1][tid - KO];
-        else if (tid < 11 * KO) v = w.b2[2][tid - 8 * KO];
-        b2[tid] = v;
+        if (j < KO) v = w.b2[0][j];
+        else if (j < 8 * KO) v = w.b2[1][j - KO];
+        else if (j < 11 * KO) v = w.b2[2][j - 8 * KO];
+        b2[j] = v;
     }
 }
 
@@ -650,11 +674,11 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
                     const float *__restrict__ S0 /*[64]*/, const float *__restrict__ gW1T, const float *__restrict__ gb1,
                     const float *__restrict__ gW2T, const float *__restrict__ gb2, float *__restrict__ m1,
                     float *__restrict__ m2) {
-    const int tid = threadIdx.x;
+    const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;      // every output is independent
     const int ncols = DP + GD;
     const float invV = 1.f / (float)V;
     // S1[o][c] = sum_rows dgeo[o] * xhat[c] = rstd[c] * (S1raw[o][c] - mu[c] * S0branch[o])
-    for (int c = tid; c < LDX; c += 256) {
+    for (int c = tid; c < LDX; c += nthr) {
         if (c >= ncols) { m1[c] = 0.f; m2[c] = 0.f; continue; }
         const bool pl = c < DP;
         const float *WG = pl ? WpG : WcG;
@@ -672,12 +696,12 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
     // plane branch parameter grads
     for (int l = 0; l <= level; ++l) {
         const int d = level_dim(l, rc), base = level_base(l, rc);
-        for (int e = tid; e < 32 * d; e += 256) {
+        for (int e = tid; e < 32 * d; e += nthr) {
             const int o = e / d, cl = e - o * d, c = base + cl;
             const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[o]);
             if (gw.lin_w[l]) gw.lin_w[l][o * d + cl] += w.bn_w[l][cl] * s1 + w.bn_b[l][cl] * S0[o];
         }
-        for (int cl = tid; cl < d; cl += 256) {
+        for (int cl = tid; cl < d; cl += nthr) {
             const int c = base + cl;
             float gg = 0.f, gb = 0.f;
             for (int o = 0; o < 32; ++o) {
@@ -688,14 +712,14 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
             if (gw.bn_w[l]) gw.bn_w[l][cl] += gg;
             if (gw.bn_b[l]) gw.bn_b[l][cl] += gb;
         }
-        if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] += S0[tid];
+        if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] += S0[tid];      // tid is grid-wide: only CTA 0 has tid < 32
         // context branch
-        for (int e = tid; e < 32 * GD; e += 256) {
+        for (int e = tid; e < 32 * GD; e += nthr) {
             const int o = e / GD, g = e - o * GD, c = DP + g;
             const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[32 + o]);
             if (gw.clin_w[l]) gw.clin_w[l][o * GD + g] += w.cbn_w[l][g] * s1 + w.cbn_b[l][g] * S0[32 + o];
         }
-        for (int g = tid; g < GD; g += 256) {
+        for (int g = tid; g < GD; g += nthr) {
             const int c = DP + g;
             float gg = 0.f, gb = 0.f;
             for (int o = 0; o < 32; ++o) {
@@ -714,7 +738,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
         const int app = hd == 2 ? w.app_dim : 0;
         const int in_h = 35 + dd + 64 + app;
         if (gw.w1[hd])
-            for (int e = tid; e < 32 * in_h; e += 256) {
+            for (int e = tid; e < 32 * in_h; e += nthr) {
                 const int o = e / in_h, col = e - o * in_h;
                 const int n = hd * 32 + o;
                 float v;
@@ -728,17 +752,17 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
         const int nout = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO);
         const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO);
         if (gw.w2[hd])
-            for (int e = tid; e < nout * 32; e += 256) {
+            for (int e = tid; e < nout * 32; e += nthr) {
                 const int j = e >> 5, ii = e & 31;
                 gw.w2[hd][e] += gW2T[(hd * 32 + ii) * ZD + j0 + j];
             }
         if (gw.b2[hd])
-            for (int j = tid; j < nout; j += 256) gw.b2[hd][j] += gb2[j0 + j];
+            for (int j = tid; j < nout; j += nthr) gw.b2[hd][j] += gb2[j0 + j];
     }
     if (gw.app_vec && w.app_dim > 0) {
         const int dd = w.use_dist[2];
         const int in_h = 35 + dd + 64 + w.app_dim;
-        for (int a = tid; a < w.app_dim; a += 256) {
+        for (int a = tid; a < w.app_dim; a += nthr) {
             float s = 0.f;
             for (int o = 0; o < 32; ++o) s = fmaf(w.w1[2][o * in_h + 35 + dd + 64 + a], gb1[64 + o], s);
             gw.app_vec[a] += s;
@@ -944,16 +968,16 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
     dec_gather_kernel<<<gather_grid(V), GATHER_WARPS * 32, GATHER_WARPS * 2 * dd.LDX * sizeof(float), st>>>(
         p, V, dd.rc, dd.DP, dd.LDX, f.X, f.XIN, f.stats, use_tc ? f.XT : nullptr);
     SPLATCO_CHECK_LAUNCH();
-    dec_fold_kernel<<<1, 256, 0, st>>>(w, V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
+    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
                                        f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
     SPLATCO_CHECK_LAUNCH();
     const int nb = ceil_div(V, 256);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.bsum, 0, (size_t)nb * sizeof(uint32_t), st));
     if (use_tc) {
         // fused tcgen05 path: geo -> hidden -> heads -> activations in one persistent kernel
-        dec_tc_pack_kernel<<<1, 256, 0, st>>>(dd.DP, f.WpT, f.WcT, f.W1T, f.W2T, f.BA, f.W1B, f.W2B);
+        dec_tc_pack_kernel<<<12, 256, 0, st>>>(dd.DP, f.WpT, f.WcT, f.W1T, f.W2T, f.BA, f.W1B, f.W2B);
         SPLATCO_CHECK_LAUNCH();
-        dec_tc_pack_bwd_kernel<<<1, 256, 0, st>>>(dd.DP, f.W2T, f.W1T, f.WpG, f.WcG, f.W2R, f.W1R, f.WPCR);   // for the backward
+        dec_tc_pack_bwd_kernel<<<12, 256, 0, st>>>(dd.DP, f.W2T, f.W1T, f.WpG, f.WcG, f.W2R, f.W1R, f.WPCR);   // for the backward
         SPLATCO_CHECK_LAUNCH();
         static bool attr_set = false;
         if (!attr_set) {
@@ -1058,14 +1082,12 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     }
     // weight gradients: gW2T += H^T dZ (block-diagonal), gW1T += X100^T dH, S1raw = dgeo^T X (both branches)
     {
-        TnGroup grp;
+        WgGroup grp;
         grp.count = 0;
-        int tiles = 0;
         auto add = [&](int M, int N, const float *A, int lda, const float *B, int ldb, float *C, int ldc) {
-            TnProblem &q = grp.p[grp.count++];
+            WgProblem &q = grp.p[grp.count++];
             q.A = A; q.B = B; q.C = C; q.M = M; q.N = N; q.lda = lda; q.ldb = ldb; q.ldc = ldc;
-            q.tile0 = tiles; q.tiles_n = ceil_div(N, 64);
-            tiles += ceil_div(M, 64) * q.tiles_n;
+            q.shape = M > 32 ? 4 : (N <= 16 ? 0 : (N <= 32 ? 1 : (N <= 64 ? 2 : 3)));
         };
         for (int hd = 0; hd < 3; ++hd) {
             const int j0 = hd == 0 ? 0 : (hd == 1 ? KO : 8 * KO), nj = hd == 0 ? KO : (hd == 1 ? 7 * KO : 3 * KO), i0 = 32 * hd;
@@ -1074,10 +1096,22 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
         add(XI, HD, f.XIN, XI, b.DH, HD, b.gW1T, HD);
         add(32, DP, b.DX + 36, XI, f.X, LDX, b.S1, LDX);
         add(32, GD, b.DX + 68, XI, f.X + DP, LDX, b.S1 + DP, LDX);
-        sgemm_tn64_grouped_kernel<<<dim3(ceil_div(V, KCH), tiles), 256, 0, st>>>(grp, V, KCH);
+        // deal ~2 CTAs per SM to the problems in proportion to their (padded) FMA counts
+        static const int kWork[5] = {2 * 1, 2 * 2, 2 * 4, 2 * 5, 8 * 6};
+        int total = 0;
+        for (int i = 0; i < grp.count; ++i) total += kWork[grp.p[i].shape];
+        const int budget = 2 * 148, max_slices = max(1, ceil_div(V, 2 * WG_KB));
+        int ctas = 0;
+        for (int i = 0; i < grp.count; ++i) {
+            WgProblem &q = grp.p[i];
+            q.nslices = min(max_slices, max(1, budget * kWork[q.shape] / total));
+            q.cta0 = ctas;
+            ctas += q.nslices;
+        }
+        dec_wgrad_kernel<<<ctas, 256, 0, st>>>(grp, V);
         SPLATCO_CHECK_LAUNCH();
     }
-    dec_bwd_fold_kernel<<<1, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+    dec_bwd_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                            b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();
     dec_bwd_inputs_kernel<<<gather_grid(V), GATHER_WARPS * 32, 0, st>>>(p, gi, V, dd.rc, DP, LDX, f.X, f.XIN, f.mu, f.rstd,

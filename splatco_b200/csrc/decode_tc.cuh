@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(256)
 dec_tc_pack_kernel(int DP, const float *__restrict__ WpT, const float *__restrict__ WcT, const float *__restrict__ W1T,
                    const float *__restrict__ W2T, uint8_t *__restrict__ BA, uint8_t *__restrict__ W1B,
                    uint8_t *__restrict__ W2B) {
-    const int tid = threadIdx.x;
+    const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
     // stage A: rows n < 32; chunks 0..15 Wp (k = P channel), 16..33 Wc (k = g channel)
-    for (int e = tid; e < 34 * 32; e += 256) {
+    for (int e = tid; e < 34 * 32; e += nthr) {
         const int c = e >> 5, n = e & 31;
         float w[4];
 #pragma unroll
@@ -58,7 +58,7 @@ dec_tc_pack_kernel(int DP, const float *__restrict__ WpT, const float *__restric
         *reinterpret_cast<float4 *>(BA + TC_BA_HALF + (size_t)e * 16) = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
     }
     // stage B: rows n < 96, K order = x100 (feat | dir,dist | geo), 26 chunks
-    for (int e = tid; e < 26 * 96; e += 256) {
+    for (int e = tid; e < 26 * 96; e += nthr) {
         const int c = e / 96, n = e - c * 96;
         float w[4];
 #pragma unroll
@@ -68,7 +68,7 @@ dec_tc_pack_kernel(int DP, const float *__restrict__ WpT, const float *__restric
         *reinterpret_cast<float4 *>(W1B + TC_W1_HALF + (size_t)e * 16) = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
     }
     // stage C: rows n < 112, K = hidden index, 24 chunks
-    for (int e = tid; e < 24 * 112; e += 256) {
+    for (int e = tid; e < 24 * 112; e += nthr) {
         const int c = e / 112, n = e - c * 112;
         float w[4];
 #pragma unroll
@@ -124,11 +124,23 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
             tc::bulk_g2s(sm + TC_OFF_B, BA, 2 * TC_BA_HALF, &barL);
         }
         const float4 *xt = reinterpret_cast<const float4 *>(XT) + (size_t)tile * nch * TC_ROWS;
-        for (int c = 0; c < nch; ++c) {
-            const float4 x = xt[c * TC_ROWS + tid];
-            const int sc = c < npc ? 1 + c : (c < npc + 18 ? 18 + (c - npc) : 0);
-            const float v4[4] = {x.x, x.y, x.z, x.w};
-            tc_store_split(sm, sc, tid, v4);
+        // 8 independent 16-byte loads in flight per thread (one dependent load per chunk made this loop the
+        // kernel's critical path: ~34 serialized L2 round trips per tile)
+#pragma unroll 1
+        for (int c0 = 0; c0 < nch; c0 += 8) {
+            float4 x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (c0 + q < nch) x[q] = __ldg(xt + (c0 + q) * TC_ROWS + tid);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = c0 + q;
+                if (c < nch) {
+                    const int sc = c < npc ? 1 + c : (c < npc + 18 ? 18 + (c - npc) : 0);
+                    const float v4[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
+                    tc_store_split(sm, sc, tid, v4);
+                }
+            }
         }
         for (int pc = npc; pc < TC_NP + 1; ++pc) {          // zero the P padding chunks and chunk 17
             const uint32_t off = (uint32_t)(1 + pc) * TC_CHUNK + (uint32_t)tid * 16u;

@@ -28,34 +28,34 @@ __global__ void __launch_bounds__(256)
 dec_tc_pack_bwd_kernel(int DP, const float *__restrict__ W2T, const float *__restrict__ W1T,
                        const float *__restrict__ WpG, const float *__restrict__ WcG, uint8_t *__restrict__ W2R,
                        uint8_t *__restrict__ W1R, uint8_t *__restrict__ WPCR) {
-    const int tid = threadIdx.x;
+    const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
     auto put = [](uint8_t *dst, uint32_t half, size_t e, const float *w) {
         const float4 h = make_float4(tc::tf32_hi(w[0]), tc::tf32_hi(w[1]), tc::tf32_hi(w[2]), tc::tf32_hi(w[3]));
         *reinterpret_cast<float4 *>(dst + e * 16) = h;
         *reinterpret_cast<float4 *>(dst + half + e * 16) = make_float4(w[0] - h.x, w[1] - h.y, w[2] - h.z, w[3] - h.w);
     };
-    for (int e = tid; e < 28 * HD; e += 256) {                // B[i][j] = W2T[i][j]
+    for (int e = tid; e < 28 * HD; e += nthr) {                // B[i][j] = W2T[i][j]
         const int c = e / HD, i = e - c * HD;
         float w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[q] = W2T[i * ZD + 4 * c + q];
         put(W2R, TCB_W2R_HALF, e, w);
     }
-    for (int e = tid; e < 24 * ZD; e += 256) {                // B[n][k] = W1T[n][k], rows >= 100 zero
+    for (int e = tid; e < 24 * ZD; e += nthr) {                // B[n][k] = W1T[n][k], rows >= 100 zero
         const int c = e / ZD, n = e - c * ZD;
         float w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[q] = n < XI ? W1T[n * HD + 4 * c + q] : 0.f;
         put(W1R, TCB_W1R_HALF, e, w);
     }
-    for (int e = tid; e < 8 * TCB_NP; e += 256) {             // B[c][o] = WpG[o][c]
+    for (int e = tid; e < 8 * TCB_NP; e += nthr) {             // B[c][o] = WpG[o][c]
         const int c8 = e / TCB_NP, n = e - c8 * TCB_NP;
         float w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) w[q] = n < DP ? WpG[(4 * c8 + q) * DP + n] : 0.f;
         put(WPCR, TCB_WPC_HALF, e, w);
     }
-    for (int e = tid; e < 8 * TCB_NC; e += 256) {             // B[g][o] = WcG[o][g]
+    for (int e = tid; e < 8 * TCB_NC; e += nthr) {             // B[g][o] = WcG[o][g]
         const int c8 = e / TCB_NC, n = e - c8 * TCB_NC;
         float w[4];
 #pragma unroll
@@ -118,19 +118,35 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
             tc::bulk_g2s(sm + TCB_OFF_B, W2R, 2 * TCB_W2R_HALF, &barL);
         }
         const float4 *zrow = reinterpret_cast<const float4 *>(DZ + (size_t)row * ZD);
-#pragma unroll 1
-        for (int c = 0; c < TCB_ACH; c += 2) {
-            float v[8];
-            if (valid) {
-                const float4 x0 = zrow[c], x1 = zrow[c + 1];
-                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-            } else {
+        // the ReLU gate of epilogue 1 as 96 bits, so that its H row loads are issued here, all independent,
+        // instead of one dependent round trip per 8 columns inside the TMEM read-out loop
+        uint32_t hbits[3] = {0u, 0u, 0u};
+        if (valid) {
+            const float4 *hrow = reinterpret_cast<const float4 *>(Hs + (size_t)row * HD);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = 0.f;
+            for (int w = 0; w < 3; ++w) {
+                float4 h[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = __ldg(hrow + 8 * w + q);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    hbits[w] |= (h[q].x > 0.f ? 1u : 0u) << (4 * q) | (h[q].y > 0.f ? 2u : 0u) << (4 * q) |
+                                (h[q].z > 0.f ? 4u : 0u) << (4 * q) | (h[q].w > 0.f ? 8u : 0u) << (4 * q);
             }
-            tcb_store_split(sm, c, tid, v);
-            tcb_store_split(sm, c + 1, tid, v + 4);
-            colsum8_add(v, lane, gb2 + 4 * c, ZD - 4 * c);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < TCB_ACH; c0 += 14) {               // two halves of the dZ row, 14 loads in flight each
+            float4 x[14];
+#pragma unroll
+            for (int q = 0; q < 14; ++q) x[q] = valid ? __ldg(zrow + c0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 14; q += 2) {
+                const int c = c0 + q;
+                const float v[8] = {x[q].x, x[q].y, x[q].z, x[q].w, x[q + 1].x, x[q + 1].y, x[q + 1].z, x[q + 1].w};
+                tcb_store_split(sm, c, tid, v);
+                tcb_store_split(sm, c + 1, tid, v + 4);
+                colsum8_add(v, lane, gb2 + 4 * c, ZD - 4 * c);
+            }
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -148,16 +164,15 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
             tc::bulk_g2s(sm + TCB_OFF_B, W1R, 2 * TCB_W1R_HALF, &barL);
         }
         // ---- epilogue 1: ReLU gate, dH -> global + stage-2 operand chunks 0..23, gb1 ------------------------------
-        const float4 *hrow = reinterpret_cast<const float4 *>(Hs + (size_t)row * HD);
 #pragma unroll 1
         for (int n0 = 0; n0 < HD; n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
             if (valid) {
-                const float4 h0 = hrow[n0 / 4], h1 = hrow[n0 / 4 + 1];
-                v[0] = h0.x > 0.f ? v[0] : 0.f; v[1] = h0.y > 0.f ? v[1] : 0.f; v[2] = h0.z > 0.f ? v[2] : 0.f; v[3] = h0.w > 0.f ? v[3] : 0.f;
-                v[4] = h1.x > 0.f ? v[4] : 0.f; v[5] = h1.y > 0.f ? v[5] : 0.f; v[6] = h1.z > 0.f ? v[6] : 0.f; v[7] = h1.w > 0.f ? v[7] : 0.f;
+                const uint32_t gate = (n0 < 32 ? hbits[0] : (n0 < 64 ? hbits[1] : hbits[2])) >> (n0 & 31);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = (gate >> q) & 1u ? v[q] : 0.f;
                 float4 *dst = reinterpret_cast<float4 *>(DH + (size_t)row * HD + n0);
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -247,64 +262,100 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
     if (warp == 0) tc::tmem_dealloc<256>(tmem);
 }
 
-// ---- grouped split-K  C_p[M,N] += A_p^T B_p  (weight-gradient reductions over anchors) ------------------------
-// All products of one backward pass share K = V, so they are launched as ONE grid: blockIdx.y walks the
-// 64x64 output tiles of every problem, blockIdx.x the K slices.  Each problem alone is a single wave of
-// latency-bound CTAs; together they keep ~10 CTAs per SM in flight.  4x4 register blocks.
-struct TnProblem { const float *A; const float *B; float *C; int M, N, lda, ldb, ldc, tile0, tiles_n; };
-constexpr int TN_MAX_PROBLEMS = 8;
-struct TnGroup { TnProblem p[TN_MAX_PROBLEMS]; int count; };
+// ---- weight-gradient reductions over anchors:  C_p[M,N] += A_p[:, :M]^T B_p[:, :N]  ---------------------------
+// Every product of a backward pass has a SMALL output (at most 100 x 96) and a long reduction (K = V visible
+// anchors), so one CTA keeps a whole output matrix in registers (16 x 16 threads, TM x TN each) and walks a
+// slice of the rows: operands are read exactly once, staged 32 rows at a time through shared memory with the
+// next block's global loads in flight during the FMAs, and the partial result is added with fp32 REDs.
+// CTAs are dealt to the problems in proportion to their FMA count (blockIdx.x -> problem via cta0[]).
+struct WgProblem { const float *A; const float *B; float *C; int M, N, lda, ldb, ldc, cta0, nslices, shape; };
+constexpr int WG_MAX_PROBLEMS = 8;
+struct WgGroup { WgProblem p[WG_MAX_PROBLEMS]; int count; };
+constexpr int WG_KB = 32;                        // rows per shared-memory block
+constexpr int WG_SMEM_FLOATS = WG_KB * (128 + 96);
 
-__global__ void __launch_bounds__(256)
-sgemm_tn64_grouped_kernel(TnGroup g, int K, int kchunk) {
-    __shared__ __align__(16) float As[16][68];
-    __shared__ __align__(16) float Bs[16][68];
-    int pi = 0;
-#pragma unroll
-    for (int i = 1; i < TN_MAX_PROBLEMS; ++i)
-        if (i < g.count && (int)blockIdx.y >= g.p[i].tile0) pi = i;
-    const TnProblem &pr = g.p[pi];
-    const int t = blockIdx.y - pr.tile0;
-    const int m0 = (t / pr.tiles_n) * 64, n0 = (t % pr.tiles_n) * 64;
-    const int M = pr.M, N = pr.N, lda = pr.lda, ldb = pr.ldb;
+template <int TM, int TN>
+__device__ __forceinline__ void wgrad_body(const WgProblem &pr, int kbeg, int kend, float *smem) {
+    constexpr int MP = TM * 16, NP = TN * 16;
+    constexpr int NA = (WG_KB * MP + 255) / 256, NB = (WG_KB * NP + 255) / 256;
+    float *As = smem, *Bs = smem + WG_KB * MP;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const float *__restrict__ A = pr.A;
     const float *__restrict__ B = pr.B;
-    const int tid = threadIdx.x;
-    const int kbeg = blockIdx.x * kchunk, kend = min(K, kbeg + kchunk);
-    const int ty = tid >> 4, tx = tid & 15;
-    float acc[4][4] = {};
-    for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    const int M = pr.M, N = pr.N, lda = pr.lda, ldb = pr.ldb;
+    float acc[TM][TN];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int e = tid + i * 256, c = e & 63, k = e >> 6;
-            const int gk = k0 + k;
-            As[k][c] = (gk < kend && m0 + c < M) ? A[(size_t)gk * lda + m0 + c] : 0.f;
-            Bs[k][c] = (gk < kend && n0 + c < N) ? B[(size_t)gk * ldb + n0 + c] : 0.f;
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    float ra[NA], rb[NB];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) {
+            const int e = tid + q * 256, r = e / MP, c = e - r * MP;
+            ra[q] = (e < WG_KB * MP && c < M && k0 + r < kend) ? __ldg(A + (size_t)(k0 + r) * lda + c) : 0.f;
         }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) {
+            const int e = tid + q * 256, r = e / NP, c = e - r * NP;
+            rb[q] = (e < WG_KB * NP && c < N && k0 + r < kend) ? __ldg(B + (size_t)(k0 + r) * ldb + c) : 0.f;
+        }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += WG_KB) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) { const int e = tid + q * 256; if (e < WG_KB * MP) As[e] = ra[q]; }
+#pragma unroll
+        for (int q = 0; q < NB; ++q) { const int e = tid + q * 256; if (e < WG_KB * NP) Bs[e] = rb[q]; }
         __syncthreads();
+        if (k0 + WG_KB < kend) fetch(k0 + WG_KB);
+#pragma unroll 4
+        for (int k = 0; k < WG_KB; ++k) {
+            float a[TM], b[TN];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            for (int i = 0; i < TM; ++i) a[i] = As[k * MP + ty * TM + i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k * NP + tx * TN + j];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
     float *__restrict__ C = pr.C;
-    const int ldc = pr.ldc;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int gm = m0 + ty * 4 + i;
-        if (gm >= M) continue;
+    for (int i = 0; i < TM; ++i) {
+        const int m = ty * TM + i;
+        if (m >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
-            if (gn < N && acc[i][j] != 0.f) atomicAdd(&C[(size_t)gm * ldc + gn], acc[i][j]);
+        for (int j = 0; j < TN; ++j) {
+            const int n = tx * TN + j;
+            if (n < N && acc[i][j] != 0.f) atomicAdd(&C[(size_t)m * pr.ldc + n], acc[i][j]);
         }
+    }
+}
+
+// output-shape classes (TM x TN per thread): 0: 32 x <=16   1: 32 x <=32   2: 32 x <=64   3: 32 x <=80   4: <=128 x <=96
+__global__ void __launch_bounds__(256)
+dec_wgrad_kernel(WgGroup g, int K) {
+    __shared__ __align__(16) float smem[WG_SMEM_FLOATS];
+    int pi = 0;
+#pragma unroll
+    for (int i = 1; i < WG_MAX_PROBLEMS; ++i)
+        if (i < g.count && (int)blockIdx.x >= g.p[i].cta0) pi = i;
+    const WgProblem &pr = g.p[pi];
+    const int slice = blockIdx.x - pr.cta0;
+    const int rows = (K + pr.nslices - 1) / pr.nslices;
+    const int per = (rows + WG_KB - 1) / WG_KB * WG_KB;         // slices start on block boundaries
+    const int kbeg = slice * per, kend = min(K, kbeg + per);
+    if (kbeg >= kend) return;
+    switch (pr.shape) {
+        case 0: wgrad_body<2, 1>(pr, kbeg, kend, smem); break;
+        case 1: wgrad_body<2, 2>(pr, kbeg, kend, smem); break;
+        case 2: wgrad_body<2, 4>(pr, kbeg, kend, smem); break;
+        case 3: wgrad_body<2, 5>(pr, kbeg, kend, smem); break;
+        default: wgrad_body<8, 6>(pr, kbeg, kend, smem); break;
     }
 }
 
