@@ -82,3 +82,27 @@ def check(rc: int, what: str):
 def ptr(t):
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+# ---- cheap per-call plumbing (these run dozens of times per view; the torch.cuda wrappers cost ~10 us each) ----
+import contextlib as _contextlib
+
+import torch as _torch
+
+_NULL = _contextlib.nullcontext()
+
+
+def raw_stream(device) -> int:
+    """cudaStream_t of torch's current stream on `device`, as an int."""
+    idx = device.index
+    if idx is None:
+        idx = _torch.cuda.current_device()
+    return _torch._C._cuda_getCurrentRawStream(idx)
+
+
+def on_device(device):
+    """Context that makes `device` current; a no-op object when it already is (the common case)."""
+    idx = device.index
+    if idx is None or idx == _torch.cuda.current_device():
+        return _NULL
+    return _torch.cuda.device(device)

@@ -48,7 +48,7 @@ size_t bin_offsets(int64_t R, size_t off[7]) {
     return o;
 }
 
-size_t img_offsets(int H, int W, size_t off[8]) {
+size_t img_offsets(int H, int W, size_t off[9]) {
     const size_t T = (size_t)ceil_div(W, TILE) * ceil_div(H, TILE);
     const size_t hw = (size_t)H * W;
     size_t o = 0;
@@ -59,7 +59,8 @@ size_t img_offsets(int H, int W, size_t off[8]) {
     off[4] = o; o += align_up(T * sizeof(uint32_t));      // cursor
     off[5] = o; o += align_up(3 * T * sizeof(uint32_t));  // per-size-class tile lists of the per-tile sort
     off[6] = o; o += align_up(8 * sizeof(uint32_t));      // list lengths / queue heads
-    off[7] = o;
+    off[7] = o; o += align_up(T * sizeof(uint32_t));      // blend launch order (longest tiles first)
+    off[8] = o;
     return o;
 }
 
@@ -92,7 +93,7 @@ BinWs bin_view(void *base, int64_t R) {
 }
 
 ImgWs img_view(void *base, int H, int W) {
-    size_t off[8];
+    size_t off[9];
     img_offsets(H, W, off);
     char *b = (char *)base;
     ImgWs w;
@@ -103,6 +104,7 @@ ImgWs img_view(void *base, int H, int W) {
     w.cursor = (uint32_t *)(b + off[4]);
     w.lists = (uint32_t *)(b + off[5]);
     w.work = (uint32_t *)(b + off[6]);
+    w.order = (uint32_t *)(b + off[7]);
     return w;
 }
 
@@ -116,7 +118,7 @@ extern "C" uint64_t splatco_launch_count(void) { return (uint64_t)launch_count()
 
 extern "C" size_t splatco_geom_bytes(int P) { size_t off[7]; return geom_offsets(P, off); }
 extern "C" size_t splatco_binning_bytes(int64_t R) { size_t off[7]; return bin_offsets(R, off); }
-extern "C" size_t splatco_image_bytes(int H, int W) { size_t off[8]; return img_offsets(H, W, off); }
+extern "C" size_t splatco_image_bytes(int H, int W) { size_t off[9]; return img_offsets(H, W, off); }
 
 static int copy_layout(const size_t *src, int n, size_t *dst, int max_chunks) {
     int k = n < max_chunks ? n : max_chunks;
@@ -130,5 +132,5 @@ extern "C" int splatco_binning_layout(int64_t R, size_t *offsets, int max_chunks
     size_t off[7]; bin_offsets(R, off); return copy_layout(off, 6, offsets, max_chunks);
 }
 extern "C" int splatco_image_layout(int H, int W, size_t *offsets, int max_chunks) {
-    size_t off[8]; img_offsets(H, W, off); return copy_layout(off, 7, offsets, max_chunks);
+    size_t off[9]; img_offsets(H, W, off); return copy_layout(off, 8, offsets, max_chunks);
 }

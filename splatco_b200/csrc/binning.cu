@@ -508,6 +508,46 @@ tile_sort_global_kernel(const int2 *__restrict__ ranges, uint64_t *__restrict__ 
     }
 }
 
+// ---- launch order of the blend CTAs: longest tiles first ------------------------------------------------------
+// The blend kernels run one CTA per tile and a tile's cost is ~ its instance count; started in raster order the
+// few very long tiles that happen to sit late in the grid finish alone at the end of the kernel.  A counting sort
+// of the tiles on (count / 8, capped) in descending order is enough (one CTA, O(T)).
+constexpr int ORDER_BUCKETS = 2048;
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(int T, const int2 *__restrict__ ranges, uint32_t *__restrict__ order) {
+    __shared__ uint32_t s_cnt[ORDER_BUCKETS];
+    __shared__ uint32_t s_warp[32];
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += 1024) s_cnt[i] = 0;
+    __syncthreads();
+    auto bucket = [&](int t) {
+        const int2 r = ranges[t];
+        const int c = (r.y - r.x) >> 3;
+        return ORDER_BUCKETS - 1 - min(c, ORDER_BUCKETS - 1);      // bucket 0 = longest
+    };
+    for (int t = threadIdx.x; t < T; t += 1024) atomicAdd(&s_cnt[bucket(t)], 1u);
+    __syncthreads();
+    // exclusive scan of the 2048 counters: two per thread
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t a = s_cnt[2 * threadIdx.x], b = s_cnt[2 * threadIdx.x + 1];
+    uint32_t inc = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += n; }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t n = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= (uint32_t)d) winc += n; }
+        s_warp[lane] = winc - w;
+    }
+    __syncthreads();
+    const uint32_t excl = s_warp[warp] + inc - (a + b);
+    s_cnt[2 * threadIdx.x] = excl;
+    s_cnt[2 * threadIdx.x + 1] = excl + a;
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += 1024) order[atomicAdd(&s_cnt[bucket(t)], 1u)] = (uint32_t)t;
+}
+
 constexpr int TSORT_ITEMS_S = 4, TSORT_ITEMS_L = 16;          // 2048 / 8192 elements per CTA
 constexpr size_t tsort_smem(int items) { return (size_t)(4 * 512 * items + 16 * 256) * sizeof(uint32_t); }
 
@@ -587,7 +627,12 @@ extern "C" int splatco_binning_radix(int P, int64_t R, int H, int W, const int32
     if (rc) return rc;
     rc = splatco_sort_pairs(R, H, W, binning, stream);
     if (rc) return rc;
-    return splatco_identify_tile_ranges(R, H, W, binning, image, stream);
+    rc = splatco_identify_tile_ranges(R, H, W, binning, image, stream);
+    if (rc) return rc;
+    ImgWs im = img_view(image, H, W);
+    tile_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ceil_div(W, TILE) * ceil_div(H, TILE), im.ranges, im.order);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
@@ -642,6 +687,8 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     SPLATCO_CHECK_LAUNCH();
     tile_sort_global_kernel<<<min(T, 148), TSORT_THREADS, 0, st>>>(im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s],
                                                                    im.lists + 2 * (size_t)T, im.work);
+    SPLATCO_CHECK_LAUNCH();
+    tile_order_kernel<<<1, 1024, 0, st>>>(T, im.ranges, im.order);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

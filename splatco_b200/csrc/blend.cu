@@ -24,6 +24,9 @@
 namespace splatco {
 
 constexpr int BLEND_THREADS = TILE * TILE;   // 256
+constexpr int BLEND_BATCH = 2 * BLEND_THREADS;   // splats staged per barrier (two per thread): half the barriers of a
+                                                 // 256-splat batch, and the per-warp work imbalance averages out better
+constexpr int BLEND_WORDS = BLEND_BATCH / 32;    // 16 mask words per patch warp
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLog2Inv255 = -7.994353436858858f;     // log2(1/255)
 
@@ -81,28 +84,28 @@ __device__ __forceinline__ SplatCoef splat_setup(float sx, float sy, float A, fl
     return s;
 }
 
-// turn the per-splat 8-bit masks of one staging warp into 8 ballot words s_mask[w][staging_warp]
-__device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)[8]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// turn the per-splat 8-bit masks of one staging warp into 8 ballot words s_mask[w][word]
+__device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)[BLEND_WORDS], int word) {
+    const int lane = threadIdx.x & 31;
     uint32_t mine = 0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
         const uint32_t b = __ballot_sync(0xffffffffu, (mask8 >> w) & 1u);
         if (lane == w) mine = b;
     }
-    if (lane < 8) s_mask[lane][warp] = mine;
+    if (lane < 8) s_mask[lane][word] = mine;
 }
 
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
                  float *__restrict__ out_color, float *__restrict__ final_T,
-                 int32_t *__restrict__ n_contrib) {
-    __shared__ float4 s_k0[BLEND_THREADS];
-    __shared__ float4 s_k1[BLEND_THREADS];
-    __shared__ float s_b[BLEND_THREADS];
-    __shared__ uint32_t s_mask[8][8];          // [patch warp][staging warp]
-    const int tile = blockIdx.x;
+                 int32_t *__restrict__ n_contrib, const uint32_t *__restrict__ order) {
+    __shared__ float4 s_k0[BLEND_BATCH];
+    __shared__ float4 s_k1[BLEND_BATCH];
+    __shared__ float s_b[BLEND_BATCH];
+    __shared__ uint32_t s_mask[8][BLEND_WORDS];          // [patch warp][32 splats]
+    const int tile = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
     float u, v;
@@ -116,22 +119,27 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     int last_contributor = 0;
     const int warp = threadIdx.x >> 5;
 
-    for (int base = range.x; todo > 0; base += BLEND_THREADS, todo -= BLEND_THREADS) {
+    for (int base = range.x; todo > 0; base += BLEND_BATCH, todo -= BLEND_BATCH) {
         if (__syncthreads_and(done)) break;
-        uint32_t mask8 = 0;
-        if ((int)threadIdx.x < todo) {
-            const uint32_t id = point_list[base + threadIdx.x];
-            const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
-            const SplatCoef s = splat_setup(r0.x - cx, r0.y - cy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
-            s_k0[threadIdx.x] = s.k0; s_k1[threadIdx.x] = s.k1; s_b[threadIdx.x] = r2.x;
-            mask8 = s.mask8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                   // slot j = h * 256 + tid; its mask word = h * 8 + warp
+            const int j = h * BLEND_THREADS + (int)threadIdx.x;
+            uint32_t mask8 = 0;
+            if (j < todo) {
+                const uint32_t id = point_list[base + j];
+                const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
+                const SplatCoef sc = splat_setup(r0.x - cx, r0.y - cy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
+                s_k0[j] = sc.k0; s_k1[j] = sc.k1; s_b[j] = r2.x;
+                mask8 = sc.mask8;
+            }
+            publish_masks(mask8, s_mask, h * 8 + warp);
         }
-        publish_masks(mask8, s_mask);
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
         const int pos0 = base - range.x + 1;
+        const int nwords = min(BLEND_WORDS, (todo + 31) >> 5);
 #pragma unroll 1
-        for (int word = 0; word < 8; ++word) {
+        for (int word = 0; word < nwords; ++word) {
             uint32_t bits = s_mask[warp][word];
             while (bits) {
                 const int j = word * 32 + __ffs(bits) - 1;
@@ -156,7 +164,7 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                             last_contributor = pos0 + j;
                         }
                     }
-                    if (__all_sync(0xffffffffu, done)) { bits = 0; word = 8; }
+                    if (__all_sync(0xffffffffu, done)) { bits = 0; word = nwords; }
                 }
             }
         }
@@ -214,17 +222,25 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
 
 // Staged splat record of the backward: 64 bytes = 4 x float4
 //   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] conA, conB, conC, opacity   [3] b, id(bits), 0, 0
+//
+// Per (pixel, splat) pair the lanes only form the six moments of D = dL/dG * G about the splat centre
+// (D, D dx, D dy, D dx^2, D dx dy, D dy^2) and the three colour terms; D = dL/dalpha * ex2(e) because
+// o * G = ex2(p2 + log2 o) is the (unclamped) alpha the forward exponent already gives.  The conic / opacity
+// factors of the reference's per-pixel formulas are per-splat constants, so they are applied ONCE per
+// (warp, splat) after the warp reduction, by the lanes that own the reduced sums:
+//   dmean2D.x = -0.5 W (A Sx + B Sy)   dmean2D.y = -0.5 H (C Sy + B Sx)
+//   dconic    = -0.5 (Sxx, Sxy, Syy)   dopacity  = S / o   dcolour = (c0, c1, c2)
 __global__ void __launch_bounds__(BLEND_THREADS)
 blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
                  const float *__restrict__ final_T, const int32_t *__restrict__ n_contrib,
                  const float *__restrict__ dL_dpix, float *__restrict__ dL_dmean2D,
                  float *__restrict__ dL_dconic, float *__restrict__ dL_dopacity,
-                 float *__restrict__ dL_dcolor) {
-    __shared__ float4 s_rec[BLEND_THREADS * 4];
-    __shared__ uint32_t s_mask[8][8];
+                 float *__restrict__ dL_dcolor, const uint32_t *__restrict__ order) {
+    __shared__ float4 s_rec[BLEND_BATCH * 4];
+    __shared__ uint32_t s_mask[8][BLEND_WORDS];
     __shared__ int s_max[BLEND_THREADS / 32];
-    const int tile = blockIdx.x;
+    const int tile = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
     float u, v;
@@ -240,7 +256,6 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     if (inside) { dp0 = dL_dpix[pid]; dp1 = dL_dpix[HW + pid]; dp2 = dL_dpix[2 * HW + pid]; }
     const float neg_Tf_bg = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-    const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(s_rec);
 
@@ -251,36 +266,40 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_THREADS / 32; ++w) tile_last = max(tile_last, s_max[w]);
-    // After the butterfly, lanes with (lane & 3) == 0 own one of the 8 reduced scalars; its destination
-    // array has row stride 3: mean2D.x/.y, conic.x/.y/.z, colour.r/.g/.b.  Lane 1 owns the opacity sum.
+    // After the butterfly, lanes with (lane & 3) == 0 own one of the 8 reduced sums
+    //   ridx 0 Sx, 1 Sy, 2 Sxx, 3 Sxy, 4 Syy, 5..7 colour;   lane 1 owns S.
+    // Destination rows have stride 3: mean2D.x/.y, conic.x/.y/.z, colour.r/.g/.b.
     const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     float *const gdst = ridx < 2 ? dL_dmean2D + ridx : (ridx < 5 ? dL_dconic + (ridx - 2) : dL_dcolor + (ridx - 5));
+    const float own_scale = ridx < 2 ? (ridx == 0 ? -0.5f * (float)W : -0.5f * (float)H) : (ridx < 5 ? -0.5f : 1.0f);
 
-    // walk positions tile_last-1 .. 0 in batches of 256, back to front; slot j holds position hi-1-j
-    for (int hi = tile_last; hi > 0; hi -= BLEND_THREADS) {
-        const int nb = min(BLEND_THREADS, hi);
+    // walk positions tile_last-1 .. 0 in batches, back to front; slot j holds position hi-1-j
+    for (int hi = tile_last; hi > 0; hi -= BLEND_BATCH) {
+        const int nb = min(BLEND_BATCH, hi);
         __syncthreads();                        // every warp is done with the previous batch
-        {
-            const int j = threadIdx.x;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = h * BLEND_THREADS + (int)threadIdx.x;
             uint32_t mask8 = 0;
             if (j < nb) {
                 const uint32_t id = point_list[range.x + hi - 1 - j];
                 const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
                 const float sx = r0.x - cx, sy = r0.y - cy;
-                const SplatCoef s = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
-                s_rec[4 * j] = s.k0; s_rec[4 * j + 1] = s.k1;
+                const SplatCoef sc = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
+                s_rec[4 * j] = sc.k0; s_rec[4 * j + 1] = sc.k1;
                 s_rec[4 * j + 2] = make_float4(r0.z, r0.w, r1.x, r1.y);
                 s_rec[4 * j + 3] = make_float4(r2.x, __uint_as_float(id), 0.f, 0.f);
-                mask8 = s.mask8;
+                mask8 = sc.mask8;
             }
-            publish_masks(mask8, s_mask);
+            publish_masks(mask8, s_mask, h * 8 + warp);
         }
         __syncthreads();
         // slots whose position is at or behind this warp's deepest contributor cannot receive gradient:
         // position = hi-1-j >= warp_last  <=>  j < hi - warp_last
         const int skip = hi - warp_last;
+        const int nwords = (nb + 31) >> 5;
 #pragma unroll 1
-        for (int word = 0; word < 8; ++word) {
+        for (int word = 0; word < nwords; ++word) {
             uint32_t bits = s_mask[warp][word];
             const int lo = word * 32;
             if (skip >= lo + 32) bits = 0;
@@ -297,13 +316,12 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const bool live = (hi - 1 - j) < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
                 if (!__any_sync(0xffffffffu, live)) continue;
                 const float2 bid = lds64(addr + 48);
-                float g[8], gop = 0.f;
+                float g[8], gS = 0.f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) g[q] = 0.f;
                 if (live) {
-                    const float4 g0 = lds128(addr + 32);      // A, B, C, opacity
-                    const float G = ex2_approx(p2);
-                    const float alpha = fminf(0.99f, g0.w * G);
+                    const float au = ex2_approx(e);            // o * G
+                    const float alpha = fminf(0.99f, au);
                     const float rcp = __fdividef(1.0f, 1.0f - alpha);
                     T *= rcp;
                     const float dch = alpha * T;
@@ -315,22 +333,20 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                     float dL_dalpha = ((c0 - ar0) * dp0 + (c1 - ar1) * dp1 + (c2 - ar2) * dp2) * T;
                     last_alpha = alpha;
                     dL_dalpha = fmaf(neg_Tf_bg, rcp, dL_dalpha);
-                    const float dL_dG = g0.w * dL_dalpha;
-                    const float gdx = G * dx, gdy = G * dy;
-                    g[0] = dL_dG * (-gdx * g0.x - gdy * g0.y) * ddelx_dx;
-                    g[1] = dL_dG * (-gdy * g0.z - gdx * g0.y) * ddely_dy;
-                    const float h = -0.5f * dL_dG;
-                    g[2] = h * gdx * dx;
-                    g[3] = h * gdx * dy;
-                    g[4] = h * gdy * dy;
+                    gS = dL_dalpha * au;                       // D = dL/dG * G
+                    g[0] = gS * dx; g[1] = gS * dy;
+                    g[2] = g[0] * dx; g[3] = g[0] * dy; g[4] = g[1] * dy;
                     g[5] = dch * dp0; g[6] = dch * dp1; g[7] = dch * dp2;
-                    gop = G * dL_dalpha;
                 }
                 const float r8 = warp_reduce8(g, lane);
-                const float r1 = warp_sum(gop);
+                const float rS = warp_sum(gS);
+                const float other = __shfl_xor_sync(0xffffffffu, r8, 4);       // Sx <-> Sy for the two mean2D lanes
+                const float4 con = lds128(addr + 32);                          // A, B, C, opacity
                 const size_t id = __float_as_uint(bid.y);
-                if ((lane & 3) == 0 && r8 != 0.f) atomicAdd(gdst + 3 * id, r8);
-                if (lane == 1 && r1 != 0.f) atomicAdd(dL_dopacity + id, r1);
+                float val = own_scale * r8;
+                if (ridx < 2) val = own_scale * fmaf(ridx == 0 ? con.x : con.z, r8, con.y * other);
+                if ((lane & 3) == 0 && val != 0.f) atomicAdd(gdst + 3 * id, val);
+                if (lane == 1 && rS != 0.f) atomicAdd(dL_dopacity + id, __fdividef(rS, con.w));
             }
         }
     }
@@ -355,7 +371,8 @@ extern "C" int splatco_blend_fwd(int64_t R, int H, int W, const float *bg, const
         rec = reinterpret_cast<const float4 *>(geom);      // chunk 0 of the geometry workspace
     }
     blend_fwd_kernel<<<gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(im.ranges, plist, rec, W, H, gx, bg,
-                                                                         out_color, im.final_T, im.n_contrib);
+                                                                         out_color, im.final_T, im.n_contrib,
+                                                                         R > 0 ? im.order : nullptr);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }
@@ -373,7 +390,7 @@ extern "C" int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg
     const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
     blend_bwd_kernel<<<gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
         im.ranges, b.vals[splatco_sorted_buffer_index(H, W)], reinterpret_cast<const float4 *>(geom), W, H, gx, bg,
-        im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor);
+        im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

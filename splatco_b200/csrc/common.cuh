@@ -64,11 +64,12 @@ struct ImgWs {
     uint32_t *cursor;         // [T]  start of each tile's segment
     uint32_t *lists;          // [3][T] tiles by segment-length class (per-tile sort work lists)
     uint32_t *work;           // [8]  list lengths [0..2], queue heads [4..6]
+    uint32_t *order;          // [T]  tile handled by blend CTA b (longest tiles first)
 };
 
 size_t geom_offsets(int P, size_t off[7]);
 size_t bin_offsets(int64_t R, size_t off[7]);
-size_t img_offsets(int H, int W, size_t off[8]);
+size_t img_offsets(int H, int W, size_t off[9]);
 GeomWs geom_view(void *base, int P);
 BinWs bin_view(void *base, int64_t R);
 ImgWs img_view(void *base, int H, int W);

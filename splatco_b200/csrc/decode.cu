@@ -1100,11 +1100,12 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
         static const int kWork[5] = {2 * 1, 2 * 2, 2 * 4, 2 * 5, 8 * 6};
         int total = 0;
         for (int i = 0; i < grp.count; ++i) total += kWork[grp.p[i].shape];
-        const int budget = 2 * 148, max_slices = max(1, ceil_div(V, 2 * WG_KB));
+        // (narrow outputs run far below the FMA rate, so no CTA gets more than 768 rows whatever its share)
+        const int budget = 2 * 148, max_slices = max(1, ceil_div(V, 2 * WG_KB)), min_slices = ceil_div(V, 768);
         int ctas = 0;
         for (int i = 0; i < grp.count; ++i) {
             WgProblem &q = grp.p[i];
-            q.nslices = min(max_slices, max(1, budget * kWork[q.shape] / total));
+            q.nslices = min(max_slices, max(min_slices, budget * kWork[q.shape] / total));
             q.cta0 = ctas;
             ctas += q.nslices;
         }

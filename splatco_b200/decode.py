@@ -168,12 +168,18 @@ class _FusedDecode(torch.autograd.Function):
         tensors = [t if _plain(t) else _c(t) for t in (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz)]
         anchor_feat_c, anchor_c, offset_c, scaling_c, a_xy, a_xz, a_yz = tensors
         app_c = None if app_vec is None else (app_vec if _plain(app_vec) else _c(app_vec))
-        pc = [t if _plain(t) else _c(t) for t in params]
+        plan = cfg.plan
+        ids = tuple(map(id, params))
+        if plan.param_ids == ids:
+            pc = params                                       # same Parameter objects as last view: all fp32 contiguous
+        else:
+            pc = [t if _plain(t) else _c(t) for t in params]
+            plan.param_ids = ids if all(a is b for a, b in zip(pc, params)) else None
         V = int(cfg.vis_idx.shape[0])
         K = cfg.K
         desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c, pc)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        with torch.cuda.device(dev):
+        stream = _lib.raw_stream(dev)
+        with _lib.on_device(dev):
             ws = torch.empty(max(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
             nopac = torch.empty((V * K, 1), dtype=torch.float32, device=dev)
             mask = torch.empty(V * K, dtype=torch.bool, device=dev)
@@ -231,7 +237,7 @@ class _FusedDecode(torch.autograd.Function):
                 continue
             reqs.append((id(o) if need[n] else None, shp))
             where.append(n)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             got = _gradacc.acquire(dev, reqs)
         slots = _grad_slots(nl)
         vals = [None] * _NGRAD
@@ -246,8 +252,8 @@ class _FusedDecode(torch.autograd.Function):
             if M > 0:
                 z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
                 ups = [u if u is not None else z(*s) for u, s in zip(ups[:5], ((M, 3), (M, 3), (M, 1), (M, 3), (M, 4)))] + [ups[5]]
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            with torch.cuda.device(dev):
+            stream = _lib.raw_stream(dev)
+            with _lib.on_device(dev):
                 bws = torch.empty(max(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
                 with stage("decode_bwd"):
                     check(L.splatco_decode_bwd(C.byref(desc), _p(ctx.ws), _p(bws), M, *[_p(u) for u in ups],
@@ -276,12 +282,12 @@ class _TriPlaneAttention(torch.autograd.Function):
         hidden, ksize = int(w_ca1.shape[0]), int(w_sa.shape[-1])
         if not (xy.shape == xz.shape == yz.shape and xy.shape[2] == xy.shape[3]):
             raise NotImplementedError("splatco_b200 TriPlaneAttention supports equal square planes only")
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             ws = torch.empty(L.splatco_ta_fwd_ws_bytes(rc, E), dtype=torch.uint8, device=dev)
             outs = [torch.empty_like(ins[q]) for q in range(3)]
             with stage("triplane_attention_fwd"):
                 check(L.splatco_ta_fwd(rc, E, hidden, ksize, *[_p(t) for t in ins], _p(ws), *[_p(t) for t in outs],
-                                       torch.cuda.current_stream(dev).cuda_stream), "splatco_ta_fwd")
+                                       _lib.raw_stream(dev)), "splatco_ta_fwd")
         ctx.ins, ctx.ws, ctx.dims = ins, ws, (rc, E, hidden, ksize)
         ctx.origs = (xy, xz, yz, w_ca1, w_ca2, w_sa)
         return tuple(outs)
@@ -295,7 +301,7 @@ class _TriPlaneAttention(torch.autograd.Function):
         need = ctx.needs_input_grad
         # plane gradients go into the same per-backward-pass buffers the decode nodes scatter their
         # direct (un-attended) level-0 plane gradients into (_gradacc)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             got = _gradacc.acquire(dev, [(id(o) if need[n] else None, t.shape) for n, (o, t) in enumerate(zip(ctx.origs, ins))])
             ptrs = [g[0] for g in got]
             rets = [g[1] if need[n] else None for n, g in enumerate(got)]
@@ -306,7 +312,7 @@ class _TriPlaneAttention(torch.autograd.Function):
             with stage("triplane_attention_bwd"):
                 check(L.splatco_ta_bwd(rc, E, hidden, ksize, *[_p(t) for t in ins], _p(ctx.ws), _p(bws),
                                        *[_p(g) for g in gs], *ptrs,
-                                       torch.cuda.current_stream(dev).cuda_stream), "splatco_ta_bwd")
+                                       _lib.raw_stream(dev)), "splatco_ta_bwd")
         return tuple(rets)
 
 
@@ -355,7 +361,7 @@ class _ModelPlan:
     parameter tensors are fetched with dict lookups instead of nn.Module attribute resolution), the
     static sizes, and the descriptor template (_fill_desc)."""
     __slots__ = ("feat_ref", "level", "heads", "levels", "rc", "E", "xyz_min", "xyz_max", "bn_eps", "bn_momentum",
-                 "buffers", "ta_weights", "desc_key", "desc")
+                 "buffers", "ta_weights", "desc_key", "desc", "param_ids")
 
 
 _plans = {}
@@ -395,7 +401,7 @@ def _plan_for(pc, feat, level, heads) -> _ModelPlan:
                                  cbn_nbt=cbn.num_batches_tracked))
     ta = k0s[0].TA
     plan.ta_weights = (ta.ca.sharedMLP[0], ta.ca.sharedMLP[2], ta.sa.conv)
-    plan.desc_key = plan.desc = None
+    plan.desc_key = plan.desc = plan.param_ids = None
     if len(_plans) > 8:
         _plans.clear()
     _plans[id(pc)] = plan

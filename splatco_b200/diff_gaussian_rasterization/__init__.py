@@ -56,7 +56,7 @@ def _pinned_counter(device: torch.device, slot: int = 0) -> torch.Tensor:
 
 
 def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    return _lib.raw_stream(device)
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -208,7 +208,7 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
         color = bg.reshape(3, 1, 1).expand(3, H, W).contiguous()
         return color, st.radii, st
     stream = _stream_ptr(dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         if sp is not None and sp.binning is not None:
             # the whole forward already ran (queued inside the decode forward)
             st.PL, st.R, st.RL = sp.PL, sp.R, sp.RL
@@ -259,14 +259,12 @@ def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotat
     L = _lib.lib()
     dev = means3D.device
     P, R, H, W = st.P, st.RL, st.H, st.W          # RL: the binning workspace's layout size
-    flat = torch.zeros(10 * P, dtype=torch.float32, device=dev)
-    g_mean2D = flat[: 3 * P].view(P, 3)
-    g_conic = flat[3 * P: 6 * P].view(P, 3)
-    g_opac = flat[6 * P: 7 * P].view(P, 1)
-    g_color = flat[7 * P:].view(P, 3)
-    g_means3D = torch.empty((P, 3), dtype=torch.float32, device=dev)
-    g_scales = torch.empty((P, 3), dtype=torch.float32, device=dev)
-    g_rots = torch.empty((P, 4), dtype=torch.float32, device=dev)
+    # two allocations, two split calls: [mean2D 3 | conic 3 | opacity 1 | colour 3] is zero-filled for the blend's
+    # REDs, [means3D 3 | scales 3 | rotations 4] is overwritten by preprocess_bwd (rotations stay 16-byte aligned)
+    a, b_, c, d = torch.zeros(10 * P, dtype=torch.float32, device=dev).split_with_sizes([3 * P, 3 * P, P, 3 * P])
+    g_mean2D, g_conic, g_opac, g_color = a.view(P, 3), b_.view(P, 3), c.view(P, 1), d.view(P, 3)
+    e, f, g_ = torch.empty(12 * P, dtype=torch.float32, device=dev).split_with_sizes([4 * P, 4 * P, 4 * P])
+    g_rots, g_means3D, g_scales = e.view(P, 4), f[:3 * P].view(P, 3), g_[:3 * P].view(P, 3)
     if P == 0:
         return dict(means3D=g_means3D, means2D=g_mean2D, colors=g_color, opacities=g_opac,
                     scales=g_scales, rotations=g_rots, conic=g_conic)
@@ -278,7 +276,7 @@ def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotat
     view = _f32c(settings.viewmatrix)
     proj = _f32c(settings.projmatrix)
     stream = _stream_ptr(dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         with stage("blend_bwd"):
           check(L.splatco_blend_bwd(P, R, H, W, ptr(bg), ptr(st.geom), ptr(st.binning), ptr(st.image),
                                   ptr(grad_color), ptr(g_mean2D), ptr(g_conic), ptr(g_opac), ptr(g_color),
@@ -365,7 +363,7 @@ class GaussianRasterizer(nn.Module):
             rotations = _f32c(rotations.detach())
             scales, sstride = _rows_f32(scales.detach(), 3)
             view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
-            with torch.cuda.device(dev), stage("visible_filter"):
+            with _lib.on_device(dev), stage("visible_filter"):
                 check(L.splatco_visible_filter(N, ptr(means3D), ptr(scales), sstride, ptr(rotations),
                                                float(rs.scale_modifier), ptr(view), ptr(proj), float(rs.tanfovx),
                                                float(rs.tanfovy), int(rs.image_height), int(rs.image_width),

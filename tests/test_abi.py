@@ -43,10 +43,10 @@ def test_workspace_sizing_monotone_and_aligned():
     assert L.splatco_geom_bytes(1000) >= 1000 * (48 + 4 + 4)
     assert L.splatco_binning_bytes(1000) >= 1000 * 24
     assert L.splatco_image_bytes(545, 980) >= 545 * 980 * 8 + 62 * 35 * 8
-    offs = (C.c_size_t * 8)()
+    offs = (C.c_size_t * 16)()
     assert L.splatco_geom_layout(1000, offs, 8) == 6 and list(offs)[:6] == sorted(list(offs)[:6])
     assert L.splatco_binning_layout(5000, offs, 8) == 6
-    assert L.splatco_image_layout(545, 980, offs, 8) == 7
+    assert L.splatco_image_layout(545, 980, offs, 16) == 8
 
 
 def test_sort_pass_parity_matches_key_width():
