@@ -54,6 +54,18 @@ SCALE_FACTOR = 0.5       # anchor scale = 0.5 / N^(1/3): projected sigma ~0.5-4 
 LEVEL = 2                # activate_level in steady state (train.py:305-307)
 
 
+def ncu_evidence():
+    """Per-kernel numbers of the latest committed `ncu --set full` capture (profiles/*_traffic.json, written by
+    tools/collect_profiles.py): dram bytes per launch, issue-active, tensor-pipe-active."""
+    d = os.path.join(ROOT, "profiles")
+    files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json")) if os.path.isdir(d) else []
+    if not files:
+        return {}
+    ev = json.load(open(os.path.join(d, files[-1])))
+    ev["_file"] = "profiles/" + files[-1]
+    return ev
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -249,14 +261,29 @@ def run_ours(args):
     timed_k = [k for k in stage_sum if k in alg_bytes]
     dom = max(timed_k, key=lambda k: stage_sum[k][1]) if timed_k else None
     roof = None
+    ncu = ncu_evidence()
     if dom:
         a = stages[dom]["alg_gbs"]
+        ev = ncu.get(dom + "_kernel")
         roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
-                "frac": round(a / peak, 4), "peak_source": peak_src, "traffic": None,
+                "frac": round(a / peak, 4), "peak_source": peak_src,
+                "traffic": int(ev["dram_bytes"]) if ev else None,      # dram read+write per launch, ncu --set full
+                "traffic_source": ncu.get("_file") if ev else None,
                 "alg_bytes_per_launch": int(alg_bytes[dom])}
         if dom.startswith("blend"):
             # the blend is FP32-issue bound, not HBM bound: also report (pixel, splat) pairs/s
             roof["pairs_per_s"] = round(R * 256 / (stages[dom]["avg_ms"] * 1e-3), 1)
+    # the decode MLP runs on tcgen05 (3xTF32): algorithmic FLOPs counted once, against half the measured bf16 peak
+    mlp = None
+    ev = ncu.get("dec_tc_fwd_kernel")
+    if ev:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] / 2 if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1100.0
+        flops = V * (32.5e3 + 5.5e3 * LEVEL)
+        ach = flops / (ev["time_us"] * 1e-6) / 1e12
+        mlp = {"kernel": "dec_tc_fwd_kernel", "bound": "tensor", "achieved": round(ach, 2), "peak": round(pk, 1),
+               "unit": "TFLOP/s", "frac": round(ach / pk, 4), "tensor_pipe_active_pct": ev["tensor_active_pct"],
+               "source": ncu.get("_file"), "note": "kernel time from the committed ncu capture, not from this run"}
     out = {
         "metric": "fwd_bwd_ms_per_view", "value": round(ms_step / views, 4), "unit": "ms/view", "n_gpus": world,
         "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_step, 4), "higher_is_better": False,
@@ -271,7 +298,7 @@ def run_ours(args):
         "e2e": {"value": round((ms_e2e / args.steps) / views, 4), "unit": "ms/view",
                 "h2d_bytes_per_step": int(mv * 3 * HW * 4), "d2h_bytes_per_step": 4 + 8 * mv},
         "gpu_launches": int(launches),
-        "roofline": roof, "stages": stages, "clocks": clocks,
+        "roofline": roof, "decode_mlp": mlp, "stages": stages, "clocks": clocks,
     }
     if bucket is not None:
         out["config"]["allreduce_bytes_per_step"] = bucket.nbytes()

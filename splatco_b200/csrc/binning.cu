@@ -257,21 +257,35 @@ tile_hist_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *
     for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) row[t] = s_hist[t];
 }
 
-// thread per tile: chunk_hist[c][t] <- exclusive prefix over c; tile_count[t] = total
+// chunk_hist[c][t] <- exclusive prefix over c; tile_count[t] = total.  A CTA covers 32 tiles (coalesced rows) with 8
+// groups of threads that each scan a contiguous eighth of the chunks, so the dependent chain per thread is nchunks / 8.
 __global__ void __launch_bounds__(256)
 tile_colscan_kernel(int T, int nchunks, uint32_t *__restrict__ chunk_hist, uint32_t *__restrict__ tile_count,
                     uint32_t *__restrict__ work /*[8]: list lengths [0..2], queue heads [4..6]*/) {
+    __shared__ uint32_t s_part[8][33];
     if (blockIdx.x == 0 && threadIdx.x < 8) work[threadIdx.x] = 0;
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= T) return;
-    uint32_t run = 0;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + tx;
+    const int per = (nchunks + 7) / 8;
+    const int c0 = ty * per, c1 = min(nchunks, c0 + per);
+    uint32_t sum = 0;
+    if (t < T)
 #pragma unroll 4
-    for (int c = 0; c < nchunks; ++c) {
-        const uint32_t v = chunk_hist[(size_t)c * T + t];
-        chunk_hist[(size_t)c * T + t] = run;
-        run += v;
+        for (int c = c0; c < c1; ++c) sum += chunk_hist[(size_t)c * T + t];
+    s_part[ty][tx] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) { const uint32_t p = s_part[g][tx]; run += g < ty ? p : 0u; total += p; }
+    if (t < T) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const uint32_t v = chunk_hist[(size_t)c * T + t];
+            chunk_hist[(size_t)c * T + t] = run;
+            run += v;
+        }
+        if (ty == 0) tile_count[t] = total;
     }
-    tile_count[t] = run;
 }
 
 // one CTA; ranges[t] = [start, end) (zero for empty tiles, as identifyTileRanges leaves them), cursor[t] = start
@@ -357,7 +371,7 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
     uint32_t *s_cnt = s_dyn + 4 * CAP;                         // [NW][256]; before it: [key CAP | val CAP] x 2
     __shared__ uint32_t s_scan[NW];
     __shared__ int s_skip;
-    __shared__ uint32_t s_item;
+    __shared__ uint32_t s_item, s_vary[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t count = work[cls];
   for (;;) {                                                   // persistent CTA: next tile of this size class
@@ -369,16 +383,29 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
     const int2 rg = ranges[tile];
     const uint32_t n = (uint32_t)(rg.y - rg.x);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t k_or = 0u, k_and = 0xffffffffu;
     for (uint32_t i = tid; i < n; i += NT) {
         const uint64_t e = entries[rg.x + i];
-        s_dyn[i] = (uint32_t)(e >> 32);
+        const uint32_t kd = (uint32_t)(e >> 32);
+        s_dyn[i] = kd;
         s_dyn[CAP + i] = (uint32_t)e;
+        k_or |= kd; k_and &= kd;
     }
+    // bits that differ between any two keys of the tile: digits made of constant bits need no pass (depths of one
+    // tile share their sign/exponent byte almost always)
+    k_or = __reduce_or_sync(0xffffffffu, k_or);
+    k_and = __reduce_and_sync(0xffffffffu, k_and);
+    if (tid == 0) { s_vary[0] = 0u; s_vary[1] = 0xffffffffu; }
+    __syncthreads();
+    if (lane == 0) { atomicOr(&s_vary[0], k_or); atomicAnd(&s_vary[1], k_and); }
+    __syncthreads();
+    const uint32_t varying = s_vary[0] & ~s_vary[1];
     int cur = 0;
     const uint32_t wbase = warp * 32 * ITEMS;
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
+        if (((varying >> shift) & 255u) == 0u) continue;       // uniform across the CTA
         __syncthreads();                                       // the previous scatter (or the load) is complete
         for (uint32_t i = tid; i < NW * 256; i += NT) s_cnt[i] = 0;
         __syncthreads();
@@ -670,7 +697,7 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     }
     tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist);
     SPLATCO_CHECK_LAUNCH();
-    tile_colscan_kernel<<<ceil_div(T, 256), 256, 0, st>>>(T, nchunks, chunk_hist, im.tile_count, im.work);
+    tile_colscan_kernel<<<ceil_div(T, 32), 256, 0, st>>>(T, nchunks, chunk_hist, im.tile_count, im.work);
     SPLATCO_CHECK_LAUNCH();
     tile_scan_kernel<<<1, 1024, 0, st>>>(T, im.tile_count, im.ranges, im.cursor, (uint32_t)R, im.work, im.lists,
                                          512u * TSORT_ITEMS_S, 512u * TSORT_ITEMS_L);

@@ -1,0 +1,18 @@
+#!/bin/bash
+# Evidence run on the GPU box (one GPU): ncu launch list of a bench step + `ncu --set full` captures of the
+# dominant kernels.  Usage (from the repo root):   bash tools/make_profiles.sh <tag>
+# Outputs land in gpurun_out/ (scratch); tools/ncu_summary.py + tools/collect_profiles.py turn them into profiles/.
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --log-file $OUT/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"blend_bwd_kernel" -s 2 -c 1 -o $OUT/prof_blend_bwd_$TAG -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_blend_bwd_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"blend_fwd_kernel" -s 6 -c 1 -o $OUT/prof_blend_fwd_$TAG -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_blend_fwd_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on \
+    -k regex:"dec_(wgrad|tc_fwd|tc_bwd|gather|bwd_inputs|bwd_uncompact)_kernel|tile_sort_radix|tile_scatter|tile_hist|preprocess_(fwd|bwd)_kernel|visible_filter" \
+    -s 40 -c 22 -o $OUT/prof_rest_$TAG -f python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_rest_$TAG.log 2>&1
+ls -la $OUT | grep $TAG
