@@ -361,12 +361,12 @@ tile_scatter_kernel(int P, int T, const int32_t *__restrict__ radii, const float
 // ---- per-tile sort, segments that fit in shared memory: LSD radix on the 32 depth bits ----------------------
 // ITEMS consecutive-by-32 elements per lane, warp w owns the contiguous slice [w*32*ITEMS, (w+1)*32*ITEMS): the
 // usual stable ranking (match_any inside the warp, running per-(warp, digit) counters across its items).
-template <int ITEMS>
-__global__ void __launch_bounds__(512)
+template <int NT, int ITEMS>
+__global__ void __launch_bounds__(NT)
 tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restrict__ entries,
                        uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, const uint32_t *__restrict__ list,
                        uint32_t *__restrict__ work, int cls) {
-    constexpr int NT = 512, NW = NT / 32, CAP = NT * ITEMS;
+    constexpr int NW = NT / 32, CAP = NT * ITEMS;
     extern __shared__ uint32_t s_dyn[];
     uint32_t *s_cnt = s_dyn + 4 * CAP;                         // [NW][256]; before it: [key CAP | val CAP] x 2
     __shared__ uint32_t s_scan[NW];
@@ -575,8 +575,10 @@ tile_order_kernel(int T, const int2 *__restrict__ ranges, uint32_t *__restrict__
     for (int t = threadIdx.x; t < T; t += 1024) order[atomicAdd(&s_cnt[bucket(t)], 1u)] = (uint32_t)t;
 }
 
-constexpr int TSORT_ITEMS_S = 4, TSORT_ITEMS_L = 16;          // 2048 / 8192 elements per CTA
-constexpr size_t tsort_smem(int items) { return (size_t)(4 * 512 * items + 16 * 256) * sizeof(uint32_t); }
+// size classes of the shared-memory sort: 256 threads x 8 (2048 elements, 40 KB: five CTAs per SM) and
+// 512 threads x 16 (8192 elements, 144 KB)
+constexpr int TSORT_NT_S = 256, TSORT_ITEMS_S = 8, TSORT_NT_L = 512, TSORT_ITEMS_L = 16;
+constexpr size_t tsort_smem(int nt, int items) { return (size_t)(4 * nt * items + (nt / 32) * 256) * sizeof(uint32_t); }
 
 }  // namespace splatco
 
@@ -689,10 +691,12 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     if (!attr_set) {
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_ITEMS_S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)tsort_smem(TSORT_ITEMS_S)));
-        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_ITEMS_L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)tsort_smem(TSORT_ITEMS_L)));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_NT_S, TSORT_ITEMS_S>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tsort_smem(TSORT_NT_S, TSORT_ITEMS_S)));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_NT_L, TSORT_ITEMS_L>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)tsort_smem(TSORT_NT_L, TSORT_ITEMS_L)));
         attr_set = true;
     }
     tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist);
@@ -700,16 +704,16 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     tile_colscan_kernel<<<ceil_div(T, 32), 256, 0, st>>>(T, nchunks, chunk_hist, im.tile_count, im.work);
     SPLATCO_CHECK_LAUNCH();
     tile_scan_kernel<<<1, 1024, 0, st>>>(T, im.tile_count, im.ranges, im.cursor, (uint32_t)R, im.work, im.lists,
-                                         512u * TSORT_ITEMS_S, 512u * TSORT_ITEMS_L);
+                                         (uint32_t)(TSORT_NT_S * TSORT_ITEMS_S), (uint32_t)(TSORT_NT_L * TSORT_ITEMS_L));
     SPLATCO_CHECK_LAUNCH();
     tile_scatter_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist, im.cursor,
                                                                     b.keys[s ^ 1], (uint32_t)R);
     SPLATCO_CHECK_LAUNCH();
     // persistent sort CTAs pull tiles of their size class from the lists tile_scan built
-    tile_sort_radix_kernel<TSORT_ITEMS_S><<<min(T, 148 * 4), 512, tsort_smem(TSORT_ITEMS_S), st>>>(
+    tile_sort_radix_kernel<TSORT_NT_S, TSORT_ITEMS_S><<<min(T, 148 * 5), TSORT_NT_S, tsort_smem(TSORT_NT_S, TSORT_ITEMS_S), st>>>(
         im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s], im.lists, im.work, 0);
     SPLATCO_CHECK_LAUNCH();
-    tile_sort_radix_kernel<TSORT_ITEMS_L><<<min(T, 148), 512, tsort_smem(TSORT_ITEMS_L), st>>>(
+    tile_sort_radix_kernel<TSORT_NT_L, TSORT_ITEMS_L><<<min(T, 148), TSORT_NT_L, tsort_smem(TSORT_NT_L, TSORT_ITEMS_L), st>>>(
         im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s], im.lists + T, im.work, 1);
     SPLATCO_CHECK_LAUNCH();
     tile_sort_global_kernel<<<min(T, 148), TSORT_THREADS, 0, st>>>(im.ranges, b.keys[s ^ 1], b.keys[s], b.vals[s],

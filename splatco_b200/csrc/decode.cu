@@ -804,9 +804,25 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
             dv1 = (g1 - d1 * dot) / dist + gd * d1;
             dv2 = (g2 - d2 * dot) / dist + gd * d2;
         }
-        for (int c = lane; c < ncols; c += 32) {
-            const float xh = (xrow[c] - mu[c]) * rstd[c];
-            const float dx = rstd[c] * (dxh[c] - m1[c] - xh * m2[c]);
+        // all row loads of the (at most 6) channel groups are issued before any of them is consumed: the
+        // kernel is bound by L2 / HBM latency, not by instruction issue
+        constexpr int MAXC = 6;
+        float dxs[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            dxs[j] = 0.f;
+            if (c < ncols) {
+                const float r = __ldg(rstd + c);
+                const float xh = (__ldg(xrow + c) - __ldg(mu + c)) * r;
+                dxs[j] = r * (__ldg(dxh + c) - __ldg(m1 + c) - xh * __ldg(m2 + c));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            if (c >= ncols) break;
+            const float dx = dxs[j];
             if (c < DP) {
                 int lvl, pl, att, ch;
                 plane_channel(c, rc, lvl, pl, att, ch);
