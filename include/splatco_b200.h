@@ -149,6 +149,9 @@ typedef struct splatco_decode_desc {
     const float *app_vec;                  /* [app_dim] embedding row of this camera, or NULL           */
     const float *noise;                    /* [V, DP - 6*rc] additive plane-feature noise U(-.5,.5)*Q for
                                               levels >= 1 (scene/grids.py:159-164), or NULL (Q = 0)     */
+    int32_t plane_layout;                  /* 0: plane[] / att[] (and their gradients) are [rc,E,E] as the
+                                              reference stores them; 1: [E,E,8] channel-last copies made by
+                                              splatco_pack_planes (rc <= 8)                              */
 } splatco_decode_desc;
 
 /* Gradient destinations (same shapes as the inputs).  EVERY destination is ACCUMULATED into (+=):
@@ -166,6 +169,14 @@ typedef struct splatco_decode_grads {
     float *w1[3], *b1[3], *w2[3], *b2[3];
     float *app_vec;
 } splatco_decode_grads;
+
+/* Channel-last copies of three [rc,E,E] planes: out[(y*E + x)*8 + ch] (ch >= rc zero).  The gather reads 4 sectors
+ * per plane sample instead of 4 per channel, and the backward's bilinear scatter issues one request per texel.
+ * splatco_unpack_planes_add adds channel-last gradients back into [rc,E,E] gradients (+=). */
+int splatco_pack_planes(int rc, int E, const float *xy, const float *xz, const float *yz, float *pxy, float *pxz,
+                        float *pyz, void *stream);
+int splatco_unpack_planes_add(int rc, int E, const float *gpxy, const float *gpxz, const float *gpyz, float *gxy,
+                              float *gxz, float *gyz, void *stream);
 
 size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level);
 size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level);

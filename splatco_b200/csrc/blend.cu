@@ -221,7 +221,7 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
 }
 
 // Staged splat record of the backward: 64 bytes = 4 x float4
-//   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] conA, conB, conC, opacity   [3] b, id(bits), 0, 0
+//   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] conA, conB, conC, 1/opacity   [3] b, id(bits), 0, 0
 //
 // Per (pixel, splat) pair the lanes only form the six moments of D = dL/dG * G about the splat centre
 // (D, D dx, D dy, D dx^2, D dx dy, D dy^2) and the three colour terms; D = dL/dalpha * ex2(e) because
@@ -287,7 +287,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const float sx = r0.x - cx, sy = r0.y - cy;
                 const SplatCoef sc = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
                 s_rec[4 * j] = sc.k0; s_rec[4 * j + 1] = sc.k1;
-                s_rec[4 * j + 2] = make_float4(r0.z, r0.w, r1.x, r1.y);
+                s_rec[4 * j + 2] = make_float4(r0.z, r0.w, r1.x, r1.y > 0.f ? 1.0f / r1.y : 0.f);
                 s_rec[4 * j + 3] = make_float4(r2.x, __uint_as_float(id), 0.f, 0.f);
                 mask8 = sc.mask8;
             }
@@ -322,7 +322,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 if (live) {
                     const float au = ex2_approx(e);            // o * G
                     const float alpha = fminf(0.99f, au);
-                    const float rcp = __fdividef(1.0f, 1.0f - alpha);
+                    const float rcp = rcp_approx(1.0f - alpha);         // 1 - alpha >= 0.01
                     T *= rcp;
                     const float dch = alpha * T;
                     const float c0 = k1.z, c1 = k1.w, c2 = bid.x;
@@ -341,12 +341,14 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const float r8 = warp_reduce8(g, lane);
                 const float rS = warp_sum(gS);
                 const float other = __shfl_xor_sync(0xffffffffu, r8, 4);       // Sx <-> Sy for the two mean2D lanes
-                const float4 con = lds128(addr + 32);                          // A, B, C, opacity
-                const size_t id = __float_as_uint(bid.y);
-                float val = own_scale * r8;
-                if (ridx < 2) val = own_scale * fmaf(ridx == 0 ? con.x : con.z, r8, con.y * other);
-                if ((lane & 3) == 0 && val != 0.f) atomicAdd(gdst + 3 * id, val);
-                if (lane == 1 && rS != 0.f) atomicAdd(dL_dopacity + id, __fdividef(rS, con.w));
+                const float4 con = lds128(addr + 32);                          // A, B, C, 1/opacity
+                const uint32_t id = __float_as_uint(bid.y);
+                // owners of Sx / Sy combine them with the conic (cA own + cB other); every other owner has cA = 1, cB = 0
+                const float cA = ridx == 0 ? con.x : (ridx == 1 ? con.z : 1.0f);
+                const float cB = ridx < 2 ? con.y : 0.0f;
+                const float val = own_scale * fmaf(cA, r8, cB * other);
+                if ((lane & 3) == 0 && val != 0.f) atomicAdd(gdst + 3u * id, val);
+                if (lane == 1 && rS != 0.f) atomicAdd(dL_dopacity + id, rS * con.w);
             }
         }
     }

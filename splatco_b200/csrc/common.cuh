@@ -85,6 +85,9 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }

@@ -191,6 +191,7 @@ struct DecPtrs {
     int E[3];
     const float *mn, *mx, *cam;      // device pointers (3 floats each)
     const float *noise;
+    int packed;                      // 1: planes are [E,E,8] channel-last (splatco_pack_planes), 0: [rc,E,E]
 };
 
 struct Bilin { int i00, i01, i10, i11; float w00, w01, w10, w11; };
@@ -210,19 +211,20 @@ __device__ __forceinline__ Bilin bilin_setup(float u, float v, int E) {
     b.i11 = (iu1 && iv1) ? u1 * E + v1 : -1; b.w11 = wu1 * wv1;
     return b;
 }
-__device__ __forceinline__ float bilin_fetch(const float *__restrict__ p, const Bilin &b) {
+// ts = texel stride in floats (1 for [rc,E,E] planes, 8 for channel-last planes)
+__device__ __forceinline__ float bilin_fetch(const float *__restrict__ p, const Bilin &b, int ts) {
     float r = 0.f;
-    if (b.i00 >= 0) r = fmaf(__ldg(p + b.i00), b.w00, r);
-    if (b.i01 >= 0) r = fmaf(__ldg(p + b.i01), b.w01, r);
-    if (b.i10 >= 0) r = fmaf(__ldg(p + b.i10), b.w10, r);
-    if (b.i11 >= 0) r = fmaf(__ldg(p + b.i11), b.w11, r);
+    if (b.i00 >= 0) r = fmaf(__ldg(p + (size_t)b.i00 * ts), b.w00, r);
+    if (b.i01 >= 0) r = fmaf(__ldg(p + (size_t)b.i01 * ts), b.w01, r);
+    if (b.i10 >= 0) r = fmaf(__ldg(p + (size_t)b.i10 * ts), b.w10, r);
+    if (b.i11 >= 0) r = fmaf(__ldg(p + (size_t)b.i11 * ts), b.w11, r);
     return r;
 }
-__device__ __forceinline__ void bilin_scatter(float *__restrict__ p, const Bilin &b, float g) {
-    if (b.i00 >= 0) atomicAdd(p + b.i00, g * b.w00);
-    if (b.i01 >= 0) atomicAdd(p + b.i01, g * b.w01);
-    if (b.i10 >= 0) atomicAdd(p + b.i10, g * b.w10);
-    if (b.i11 >= 0) atomicAdd(p + b.i11, g * b.w11);
+__device__ __forceinline__ void bilin_scatter(float *__restrict__ p, const Bilin &b, float g, int ts) {
+    if (b.i00 >= 0) atomicAdd(p + (size_t)b.i00 * ts, g * b.w00);
+    if (b.i01 >= 0) atomicAdd(p + (size_t)b.i01 * ts, g * b.w01);
+    if (b.i10 >= 0) atomicAdd(p + (size_t)b.i10 * ts, g * b.w10);
+    if (b.i11 >= 0) atomicAdd(p + (size_t)b.i11 * ts, g * b.w11);
 }
 
 // channel c of the plane block -> (level, plane 0..2, attended?, channel within plane)
@@ -275,8 +277,10 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
                 plane_axes(pl, ind, u, w);
                 const int E = p.E[lvl];
                 const Bilin b = bilin_setup(u, w, E);
-                const float *base = (att ? p.att[pl] : p.plane[lvl][pl]) + (size_t)ch * E * E;
-                val = bilin_fetch(base, b);
+                // channel-last planes: the rc channels of a texel share one 32-byte sector, so the lanes of one
+                // plane sample touch 4 sectors instead of 4 per channel
+                const float *base = (att ? p.att[pl] : p.plane[lvl][pl]) + (p.packed ? (size_t)ch : (size_t)ch * E * E);
+                val = bilin_fetch(base, b, p.packed ? 8 : 1);
                 if (p.noise && c >= 6 * rc) val += __ldg(p.noise + (size_t)v * (DP - 6 * rc) + (c - 6 * rc));
             } else {
                 const int g = c - DP;
@@ -831,7 +835,7 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
                 const int E = p.E[lvl];
                 const Bilin b = bilin_setup(u, w, E);
                 float *base = (att ? gi.att[pl] : gi.plane[lvl][pl]);
-                if (base) bilin_scatter(base + (size_t)ch * E * E, b, dx);
+                if (base) bilin_scatter(base + (p.packed ? (size_t)ch : (size_t)ch * E * E), b, dx, p.packed ? 8 : 1);
             } else {
                 const int g = c - DP;
                 if (g < FD) gi.anchor_feat[(size_t)i * FD + g] += dx + dx100[g];
@@ -906,6 +910,7 @@ int check_desc(const splatco_decode_desc *d) {
     SPLATCO_REQUIRE(d->rc >= 1 && d->rc * 12 <= DEC_MAX_DP, "decode: channels per plane %d unsupported", d->rc);
     SPLATCO_REQUIRE(d->V >= 0 && d->N >= d->V, "decode: bad sizes N=%d V=%d", d->N, d->V);
     SPLATCO_REQUIRE(d->app_dim >= 0 && (d->app_dim == 0 || d->app_vec), "decode: appearance vector missing");
+    SPLATCO_REQUIRE(d->plane_layout == 0 || (d->plane_layout == 1 && d->rc <= 8), "decode: bad plane_layout %d", d->plane_layout);
     if (d->V == 0) return 0;
     SPLATCO_REQUIRE(d->anchor_feat && d->anchor && d->offset && d->scaling && d->vis, "decode: null input");
     SPLATCO_REQUIRE(d->xyz_min && d->xyz_max && d->cam, "decode: null bbox / camera pointer");
@@ -932,6 +937,7 @@ DecPtrs make_ptrs(const splatco_decode_desc *d) {
     for (int q = 0; q < 3; ++q) p.att[q] = d->att[q];
     p.mn = d->xyz_min; p.mx = d->xyz_max; p.cam = d->cam;
     p.noise = d->noise;
+    p.packed = d->plane_layout;
     return p;
 }
 
@@ -1133,6 +1139,62 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     SPLATCO_CHECK_LAUNCH();
     dec_bwd_inputs_kernel<<<gather_grid(V), GATHER_WARPS * 32, 0, st>>>(p, gi, V, dd.rc, DP, LDX, f.X, f.XIN, f.mu, f.rstd,
                                                                         b.m1, b.m2, b.DXH, b.DX, b.DGA);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- channel-last copies of the feature planes --------------------------------------------------------------
+// [rc,E,E] (the reference's nn.Parameter layout, scene/grids.py:122-125) <-> [E,E,8]: one 32-byte sector per texel.
+// Built once per iteration by the host (decode.py caches it across the mv views), like TriPlaneAttention.
+namespace splatco {
+__global__ void __launch_bounds__(256)
+pack_planes_kernel(int rc, int npix, const float *__restrict__ a, const float *__restrict__ b, const float *__restrict__ c,
+                   float *__restrict__ pa, float *__restrict__ pb, float *__restrict__ pc) {
+    const float *src = blockIdx.y == 0 ? a : (blockIdx.y == 1 ? b : c);
+    float *dst = blockIdx.y == 0 ? pa : (blockIdx.y == 1 ? pb : pc);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
+        float v[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) v[ch] = ch < rc ? __ldg(src + (size_t)ch * npix + i) : 0.f;
+        float4 *o = reinterpret_cast<float4 *>(dst + (size_t)i * 8);
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+__global__ void __launch_bounds__(256)
+unpack_planes_add_kernel(int rc, int npix, const float *__restrict__ pa, const float *__restrict__ pb,
+                         const float *__restrict__ pc, float *__restrict__ a, float *__restrict__ b, float *__restrict__ c) {
+    const float *src = blockIdx.y == 0 ? pa : (blockIdx.y == 1 ? pb : pc);
+    float *dst = blockIdx.y == 0 ? a : (blockIdx.y == 1 ? b : c);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < npix; i += gridDim.x * 256) {
+        const float4 *in = reinterpret_cast<const float4 *>(src + (size_t)i * 8);
+        const float4 lo = __ldg(in), hi = __ldg(in + 1);
+        const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+            if (ch < rc && v[ch] != 0.f) dst[(size_t)ch * npix + i] += v[ch];
+    }
+}
+}  // namespace splatco
+
+extern "C" int splatco_pack_planes(int rc, int E, const float *xy, const float *xz, const float *yz, float *pxy,
+                                   float *pxz, float *pyz, void *stream) {
+    SPLATCO_REQUIRE(rc >= 1 && rc <= 8 && E >= 1 && (int64_t)E * E < 0x7fffffff, "pack_planes: bad sizes rc=%d E=%d", rc, E);
+    SPLATCO_REQUIRE(xy && xz && yz && pxy && pxz && pyz, "pack_planes: null pointer");
+    SPLATCO_REQUIRE((((uintptr_t)pxy | (uintptr_t)pxz | (uintptr_t)pyz) & 31) == 0, "pack_planes: outputs need 32-byte alignment");
+    const int npix = E * E;
+    pack_planes_kernel<<<dim3(min(148 * 8, ceil_div(npix, 256)), 3), 256, 0, (cudaStream_t)stream>>>(rc, npix, xy, xz, yz, pxy, pxz, pyz);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_unpack_planes_add(int rc, int E, const float *gpxy, const float *gpxz, const float *gpyz,
+                                         float *gxy, float *gxz, float *gyz, void *stream) {
+    SPLATCO_REQUIRE(rc >= 1 && rc <= 8 && E >= 1 && (int64_t)E * E < 0x7fffffff, "unpack_planes_add: bad sizes rc=%d E=%d", rc, E);
+    SPLATCO_REQUIRE(gpxy && gpxz && gpyz && gxy && gxz && gyz, "unpack_planes_add: null pointer");
+    const int npix = E * E;
+    unpack_planes_add_kernel<<<dim3(min(148 * 8, ceil_div(npix, 256)), 3), 256, 0, (cudaStream_t)stream>>>(rc, npix, gpxy, gpxz, gpyz,
+                                                                                                          gxy, gxz, gyz);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

@@ -37,7 +37,7 @@ class DecodeDesc(C.Structure):
         ("bn_rm", _vp * 3), ("bn_rv", _vp * 3), ("cbn_rm", _vp * 3), ("cbn_rv", _vp * 3),
         ("bn_nbt", _vp * 3), ("cbn_nbt", _vp * 3),
         ("w1", _vp * 3), ("b1", _vp * 3), ("w2", _vp * 3), ("b2", _vp * 3),
-        ("app_vec", _vp), ("noise", _vp),
+        ("app_vec", _vp), ("noise", _vp), ("plane_layout", C.c_int32),
     ]
 
 
@@ -86,7 +86,7 @@ def _c(t):
 class DecodeConfig:
     """Everything that is not a differentiable tensor input."""
     __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
-                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan", "raster")
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan", "raster", "packed")
 
 
 # order of the differentiable parameter list handed to the autograd Function
@@ -155,6 +155,7 @@ def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, 
     d.att[0], d.att[1], d.att[2] = att[0].data_ptr(), att[1].data_ptr(), att[2].data_ptr()
     d.app_vec = app_vec.data_ptr() if app_vec is not None else None
     d.noise = cfg.noise.data_ptr() if cfg.noise is not None else None
+    d.plane_layout = 1 if cfg.packed else 0
     return d
 
 
@@ -316,6 +317,98 @@ class _TriPlaneAttention(torch.autograd.Function):
         return tuple(rets)
 
 
+class _PackPlanes(torch.autograd.Function):
+    """Channel-last copies [E,E,8] of three [1,rc,E,E] planes (splatco_pack_planes); backward adds the
+    channel-last gradients back into the planes' gradient buffers of this backward pass."""
+
+    @staticmethod
+    def forward(ctx, xy, xz, yz):
+        L = _register()
+        dev = xy.device
+        ins = [t if _plain(t) else _c(t) for t in (xy, xz, yz)]
+        rc, E = int(xy.shape[1]), int(xy.shape[2])
+        with _lib.on_device(dev):
+            outs = [torch.empty((E, E, 8), dtype=torch.float32, device=dev) for _ in range(3)]
+            with stage("pack_planes"):
+                check(L.splatco_pack_planes(rc, E, *[_p(t) for t in ins], *[_p(t) for t in outs], _lib.raw_stream(dev)),
+                      "splatco_pack_planes")
+        ctx.dims, ctx.origs, ctx.shapes = (rc, E), (xy, xz, yz), [t.shape for t in ins]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_xy, g_xz, g_yz):
+        L = _register()
+        rc, E = ctx.dims
+        dev = ctx.origs[0].device
+        need = ctx.needs_input_grad
+        with _lib.on_device(dev):
+            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, shp) for n, (o, shp) in enumerate(zip(ctx.origs, ctx.shapes))])
+            ptrs = [g[0] for g in got]
+            rets = [g[1] if need[n] else None for n, g in enumerate(got)]
+            del got
+            gs = [g if g is not None else torch.zeros((E, E, 8), dtype=torch.float32, device=dev) for g in (g_xy, g_xz, g_yz)]
+            gs = [g if _plain(g) else _c(g) for g in gs]
+            with stage("unpack_planes"):
+                check(L.splatco_unpack_planes_add(rc, E, *[_p(g) for g in gs], *ptrs, _lib.raw_stream(dev)),
+                      "splatco_unpack_planes_add")
+        return tuple(rets)
+
+
+# "auto": pack when the mv views of an iteration amortise the two extra passes over the planes; True / False force it
+PACK_PLANES = "auto"
+
+
+class _PackCache:
+    """Channel-last plane copies are view-independent like TriPlaneAttention's output: built on the first
+    view of an iteration, reused by the others, dropped when a plane changes (optimizer step) or once a
+    backward pass has flowed through them.  `uses` of the previous generation estimates mv."""
+
+    def __init__(self):
+        self.key, self.value, self.uses, self.last_uses = None, None, 0, 1
+
+    def get(self, planes, V):
+        key = (torch.is_grad_enabled(),) + tuple((id(t), t._version, t.data_ptr()) for t in planes)
+        if self.key == key:
+            self.uses += 1
+            return self.value
+        if self.key is not None:
+            self.last_uses = max(self.uses, 1)
+        self.key, self.uses = key, 1
+        want = PACK_PLANES
+        if want == "auto":
+            # measured on B200 (profiles/README.md, r1p): the channel-last layout saves ~0.7 ns per visible anchor and
+            # view in the gather + scatter kernels, packing / unpacking / zero-filling costs ~1.2 us per MB of planes
+            # per iteration -> worth it from roughly 2200 anchor-views per MB (C3: yes, C2 at mv=4: break-even, no)
+            plane_mb = sum(t.numel() for t in planes) * 4 / 1e6
+            want = V * self.last_uses > 2200.0 * plane_mb
+        if not want or int(planes[0].shape[1]) > 8:
+            self.value = None
+            return None
+        packed = []
+        for q in range(0, len(planes), 3):
+            packed += list(_PackPlanes.apply(*planes[q:q + 3]))
+        if packed[0].requires_grad:
+            packed[0].register_hook(self._invalidate)
+        self.value = tuple(packed)
+        return self.value
+
+    def _invalidate(self, grad):
+        self.key, self.value = None, None
+        return grad
+
+
+_pack_caches = {}
+
+
+def _pack_cache_for(owner) -> _PackCache:
+    c = _pack_caches.get(id(owner))
+    if c is None:
+        if len(_pack_caches) > 8:
+            _pack_caches.clear()
+        c = _pack_caches[id(owner)] = _PackCache()
+    return c
+
+
 class _TACache:
     """TriPlaneAttention is view-independent (it only reads the level-0 planes and its own weights) but
     the reference recomputes it for every view.  Its output is cached here and
@@ -450,6 +543,15 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
         params += [_par(m0, "weight"), _par(m0, "bias"), _par(m2, "weight"), _par(m2, "bias")]
     # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169)
     att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
+    # channel-last copies of every sampled plane (direct planes of the active levels + the attended ones)
+    nper = len(PER_LEVEL)
+    planes = [params[l * nper + q] for l in range(level + 1) for q in range(3)] + list(att)
+    packed = _pack_cache_for(plan.levels[0][0]).get(planes, int(cfg.vis_idx.shape[0]))
+    cfg.packed = packed is not None
+    if cfg.packed:
+        for l in range(level + 1):
+            params[l * nper: l * nper + 3] = packed[3 * l: 3 * l + 3]
+        att = packed[3 * (level + 1):]
     app_vec = None
     if cfg.app_dim > 0:
         app_vec = pc.get_appearance.embedding.weight[int(viewpoint_camera.uid)]

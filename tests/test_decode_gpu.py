@@ -65,8 +65,17 @@ def named_leaves(pc):
     return named
 
 
+@pytest.fixture(params=[False, True], ids=["planar", "channel_last"])
+def plane_layout(request):
+    """Run with the planes as the reference stores them and with the channel-last copies (decode.PACK_PLANES)."""
+    from splatco_b200 import decode
+    prev, decode.PACK_PLANES = decode.PACK_PLANES, request.param
+    yield request.param
+    decode.PACK_PLANES = prev
+
+
 @pytest.mark.parametrize("tag", ["base", "variants"])
-def test_decode_matches_reference_golden(tag):
+def test_decode_matches_reference_golden(tag, plane_layout):
     from splatco_b200.gaussian_renderer import generate_neural_gaussians
     d = np.load(os.path.join(GOLD, f"decode_{tag}.npz"))
     pc = pc_from_fixture(d)
