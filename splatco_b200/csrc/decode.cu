@@ -246,12 +246,34 @@ __device__ __forceinline__ void plane_axes(int pl, const float ind[3], float &u,
     v = pl == 0 ? ind[1] : ind[2];
 }
 
+// What plane column c samples: resolved once per CTA into shared memory (16 bytes per column) instead of once per
+// (anchor, column) in registers -- plane_channel() costs two integer divisions and the base-pointer selection a chain
+// of selects, ~50 instructions per use, and both kernels below are bound by instructions in flight.
+struct __align__(16) ColDesc { const float *base; int E; int axis; };
+__device__ __forceinline__ void build_col_table(ColDesc *tab, int DP, int rc, const int *E, const float *const (*plane)[3],
+                                                const float *const *att, int packed) {
+    for (int c = threadIdx.x; c < DP; c += blockDim.x) {
+        int lvl, pl, a, ch;
+        plane_channel(c, rc, lvl, pl, a, ch);
+        const float *b = a ? att[pl] : plane[lvl][pl];
+        ColDesc d;
+        d.E = E[lvl];
+        d.axis = pl;
+        d.base = b ? b + (packed ? (size_t)ch : (size_t)ch * d.E * d.E) : nullptr;
+        tab[c] = d;
+    }
+    __syncthreads();
+}
+
 constexpr int GATHER_WARPS = 8;
 
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
+__global__ void __launch_bounds__(GATHER_WARPS * 32, 3)
 dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__ X, float *__restrict__ XIN,
                   double *__restrict__ stats, float *__restrict__ XT) {
     extern __shared__ float s_red[];     // [GATHER_WARPS][2][LDX]
+    __shared__ ColDesc s_col[DEC_MAX_DP];
+    build_col_table(s_col, DP, rc, p.E, p.plane, p.att, p.packed);
+    const int ts = p.packed ? 8 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps_total = gridDim.x * GATHER_WARPS;
     constexpr int MAXC = 6;              // ceil((96+71)/32)
@@ -265,30 +287,35 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
         float ind[3];
         norm_coords(p, ax, ay, az, ind);
         float *xrow = X + (size_t)v * LDX;
+        // phase 1: every load of this anchor (up to 4 texels x 6 column groups per lane) with no store in between,
+        // so they are all in flight together; phase 2 writes the row.  (One group's loads at a time made the
+        // plane-texel latency the critical path: ncu showed ~40 % of the stall samples on these lines.)
+        float vals[MAXC];
 #pragma unroll
         for (int j = 0; j < MAXC; ++j) {
             const int c = lane + 32 * j;
-            if (c >= ncols) break;
-            float val;
+            float val = 0.f;
             if (c < DP) {
-                int lvl, pl, att, ch;
-                plane_channel(c, rc, lvl, pl, att, ch);
+                const ColDesc cd = s_col[c];
                 float u, w;
-                plane_axes(pl, ind, u, w);
-                const int E = p.E[lvl];
-                const Bilin b = bilin_setup(u, w, E);
-                // channel-last planes: the rc channels of a texel share one 32-byte sector, so the lanes of one
-                // plane sample touch 4 sectors instead of 4 per channel
-                const float *base = (att ? p.att[pl] : p.plane[lvl][pl]) + (p.packed ? (size_t)ch : (size_t)ch * E * E);
-                val = bilin_fetch(base, b, p.packed ? 8 : 1);
+                plane_axes(cd.axis, ind, u, w);
+                // (channel-last planes: the rc channels of a texel share one 32-byte sector)
+                val = bilin_fetch(cd.base, bilin_setup(u, w, cd.E), ts);
                 if (p.noise && c >= 6 * rc) val += __ldg(p.noise + (size_t)v * (DP - 6 * rc) + (c - 6 * rc));
-            } else {
+            } else if (c < ncols) {
                 const int g = c - DP;
                 if (g < FD) val = __ldg(p.anchor_feat + (size_t)i * FD + g);
                 else if (g < FD + 3) val = g == FD ? ax : (g == FD + 1 ? ay : az);
                 else if (g < FD + 3 + 3 * KO) val = __ldg(p.offset + (size_t)i * 3 * KO + (g - FD - 3));
                 else val = __ldg(p.scaling + (size_t)i * 6 + (g - FD - 3 - 3 * KO));
             }
+            vals[j] = val;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane + 32 * j;
+            if (c >= ncols) break;
+            const float val = vals[j];
             xrow[c] = val;
             if (XT) {       // tile / chunk layout for the tensor-core kernel: [tile][chunk][row][4]; g starts on a fresh chunk
                 const int cc = c < DP ? c : ((DP + 3) & ~3) + (c - DP);
@@ -778,7 +805,8 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
 // bilinear scatter into the plane gradients, and the per-anchor rows of the N-row gradient tensors.
 // One warp per visible anchor (same mapping as the gather).
 struct DecInputGrads {
-    float *anchor_feat, *anchor, *offset, *scaling;     // [N,*], visible rows accumulated (+=)
+    float *anchor_feat, *anchor, *offset, *scaling;     // [N,*], visible rows accumulated (fire-and-forget REDs: a
+                                                        // read-modify-write would stall on its own load)
     float *plane[3][3];
     float *att[3];
 };
@@ -788,6 +816,9 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
                       const float *__restrict__ XIN, const float *__restrict__ mu, const float *__restrict__ rstd,
                       const float *__restrict__ m1, const float *__restrict__ m2, const float *__restrict__ DXH,
                       const float *__restrict__ DX, const float *__restrict__ DGA) {
+    __shared__ ColDesc s_col[DEC_MAX_DP];
+    build_col_table(s_col, DP, rc, p.E, gi.plane, gi.att, p.packed);        // bases of the plane GRADIENTS (may be null)
+    const int ts = p.packed ? 8 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps_total = gridDim.x * GATHER_WARPS;
     const int ncols = DP + GD;
@@ -828,23 +859,21 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
             if (c >= ncols) break;
             const float dx = dxs[j];
             if (c < DP) {
-                int lvl, pl, att, ch;
-                plane_channel(c, rc, lvl, pl, att, ch);
-                float u, w;
-                plane_axes(pl, ind, u, w);
-                const int E = p.E[lvl];
-                const Bilin b = bilin_setup(u, w, E);
-                float *base = (att ? gi.att[pl] : gi.plane[lvl][pl]);
-                if (base) bilin_scatter(base + (p.packed ? (size_t)ch : (size_t)ch * E * E), b, dx, p.packed ? 8 : 1);
+                const ColDesc cd = s_col[c];
+                if (cd.base) {
+                    float u, w;
+                    plane_axes(cd.axis, ind, u, w);
+                    bilin_scatter(const_cast<float *>(cd.base), bilin_setup(u, w, cd.E), dx, ts);
+                }
             } else {
                 const int g = c - DP;
-                if (g < FD) gi.anchor_feat[(size_t)i * FD + g] += dx + dx100[g];
+                if (g < FD) atomicAdd(&gi.anchor_feat[(size_t)i * FD + g], dx + dx100[g]);
                 else if (g < FD + 3) {
                     const int q = g - FD;
-                    gi.anchor[3 * (size_t)i + q] += dx + dga[q] + (q == 0 ? dv0 : (q == 1 ? dv1 : dv2));
+                    atomicAdd(&gi.anchor[3 * (size_t)i + q], dx + dga[q] + (q == 0 ? dv0 : (q == 1 ? dv1 : dv2)));
                 }
-                else if (g < FD + 3 + 3 * KO) gi.offset[(size_t)i * 3 * KO + (g - FD - 3)] += dx + dga[3 + (g - FD - 3)];
-                else gi.scaling[(size_t)i * 6 + (g - FD - 3 - 3 * KO)] += dx + dga[33 + (g - FD - 3 - 3 * KO)];
+                else if (g < FD + 3 + 3 * KO) atomicAdd(&gi.offset[(size_t)i * 3 * KO + (g - FD - 3)], dx + dga[3 + (g - FD - 3)]);
+                else atomicAdd(&gi.scaling[(size_t)i * 6 + (g - FD - 3 - 3 * KO)], dx + dga[33 + (g - FD - 3 - 3 * KO)]);
             }
         }
     }
