@@ -216,6 +216,18 @@ int splatco_ta_bwd(int rc, int E, int hidden, int ksize, const float *xy, const 
                    const float *g_out_xy, const float *g_out_xz, const float *g_out_yz, float *g_xy,
                    float *g_xz, float *g_yz, float *g_w_ca1, float *g_w_ca2, float *g_w_sa, void *stream);
 
+/* ---- densification statistics of one view --------------------------------
+ * Replaces GaussianModel.training_statis (scene/gaussian_model.py:761-782; called at train.py:264-266 with the
+ * last view's outputs).  vis_idx [V]: ascending indices of the anchors in voxel_visible_mask; neural_opacity
+ * [V*K]; selection_mask [V*K] (uint8, the decode's opacity mask) with selection_excl [V*K] its exclusive prefix
+ * sum (= index of the offset among the M rendered Gaussians); update_filter [M] (uint8, radii > 0);
+ * viewspace_grad [M,3] (.grad of viewspace_points; may be NULL if M == 0).  Updates in place opacity_accum [N],
+ * anchor_demon [N], offset_gradient_accum [N*K], offset_denom [N*K]. */
+int splatco_training_statis(int V, int K, const int32_t *vis_idx, const float *neural_opacity,
+                            const uint8_t *selection_mask, const int32_t *selection_excl,
+                            const uint8_t *update_filter, const float *viewspace_grad, float *opacity_accum,
+                            float *anchor_demon, float *offset_gradient_accum, float *offset_denom, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:
  * C[M,N] = A[M,K] * B[N,K]^T (row-major fp32, N <= 112, K <= 136).  variant bit0: swapped LBO/SBO
