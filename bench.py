@@ -7,7 +7,8 @@ A "step" is one training iteration's render work for the `--mv` multi-view batch
 configs[1]: Tanks&Temples-shaped, 100k anchors x 10 offsets ~ 1M candidate Gaussians, 980x545, mv=4):
 for every view   prefilter_voxel -> generate_neural_gaussians (fused decode) -> preprocess ->
 binning/sort -> blend,   the reference's per-view loss terms that touch the hot path's outputs
-(L1 + 0.01*mean(prod(scaling)), train.py:192-196; SSIM is SURVEY §8 row f3, not timed),   then ONE
+(0.8*L1 + 0.2*(1-SSIM) + 0.01*mean(prod(scaling)), train.py:192-196; the image part is the fused
+l1_ssim_loss of SURVEY §8 row f3),   then ONE
 backward over the summed loss (train.py:240), through the drop-in `gaussian_renderer.render()`.
 With N > 1 every rank renders its own mv views (weak scaling, views sharded by rank) and the
 parameter gradients are all-reduced with NCCL.
@@ -143,6 +144,7 @@ def run_ours(args):
     import torch.distributed as dist
     from splatco_b200 import _lib, profiling
     from splatco_b200.gaussian_renderer import prefilter_voxel, render
+    from splatco_b200.loss import l1_ssim_loss
     from splatco_b200.multiview import GradBucket
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,7 +177,8 @@ def run_ours(args):
             gt = gts_pinned[v].to(device, non_blocking=True) if host_inputs else gts_dev[v]
             vm = prefilter_voxel(cams[v], pc, PIPE, bg)
             pkg = render(cams[v], pc, PIPE, bg, visible_mask=vm, retain_grad=True)
-            loss = (pkg["render"] - gt).abs().mean() + 0.01 * pkg["scaling"].prod(dim=1).mean()
+            # the reference's per-view loss (train.py:192-196, lambda_dssim = 0.2 from arguments/__init__.py), image part fused
+            loss = l1_ssim_loss(pkg["render"], gt, 0.2) + 0.01 * pkg["scaling"].prod(dim=1).mean()
             total = loss if total is None else total + loss
             Ms.append(pkg["radii"].shape[0]); Vs.append(pkg["selection_mask"].shape[0] // cfg["K"])
         total.backward()
@@ -291,7 +294,7 @@ def run_ours(args):
         "config": {"workload": cfg["desc"], "path": "prefilter_voxel + render() drop-in: decode, preprocess, binning, blend, fwd+bwd",
                    "anchors": N, "visible_anchors": int(V), "gaussians": int(M), "instances_R": int(R),
                    "activate_level": LEVEL, "plane_size": cfg["plane_size"], "num_channels": cfg["C"], "Q0": 0.03,
-                   "mv": mv, "views_per_step": views, "loss": "L1 + 0.01*mean(prod(scaling)) (torch elementwise)",
+                   "mv": mv, "views_per_step": views, "loss": "0.8*L1 + 0.2*(1-SSIM) (fused kernels) + 0.01*mean(prod(scaling)), train.py:192-196",
                    "l2": "per-step working set (planes + workspaces) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"view-sharded dp{world}, NCCL grad all-reduce" if world > 1 else "single GPU"},
         "it_per_s": round(1000.0 / ms_step, 3),

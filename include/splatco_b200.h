@@ -228,6 +228,17 @@ int splatco_training_statis(int V, int K, const int32_t *vis_idx, const float *n
                             const uint8_t *update_filter, const float *viewspace_grad, float *opacity_accum,
                             float *anchor_demon, float *offset_gradient_accum, float *offset_denom, void *stream);
 
+/* ---- fused L1 + SSIM image loss ------------------------------------------
+ * Replaces l1_loss + ssim of utils/loss_utils.py:17-18,33-63 as combined at train.py:192-196:
+ *   loss = (1 - lambda_dssim) * mean|img - gt| + lambda_dssim * (1 - mean(ssim_map(img, gt)))
+ * img, gt: [C,H,W] fp32.  fwd writes out3[0..2] = (loss, l1, ssim) on the device and keeps the three
+ * partial-derivative maps in ws (splatco_loss_ws_bytes); bwd writes dL/dimg = *grad_loss * dloss/dimg. */
+size_t splatco_loss_ws_bytes(int C, int H, int W);
+int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, void *ws,
+                        float *out3, void *stream);
+int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, const void *ws,
+                        const float *grad_loss, float *dL_dimg, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:
  * C[M,N] = A[M,K] * B[N,K]^T (row-major fp32, N <= 112, K <= 136).  variant bit0: swapped LBO/SBO

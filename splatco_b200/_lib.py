@@ -52,6 +52,9 @@ SIGNATURES = {
     "splatco_ta_bwd_ws_bytes": (_sz, [_i, _i]),
     "splatco_ta_fwd": (_i, [_i, _i, _i, _i] + [_vp] * 11),
     "splatco_ta_bwd": (_i, [_i, _i, _i, _i] + [_vp] * 18),
+    "splatco_loss_ws_bytes": (_sz, [_i, _i, _i]),
+    "splatco_l1_ssim_fwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
+    "splatco_l1_ssim_bwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "splatco_training_statis": (_i, [_i, _i] + [_vp] * 11),
     "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }

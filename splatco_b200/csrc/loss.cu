@@ -1,0 +1,199 @@
+// Fused L1 + SSIM image loss, forward and backward.
+// Reference being replaced (file:line in /root/reference):
+//   utils/loss_utils.py:17-18    l1_loss  = mean |img - gt|
+//   utils/loss_utils.py:33-63    ssim: 11x11 Gaussian window (sigma 1.5, outer product of the normalised 1-D window),
+//                                five grouped conv2d with zero padding 5, C1 = 0.01^2, C2 = 0.03^2, mean of the map
+//   train.py:192-196             loss = (1 - lambda) * Ll1 + lambda * (1 - ssim(image, gt))   (+ scaling term, not here)
+// The reference spends 5 cuDNN grouped convolutions + ~15 elementwise launches per call and the same again in
+// autograd's backward.  Here: one forward kernel (16x16-pixel tiles, 5-pixel halo in shared memory, separable
+// window: 11 horizontal + 11 vertical taps instead of 121) that also stores the three partial-derivative maps
+// dm/dmu1, dm/dE[x^2], dm/dE[xy], and one backward kernel that convolves those maps with the same window:
+//   dL/dx = conv(dm/dmu1) + 2 x conv(dm/dE[x^2]) + y conv(dm/dE[xy])          (window symmetric)
+// HBM-bound: forward reads 2 and writes 3 floats per pixel-channel, backward reads 5 and writes 1.
+#include "common.cuh"
+
+namespace splatco {
+
+constexpr int LS_T = 16, LS_R = 5, LS_K = 11, LS_REG = LS_T + 2 * LS_R;      // 26
+constexpr float LS_C1 = 0.01f * 0.01f, LS_C2 = 0.03f * 0.03f;
+
+struct LossWindow { float g[LS_K]; };
+
+// normalised 1-D Gaussian window, computed like utils/loss_utils.py:23-25 (fp32 exp, fp32 sum)
+static LossWindow make_window() {
+    LossWindow w;
+    float s = 0.f;
+    for (int x = 0; x < LS_K; ++x) { w.g[x] = expf(-(float)((x - LS_K / 2) * (x - LS_K / 2)) / (2.0f * 1.5f * 1.5f)); s += w.g[x]; }
+    for (int x = 0; x < LS_K; ++x) w.g[x] /= s;
+    return w;
+}
+
+// sums[0] += sum |x - y|, sums[1] += sum ssim_map   (fp64 accumulators: the means are over ~1.6 M terms)
+__global__ void __launch_bounds__(LS_T * LS_T)
+l1_ssim_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossWindow win,
+                   float *__restrict__ d_mu1, float *__restrict__ d_exx, float *__restrict__ d_exy,
+                   double *__restrict__ sums) {
+    __shared__ float s_x[LS_REG][LS_REG + 1], s_y[LS_REG][LS_REG + 1];
+    __shared__ float s_h[5][LS_REG][LS_T + 1];          // horizontally filtered x, y, xx, yy, xy
+    __shared__ float s_red[2][LS_T * LS_T / 32];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * LS_T, y0 = blockIdx.y * LS_T;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    for (int r = tid; r < LS_REG * LS_REG; r += LS_T * LS_T) {
+        const int ry = r / LS_REG, rx = r - ry * LS_REG;
+        const int gy = y0 + ry - LS_R, gx = x0 + rx - LS_R;
+        float a = 0.f, b = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) { a = __ldg(img + plane + (size_t)gy * W + gx); b = __ldg(gt + plane + (size_t)gy * W + gx); }
+        s_x[ry][rx] = a; s_y[ry][rx] = b;
+    }
+    __syncthreads();
+    for (int r = tid; r < LS_REG * LS_T; r += LS_T * LS_T) {
+        const int ry = r / LS_T, cx = r - ry * LS_T;
+        float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+#pragma unroll
+        for (int k = 0; k < LS_K; ++k) {
+            const float a = s_x[ry][cx + k], b = s_y[ry][cx + k], g = win.g[k];
+            hx = fmaf(g, a, hx); hy = fmaf(g, b, hy);
+            hxx = fmaf(g, a * a, hxx); hyy = fmaf(g, b * b, hyy); hxy = fmaf(g, a * b, hxy);
+        }
+        s_h[0][ry][cx] = hx; s_h[1][ry][cx] = hy; s_h[2][ry][cx] = hxx; s_h[3][ry][cx] = hyy; s_h[4][ry][cx] = hxy;
+    }
+    __syncthreads();
+    const int ly = tid / LS_T, lx = tid - ly * LS_T;
+    const int gy = y0 + ly, gx = x0 + lx;
+    float l1 = 0.f, m = 0.f;
+    if (gy < H && gx < W) {
+        float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+        for (int k = 0; k < LS_K; ++k) {
+            const float g = win.g[k];
+            mu1 = fmaf(g, s_h[0][ly + k][lx], mu1); mu2 = fmaf(g, s_h[1][ly + k][lx], mu2);
+            exx = fmaf(g, s_h[2][ly + k][lx], exx); eyy = fmaf(g, s_h[3][ly + k][lx], eyy);
+            exy = fmaf(g, s_h[4][ly + k][lx], exy);
+        }
+        const float s1 = exx - mu1 * mu1, s2 = eyy - mu2 * mu2, s12 = exy - mu1 * mu2;
+        const float A = 2.f * mu1 * mu2 + LS_C1, B = 2.f * s12 + LS_C2;
+        const float Cc = mu1 * mu1 + mu2 * mu2 + LS_C1, D = s1 + s2 + LS_C2;
+        const float inv = 1.f / (Cc * D);
+        m = A * B * inv;
+        // partial derivatives of m with E[x], E[x^2], E[xy] as the independent variables
+        const size_t o = plane + (size_t)gy * W + gx;
+        d_mu1[o] = 2.f * mu2 * (B - A) * inv - m * 2.f * mu1 * (D - Cc) * inv;
+        d_exx[o] = -m / D;
+        d_exy[o] = 2.f * A * inv;
+        l1 = fabsf(s_x[ly + LS_R][lx + LS_R] - s_y[ly + LS_R][lx + LS_R]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { l1 += __shfl_xor_sync(0xffffffffu, l1, d); m += __shfl_xor_sync(0xffffffffu, m, d); }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = l1; s_red[1][tid >> 5] = m; }
+    __syncthreads();
+    if (tid < 2) {
+        double s = 0.0;
+        for (int w = 0; w < LS_T * LS_T / 32; ++w) s += (double)s_red[tid][w];
+        atomicAdd(&sums[tid], s);
+    }
+}
+
+// out[0] = loss, out[1] = l1 mean, out[2] = ssim mean
+__global__ void l1_ssim_finish_kernel(const double *__restrict__ sums, double count, float lambda, float *__restrict__ out) {
+    const double l1 = sums[0] / count, ss = sums[1] / count;
+    out[0] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ss));
+    out[1] = (float)l1;
+    out[2] = (float)ss;
+}
+
+// dL/dimg = g_loss * [ (1 - lambda) sign(x - y) / count  -  lambda / count * (conv(d_mu1) + 2 x conv(d_exx) + y conv(d_exy)) ]
+__global__ void __launch_bounds__(LS_T * LS_T)
+l1_ssim_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossWindow win,
+                   const float *__restrict__ d_mu1, const float *__restrict__ d_exx, const float *__restrict__ d_exy,
+                   const float *__restrict__ g_loss, float c_l1, float c_ssim, float *__restrict__ dimg) {
+    __shared__ float s_m[3][LS_REG][LS_REG + 1];
+    __shared__ float s_h[3][LS_REG][LS_T + 1];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * LS_T, y0 = blockIdx.y * LS_T;
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    for (int r = tid; r < LS_REG * LS_REG; r += LS_T * LS_T) {
+        const int ry = r / LS_REG, rx = r - ry * LS_REG;
+        const int gy = y0 + ry - LS_R, gx = x0 + rx - LS_R;
+        float a = 0.f, b = 0.f, c = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            const size_t o = plane + (size_t)gy * W + gx;
+            a = __ldg(d_mu1 + o); b = __ldg(d_exx + o); c = __ldg(d_exy + o);
+        }
+        s_m[0][ry][rx] = a; s_m[1][ry][rx] = b; s_m[2][ry][rx] = c;
+    }
+    __syncthreads();
+    for (int r = tid; r < LS_REG * LS_T; r += LS_T * LS_T) {
+        const int ry = r / LS_T, cx = r - ry * LS_T;
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LS_K; ++k) {
+            const float g = win.g[k];
+            h0 = fmaf(g, s_m[0][ry][cx + k], h0); h1 = fmaf(g, s_m[1][ry][cx + k], h1); h2 = fmaf(g, s_m[2][ry][cx + k], h2);
+        }
+        s_h[0][ry][cx] = h0; s_h[1][ry][cx] = h1; s_h[2][ry][cx] = h2;
+    }
+    __syncthreads();
+    const int ly = tid / LS_T, lx = tid - ly * LS_T;
+    const int gy = y0 + ly, gx = x0 + lx;
+    if (gy >= H || gx >= W) return;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LS_K; ++k) {
+        const float g = win.g[k];
+        v0 = fmaf(g, s_h[0][ly + k][lx], v0); v1 = fmaf(g, s_h[1][ly + k][lx], v1); v2 = fmaf(g, s_h[2][ly + k][lx], v2);
+    }
+    const size_t o = plane + (size_t)gy * W + gx;
+    const float x = __ldg(img + o), y = __ldg(gt + o);
+    const float dssim = v0 + 2.f * x * v1 + y * v2;
+    const float d = x - y;
+    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    dimg[o] = __ldg(g_loss) * (c_l1 * sgn - c_ssim * dssim);
+}
+
+}  // namespace splatco
+
+using namespace splatco;
+
+static int loss_check(int C, int H, int W) {
+    SPLATCO_REQUIRE(C >= 1 && C <= 65535 && H >= 1 && W >= 1 && (int64_t)C * H * W < 0x7fffffff, "l1_ssim: bad sizes C=%d H=%d W=%d", C, H, W);
+    return 0;
+}
+
+extern "C" size_t splatco_loss_ws_bytes(int C, int H, int W) {
+    return 3 * align_up((size_t)C * H * W * sizeof(float)) + align_up(2 * sizeof(double));
+}
+
+extern "C" int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, void *ws,
+                                   float *out3, void *stream) {
+    if (loss_check(C, H, W)) return -1;
+    SPLATCO_REQUIRE(img && gt && ws && out3, "l1_ssim_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t map = align_up((size_t)C * H * W * sizeof(float));
+    char *b = (char *)ws;
+    double *sums = (double *)(b + 3 * map);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    static const LossWindow win = make_window();
+    const dim3 grid(ceil_div(W, LS_T), ceil_div(H, LS_T), C);
+    l1_ssim_fwd_kernel<<<grid, LS_T * LS_T, 0, st>>>(H, W, img, gt, win, (float *)b, (float *)(b + map), (float *)(b + 2 * map), sums);
+    SPLATCO_CHECK_LAUNCH();
+    l1_ssim_finish_kernel<<<1, 1, 0, st>>>(sums, (double)C * H * W, lambda_dssim, out3);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, const void *ws,
+                                   const float *grad_loss, float *dL_dimg, void *stream) {
+    if (loss_check(C, H, W)) return -1;
+    SPLATCO_REQUIRE(img && gt && ws && grad_loss && dL_dimg, "l1_ssim_bwd: null pointer");
+    const size_t map = align_up((size_t)C * H * W * sizeof(float));
+    const char *b = (const char *)ws;
+    static const LossWindow win = make_window();
+    const float count = (float)((double)C * H * W);
+    const dim3 grid(ceil_div(W, LS_T), ceil_div(H, LS_T), C);
+    l1_ssim_bwd_kernel<<<grid, LS_T * LS_T, 0, (cudaStream_t)stream>>>(H, W, img, gt, win, (const float *)b, (const float *)(b + map),
+                                                                      (const float *)(b + 2 * map), grad_loss,
+                                                                      (1.f - lambda_dssim) / count, lambda_dssim / count, dL_dimg);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
