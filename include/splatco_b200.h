@@ -66,6 +66,16 @@ int splatco_visible_filter(int N, const float *means3D, const float *scales, int
                            float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
                            void *stream);
 
+/* Same filter, plus what render() derives from it next: mask_out[N] (uint8 0/1 = radii > 0, the bool tensor
+ * prefilter_voxel returns, gaussian_renderer/__init__.py:243-244), the ascending list idx_out[<= N] of the visible
+ * anchors (what the boolean indexing at :21-29 computes) and their count (device, in ws; copied to count_host
+ * (pinned) asynchronously if not NULL).  ws: splatco_visible_compact_ws_bytes(N). */
+size_t splatco_visible_compact_ws_bytes(int N);
+int splatco_visible_filter_compact(int N, const float *means3D, const float *scales, int scale_stride,
+                                   const float *rots, float scale_mod, const float *view, const float *proj,
+                                   float tanfovx, float tanfovy, int H, int W, int32_t *radii_out, uint8_t *mask_out,
+                                   int32_t *idx_out, void *ws, int32_t *count_host, void *stream);
+
 /* ---- forward, stage 1: preprocess + tile counts + scan --------------------------------------
  * Fills geom, radii_out[P]; leaves the instance count R in geom (device) and, if
  * num_rendered_host != NULL (pinned host memory), copies it there asynchronously on `stream`. */

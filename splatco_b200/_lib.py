@@ -29,6 +29,8 @@ SIGNATURES = {
     "splatco_image_layout": (_i, [_i, _i, C.POINTER(_sz), _i]),
     "splatco_sorted_buffer_index": (_i, [_i, _i]),
     "splatco_visible_filter": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp]),
+    "splatco_visible_compact_ws_bytes": (_sz, [_i]),
+    "splatco_visible_filter_compact": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd_counted": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_binning": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),

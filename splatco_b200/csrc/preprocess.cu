@@ -154,6 +154,50 @@ visible_filter_kernel(int N, const float *__restrict__ means3D, const float *__r
     radii[i] = o.radius;
 }
 
+// ---- anchor prefilter + stable compaction of the visible indices -----------------------------------------------
+// prefilter_voxel returns a bool mask (gaussian_renderer/__init__.py:243-244) that render() immediately turns back
+// into an index list with boolean indexing (:21-29).  The filter writes the mask, per-CTA counts, and (after the scan
+// of the counts) the ascending index list itself, so the host needs neither torch.nonzero nor its two syncs.
+__global__ void __launch_bounds__(PRE_THREADS)
+visible_filter_mask_kernel(int N, const float *__restrict__ means3D, const float *__restrict__ scales,
+                           int scale_stride, const float *__restrict__ rots, float mod,
+                           const float *__restrict__ view, const float *__restrict__ proj, float tanfovx,
+                           float tanfovy, float fx, float fy, int H, int W, int gx, int gy,
+                           int32_t *__restrict__ radii, uint8_t *__restrict__ mask, uint32_t *__restrict__ block_sums) {
+    __shared__ float s_cam[32];
+    stage_cam(s_cam, view, proj);
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    int radius = 0;
+    if (i < N) {
+        const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+        const float *sp = scales + (size_t)scale_stride * i;
+        const float4 q = *reinterpret_cast<const float4 *>(rots + 4 * (size_t)i);
+        Proj o;
+        project_one(x, y, z, sp[0], sp[1], sp[2], q, mod, s_cam, s_cam + 16, tanfovx, tanfovy, fx, fy, H, W, gx, gy, o);
+        radius = o.radius;
+        radii[i] = radius;
+        mask[i] = radius > 0 ? 1 : 0;
+    }
+    const int cnt = __syncthreads_count(radius > 0);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = (uint32_t)cnt;
+}
+
+__global__ void __launch_bounds__(PRE_THREADS)
+visible_compact_kernel(int N, const uint8_t *__restrict__ mask, const uint32_t *__restrict__ block_offsets,
+                       int32_t *__restrict__ idx_out) {
+    __shared__ uint32_t s_warp[PRE_THREADS / 32];
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const bool vis = i < N && mask[i];
+    const uint32_t b = __ballot_sync(0xffffffffu, vis);
+    if (lane == 0) s_warp[warp] = __popc(b);
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < PRE_THREADS / 32; ++w) woff += (w < (int)warp) ? s_warp[w] : 0u;
+    if (vis) idx_out[block_offsets[blockIdx.x] + woff + __popc(b & lanemask_lt())] = i;
+}
+
 // ---- preprocess forward: also emits per-block tile-count sums (first level of the scan) ---------
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_kernel(int P, const uint32_t *__restrict__ P_dev, const float *__restrict__ means3D, const float *__restrict__ scales,
@@ -350,6 +394,39 @@ extern "C" int splatco_visible_filter(int N, const float *means3D, const float *
     visible_filter_kernel<<<ceil_div(N, PRE_THREADS), PRE_THREADS, 0, (cudaStream_t)stream>>>(
         N, means3D, scales, scale_stride, rots, scale_mod, view, proj, tanfovx, tanfovy, fx, fy, H, W, gx, gy, radii_out);
     SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" size_t splatco_visible_compact_ws_bytes(int N) {
+    const size_t nb = (size_t)(N > 0 ? (N + PRE_THREADS - 1) / PRE_THREADS : 1);
+    return 2 * align_up(nb * sizeof(uint32_t)) + align_up(sizeof(uint32_t));
+}
+
+extern "C" int splatco_visible_filter_compact(int N, const float *means3D, const float *scales, int scale_stride,
+                                              const float *rots, float scale_mod, const float *view, const float *proj,
+                                              float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,
+                                              uint8_t *mask_out, int32_t *idx_out, void *ws, int32_t *count_host,
+                                              void *stream) {
+    SPLATCO_REQUIRE(N >= 0 && H > 0 && W > 0, "visible_filter_compact: bad sizes N=%d H=%d W=%d", N, H, W);
+    if (N == 0) { if (count_host) *count_host = 0; return 0; }
+    SPLATCO_REQUIRE(means3D && scales && rots && view && proj && radii_out && mask_out && idx_out && ws,
+                    "visible_filter_compact: null pointer");
+    SPLATCO_REQUIRE(scale_stride >= 3, "visible_filter_compact: scale_stride %d < 3", scale_stride);
+    SPLATCO_REQUIRE(((uintptr_t)rots & 15) == 0, "visible_filter_compact: rotations must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nb = ceil_div(N, PRE_THREADS);
+    char *b = (char *)ws;
+    uint32_t *sums = (uint32_t *)b, *offs = (uint32_t *)(b + align_up((size_t)nb * 4)), *total = (uint32_t *)(b + 2 * align_up((size_t)nb * 4));
+    const float fx = (float)W / (2.0f * tanfovx), fy = (float)H / (2.0f * tanfovy);
+    const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
+    visible_filter_mask_kernel<<<nb, PRE_THREADS, 0, st>>>(N, means3D, scales, scale_stride, rots, scale_mod, view, proj, tanfovx,
+                                                          tanfovy, fx, fy, H, W, gx, gy, radii_out, mask_out, sums);
+    SPLATCO_CHECK_LAUNCH();
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, sums, offs, total);
+    SPLATCO_CHECK_LAUNCH();
+    visible_compact_kernel<<<nb, PRE_THREADS, 0, st>>>(N, mask_out, offs, idx_out);
+    SPLATCO_CHECK_LAUNCH();
+    if (count_host) SPLATCO_CHECK_CUDA(cudaMemcpyAsync(count_host, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return 0;
 }
 

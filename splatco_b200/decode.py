@@ -528,10 +528,6 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     cfg.cam = cam if _plain(cam) else _c(cam)
     cfg.bn_eps, cfg.bn_momentum = plan.bn_eps, plan.bn_momentum
     cfg.update_running = bool(update_running)
-    if visible_mask is None:
-        cfg.vis_idx = torch.arange(cfg.N, dtype=torch.int32, device=dev)
-    else:
-        cfg.vis_idx = torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
     cfg.buffers = plan.buffers
     params = []
     for pl, bn, lin, cbn, clin in plan.levels:
@@ -543,6 +539,14 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
         params += [_par(m0, "weight"), _par(m0, "bias"), _par(m2, "weight"), _par(m2, "bias")]
     # TriPlaneAttention over the level-0 planes (scene/grids.py:166-169)
     att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
+    # the visible-anchor list LAST: everything above is independent of it and overlaps with the GPU finishing the
+    # prefilter (and whatever was queued before it); prefilter_voxel already compacted the indices on the device
+    if visible_mask is None:
+        cfg.vis_idx = torch.arange(cfg.N, dtype=torch.int32, device=dev)
+    else:
+        from .diff_gaussian_rasterization import take_compaction
+        got = take_compaction(visible_mask)
+        cfg.vis_idx = got[0] if got is not None else torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
     # channel-last copies of every sampled plane (direct planes of the active levels + the attended ones)
     nper = len(PER_LEVEL)
     planes = [params[l * nper + q] for l in range(level + 1) for q in range(3)] + list(att)

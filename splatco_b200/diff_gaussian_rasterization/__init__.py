@@ -370,3 +370,57 @@ class GaussianRasterizer(nn.Module):
                                                ptr(radii), _stream_ptr(dev)), "splatco_visible_filter")
             _debug_sync(rs, "visible_filter")
             return radii
+
+
+# ---- prefilter with the index list render() needs next -------------------------------------------------------
+class _Compaction:
+    __slots__ = ("mask", "version", "idx", "counter", "event")
+
+
+def visible_mask_compact(means3D, scales, rotations, raster_settings):
+    """bool[N] mask of the anchors whose Gaussian touches the view (radii > 0) -- what prefilter_voxel returns --
+    computed together with the ascending index list of the visible anchors; the list is handed to the decode by
+    `take_compaction(mask)` when render() is called with this very mask, replacing torch.nonzero and its syncs."""
+    rs = raster_settings
+    with torch.no_grad():
+        L = _lib.lib()
+        _require_cuda(means3D, scales, rotations, rs.viewmatrix, rs.projmatrix)
+        dev = means3D.device
+        N = int(means3D.shape[0])
+        mask_u8 = torch.empty(N, dtype=torch.uint8, device=dev)
+        if N == 0:
+            return mask_u8.view(torch.bool)
+        means3D = _f32c(means3D.detach())
+        rotations = _f32c(rotations.detach())
+        scales, sstride = _rows_f32(scales.detach(), 3)
+        view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
+        cp = _Compaction()
+        with _lib.on_device(dev), stage("visible_filter"):
+            radii = torch.empty(N, dtype=torch.int32, device=dev)
+            cp.idx = torch.empty(N, dtype=torch.int32, device=dev)
+            ws = torch.empty(L.splatco_visible_compact_ws_bytes(N), dtype=torch.uint8, device=dev)
+            cp.counter = _pinned_counter(dev, 2)
+            check(L.splatco_visible_filter_compact(N, ptr(means3D), ptr(scales), sstride, ptr(rotations),
+                                                   float(rs.scale_modifier), ptr(view), ptr(proj), float(rs.tanfovx),
+                                                   float(rs.tanfovy), int(rs.image_height), int(rs.image_width),
+                                                   ptr(radii), ptr(mask_u8), ptr(cp.idx), ptr(ws), cp.counter.data_ptr(),
+                                                   _stream_ptr(dev)), "splatco_visible_filter_compact")
+            cp.event = torch.cuda.Event()
+            cp.event.record(torch.cuda.current_stream(dev))
+        _debug_sync(rs, "visible_filter")
+        cp.mask = mask_u8.view(torch.bool)
+        cp.version = cp.mask._version
+        _spec_slot.compaction = cp
+        return cp.mask
+
+
+def take_compaction(visible_mask):
+    """(idx int32 [V], V) if `visible_mask` is the untouched tensor the last visible_mask_compact returned, else None.
+    Waits for the filter's read-back only (an event), not for the stream."""
+    cp = getattr(_spec_slot, "compaction", None)
+    if cp is None or cp.mask is not visible_mask or visible_mask._version != cp.version:
+        return None
+    _spec_slot.compaction = None
+    cp.event.synchronize()
+    V = int(cp.counter[0])
+    return cp.idx[:V], V

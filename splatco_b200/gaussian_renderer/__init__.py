@@ -14,7 +14,7 @@ import math
 import torch
 
 from ..decode import generate_neural_gaussians
-from ..diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from ..diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, visible_mask_compact
 
 try:  # re-export, as the reference module does
     from scene.gaussian_model import GaussianModel  # type: ignore  # noqa: F401
@@ -99,6 +99,9 @@ def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_
     else:
         scales = pc.get_scaling
         rotations = pc.get_rotation
-    radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales[:, :3], rotations=rotations,
-                                           cov3D_precomp=cov3D_precomp)
-    return radii_pure > 0
+    if cov3D_precomp is not None:
+        radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales, rotations=rotations,
+                                               cov3D_precomp=cov3D_precomp)          # raises (unsupported, see above)
+        return radii_pure > 0
+    # radii_pure > 0, plus the index list of the visible anchors kept aside for the render() call that follows
+    return visible_mask_compact(means3D, scales[:, :3], rotations, rasterizer.raster_settings)

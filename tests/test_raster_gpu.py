@@ -141,6 +141,16 @@ def test_visible_filter_bit_exact_strided():
     got = rast.visible_filter(means3D=means.cuda(), scales=s6d[:, :3], rotations=rots.cuda(), cov3D_precomp=None)
     assert got.dtype == torch.int32 and np.array_equal(got.cpu().numpy(), want)
     assert 0 < (want > 0).sum() < want.size
+    # the compacting variant prefilter_voxel uses: same decisions, plus the ascending index list
+    from splatco_b200.diff_gaussian_rasterization import take_compaction, visible_mask_compact
+    mask = visible_mask_compact(means.cuda(), s6d[:, :3], rots.cuda(), rast.raster_settings)
+    assert mask.dtype == torch.bool and np.array_equal(mask.cpu().numpy(), want > 0)
+    idx, V = take_compaction(mask)
+    assert V == int((want > 0).sum()) and np.array_equal(idx.cpu().numpy(), np.nonzero(want > 0)[0].astype(np.int32))
+    assert take_compaction(mask) is None                      # single use
+    mask2 = visible_mask_compact(means.cuda(), s6d[:, :3], rots.cuda(), rast.raster_settings)
+    mask2[0] = ~mask2[0]                                      # a modified mask must not be trusted
+    assert take_compaction(mask2) is None
 
 
 @pytest.mark.parametrize("seed,W,H,M,sig", [(41, 64, 48, 300, (1.0, 6.0)), (42, 250, 130, 5000, (0.5, 4.0)),
