@@ -159,6 +159,9 @@ typedef struct splatco_decode_desc {
     const float *app_vec;                  /* [app_dim] embedding row of this camera, or NULL           */
     const float *noise;                    /* [V, DP - 6*rc] additive plane-feature noise U(-.5,.5)*Q for
                                               levels >= 1 (scene/grids.py:159-164), or NULL (Q = 0)     */
+    float noise_q;                         /* used when noise == NULL: != 0 adds U(-.5,.5) * noise_q to the same
+                                              features, generated in the kernel from noise_seed             */
+    uint64_t noise_seed;
     int32_t plane_layout;                  /* 0: plane[] / att[] (and their gradients) are [rc,E,E] as the
                                               reference stores them; 1: [E,E,8] channel-last copies made by
                                               splatco_pack_planes (rc <= 8)                              */

@@ -191,6 +191,8 @@ struct DecPtrs {
     int E[3];
     const float *mn, *mx, *cam;      // device pointers (3 floats each)
     const float *noise;
+    float noise_q;                   // != 0: add U(-.5,.5) * noise_q to the plane features of levels >= 1, generated here
+    unsigned long long noise_seed;
     int packed;                      // 1: planes are [E,E,8] channel-last (splatco_pack_planes), 0: [rc,E,E]
 };
 
@@ -265,6 +267,17 @@ __device__ __forceinline__ void build_col_table(ColDesc *tab, int DP, int rc, co
     __syncthreads();
 }
 
+// U(-0.5, 0.5) from a counter-based generator: two rounds of a 64-bit mix (splitmix64 finaliser) of (seed, element
+// index).  The reference draws torch.empty_like(feat).uniform_(-0.5, 0.5) * Q (scene/grids.py:159-164): any
+// independent uniform stream is equivalent; this one is reproducible from torch's seed and the call counter.
+__device__ __forceinline__ float uniform_pm_half(unsigned long long seed, unsigned long long idx) {
+    unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f) - 0.5f;        // 24 random bits
+}
+
 constexpr int GATHER_WARPS = 8;
 
 __global__ void __launch_bounds__(GATHER_WARPS * 32, 3)
@@ -301,7 +314,10 @@ dec_gather_kernel(DecPtrs p, int V, int rc, int DP, int LDX, float *__restrict__
                 plane_axes(cd.axis, ind, u, w);
                 // (channel-last planes: the rc channels of a texel share one 32-byte sector)
                 val = bilin_fetch(cd.base, bilin_setup(u, w, cd.E), ts);
-                if (p.noise && c >= 6 * rc) val += __ldg(p.noise + (size_t)v * (DP - 6 * rc) + (c - 6 * rc));
+                if (c >= 6 * rc) {
+                    if (p.noise) val += __ldg(p.noise + (size_t)v * (DP - 6 * rc) + (c - 6 * rc));
+                    else if (p.noise_q != 0.f) val = fmaf(uniform_pm_half(p.noise_seed, (unsigned long long)v * DP + c), p.noise_q, val);
+                }
             } else if (c < ncols) {
                 const int g = c - DP;
                 if (g < FD) val = __ldg(p.anchor_feat + (size_t)i * FD + g);
@@ -966,6 +982,8 @@ DecPtrs make_ptrs(const splatco_decode_desc *d) {
     for (int q = 0; q < 3; ++q) p.att[q] = d->att[q];
     p.mn = d->xyz_min; p.mx = d->xyz_max; p.cam = d->cam;
     p.noise = d->noise;
+    p.noise_q = d->noise_q;
+    p.noise_seed = d->noise_seed;
     p.packed = d->plane_layout;
     return p;
 }

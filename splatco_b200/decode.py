@@ -37,7 +37,7 @@ class DecodeDesc(C.Structure):
         ("bn_rm", _vp * 3), ("bn_rv", _vp * 3), ("cbn_rm", _vp * 3), ("cbn_rv", _vp * 3),
         ("bn_nbt", _vp * 3), ("cbn_nbt", _vp * 3),
         ("w1", _vp * 3), ("b1", _vp * 3), ("w2", _vp * 3), ("b2", _vp * 3),
-        ("app_vec", _vp), ("noise", _vp), ("plane_layout", C.c_int32),
+        ("app_vec", _vp), ("noise", _vp), ("noise_q", C.c_float), ("noise_seed", C.c_uint64), ("plane_layout", C.c_int32),
     ]
 
 
@@ -86,7 +86,7 @@ def _c(t):
 class DecodeConfig:
     """Everything that is not a differentiable tensor input."""
     __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
-                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "plan", "raster", "packed")
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "noise_q", "noise_seed", "plan", "raster", "packed")
 
 
 # order of the differentiable parameter list handed to the autograd Function
@@ -155,6 +155,7 @@ def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, 
     d.att[0], d.att[1], d.att[2] = att[0].data_ptr(), att[1].data_ptr(), att[2].data_ptr()
     d.app_vec = app_vec.data_ptr() if app_vec is not None else None
     d.noise = cfg.noise.data_ptr() if cfg.noise is not None else None
+    d.noise_q, d.noise_seed = cfg.noise_q, cfg.noise_seed
     d.plane_layout = 1 if cfg.packed else 0
     return d
 
@@ -562,6 +563,9 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     return cfg, att, app_vec, params
 
 
+_noise_calls = 0
+
+
 def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, _raster_settings=None):
     """Drop-in for gaussian_renderer.generate_neural_gaussians (reference :18-116).  `_raster_settings`
     is render()'s private hint: the GaussianRasterizationSettings it is about to rasterize the result
@@ -571,11 +575,14 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
     # GaussianLearner.inference always passes Q = self.Q0 (0.03 while training, 0 in render.py):
     # U(-.5,.5)*Q is added to the plane features of the non-TA levels (scene/grids.py:159-164)
     Q = float(getattr(pc.feat_planes, "Q0", 0.0) or 0.0)
-    cfg.noise = None
-    if Q != 0.0 and cfg.level >= 1:
-        ncol = cfg.rc * (3 if cfg.level == 1 else 6)
-        cfg.noise = torch.empty((int(cfg.vis_idx.shape[0]), ncol), dtype=torch.float32,
-                                device=cfg.vis_idx.device).uniform_(-0.5, 0.5).mul_(Q)
+    cfg.noise = getattr(pc.feat_planes, "_splatco_noise", None)      # tests inject an explicit [V, ncol] noise tensor here
+    cfg.noise_q, cfg.noise_seed = 0.0, 0
+    if cfg.noise is None and Q != 0.0 and cfg.level >= 1:
+        # generated inside the gather kernel from (torch's seed, call counter): no [V, ncol] tensor, no torch launches
+        global _noise_calls
+        _noise_calls += 1
+        cfg.noise_q = Q
+        cfg.noise_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _noise_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
     outs = _FusedDecode.apply(cfg, pc._anchor_feat, pc.get_anchor, pc._offset, pc.get_scaling, att[0], att[1], att[2],
                               app_vec, *params)
     xyz, color, opacity, scaling, rot, neural_opacity, mask = outs

@@ -196,6 +196,36 @@ def test_decode_matches_oracle_large(level, rc):
                 assert rel_err(v.grad.cpu().numpy(), pw[f"{name}.{k}"].grad.numpy()) < 3e-3, (name, k)
 
 
+def test_plane_feature_noise_generated_in_kernel():
+    """Q0 != 0 (training): U(-.5,.5)*Q is added to the plane features of levels >= 1 only (scene/grids.py:159-181:
+    the TA level's noisy tensor is discarded), a fresh draw per call.  Read back from the gathered rows X."""
+    from splatco_b200.gaussian_renderer import generate_neural_gaussians
+    from splatco_b200.model import AnchorModel
+    N, K, rc = 6000, 10, 5
+    pc = AnchorModel(N, n_offsets=K, plane_size=256, num_channels=3 * rc, device="cuda", seed=5)
+    pc.feat_planes._feat.activate_level = 2
+    cam = Cam(torch.tensor([2.5, -1.5, 0.7]).cuda(), 0)
+    DP, LDX = 12 * rc, (12 * rc + 71 + 3) // 4 * 4
+
+    def gathered(Q):
+        pc.feat_planes.Q0 = Q
+        outs = generate_neural_gaussians(cam, pc, None, is_training=True)
+        ws = outs[0].grad_fn.ws
+        return ws[: N * LDX * 4].view(torch.float32).view(N, LDX).clone()
+
+    Q = 0.03
+    x0, x1, x2 = gathered(0.0), gathered(Q), gathered(Q)
+    d1, d2 = (x1 - x0), (x2 - x0)
+    assert float(d1[:, : 6 * rc].abs().max()) == 0.0, "the TA level takes no noise"
+    assert float(d1[:, DP:].abs().max()) == 0.0, "context columns take no noise"
+    n1 = d1[:, 6 * rc: DP]
+    assert float(n1.abs().max()) <= 0.5 * Q * (1 + 1e-4) + 1e-7
+    assert abs(float(n1.mean())) < 5e-3 * Q
+    assert abs(float(n1.var()) / (Q * Q / 12.0) - 1.0) < 0.02
+    assert abs(float((n1[:, 0] * n1[:, 1]).mean())) < 0.02 * Q * Q / 12.0        # neighbouring columns uncorrelated
+    assert float((d1 - d2).abs().max()) > 0.1 * Q, "every call must draw fresh noise"
+
+
 def test_render_dropin_end_to_end():
     """prefilter_voxel + render through the drop-in gaussian_renderer: contract of the returned dict and
     gradients reaching every leaf the reference trains (gaussian_renderer/__init__.py:174-188)."""
