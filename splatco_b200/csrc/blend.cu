@@ -27,6 +27,8 @@ constexpr int BLEND_THREADS = TILE * TILE;   // 256
 constexpr int BLEND_BATCH = 2 * BLEND_THREADS;   // splats staged per barrier (two per thread): half the barriers of a
                                                  // 256-splat batch, and the per-warp work imbalance averages out better
 constexpr int BLEND_WORDS = BLEND_BATCH / 32;    // 16 mask words per patch warp
+constexpr int RB_SLOTS = 3, RB_ROWS = 9 * RB_SLOTS, RB_STRIDE = 36;     // backward reduction buffer (see blend_bwd_kernel)
+constexpr size_t BWD_SMEM = (size_t)BLEND_BATCH * 64 + (size_t)(BLEND_THREADS / 32) * RB_ROWS * RB_STRIDE * sizeof(float);
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLog2Inv255 = -7.994353436858858f;     // log2(1/255)
 
@@ -237,9 +239,15 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                  const float *__restrict__ dL_dpix, float *__restrict__ dL_dmean2D,
                  float *__restrict__ dL_dconic, float *__restrict__ dL_dopacity,
                  float *__restrict__ dL_dcolor, const uint32_t *__restrict__ order) {
-    __shared__ float4 s_rec[BLEND_BATCH * 4];
+    // dynamic shared memory (BWD_SMEM bytes): the staged records, then the per-warp transposition buffers of the
+    // gradient partials: RB_SLOTS buffered (warp, splat) visits x 9 sums x 32 lanes, rows padded to 36 floats so
+    // that both the lane-wise stores and the row-wise 16-byte loads are bank-conflict free
+    extern __shared__ float4 s_dyn4[];
+    float4 *const s_rec = s_dyn4;                                             // [BLEND_BATCH * 4]
+    float *const s_buf_all = reinterpret_cast<float *>(s_dyn4 + BLEND_BATCH * 4);   // [8][RB_ROWS * RB_STRIDE]
     __shared__ uint32_t s_mask[8][BLEND_WORDS];
     __shared__ int s_max[BLEND_THREADS / 32];
+    __shared__ int s_meta[BLEND_THREADS / 32][RB_SLOTS];
     const int tile = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
     const int tile_x = tile % gx, tile_y = tile / gx;
     int px, py;
@@ -258,6 +266,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(s_rec);
+    float *const buf = s_buf_all + warp * (RB_ROWS * RB_STRIDE);
 
     // deepest contributor over the tile: nothing behind it receives gradient
     const int warp_last = __reduce_max_sync(0xffffffffu, last);
@@ -266,17 +275,40 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     int tile_last = 0;
 #pragma unroll
     for (int w = 0; w < BLEND_THREADS / 32; ++w) tile_last = max(tile_last, s_max[w]);
-    // After the butterfly, lanes with (lane & 3) == 0 own one of the 8 reduced sums
-    //   ridx 0 Sx, 1 Sy, 2 Sxx, 3 Sxy, 4 Syy, 5..7 colour;   lane 1 owns S.
-    // Destination rows have stride 3: mean2D.x/.y, conic.x/.y/.z, colour.r/.g/.b.
-    const int ridx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float *const gdst = ridx < 2 ? dL_dmean2D + ridx : (ridx < 5 ? dL_dconic + (ridx - 2) : dL_dcolor + (ridx - 5));
-    const float own_scale = ridx < 2 ? (ridx == 0 ? -0.5f * (float)W : -0.5f * (float)H) : (ridx < 5 ? -0.5f : 1.0f);
+
+    // Flush role of this lane: row = lane of the buffer = (slot, sum kind).  kind: 0 S, 1 Sx, 2 Sy, 3 Sxx, 4 Sxy, 5 Syy,
+    // 6..8 colour.  Destination rows have stride 3 (mean2D, conic, colour) or 1 (opacity).
+    const int f_slot = lane / 9, f_kind = lane - 9 * f_slot;
+    const float half_w = -0.5f * (float)W, half_h = -0.5f * (float)H;
+    int nbuf = 0;                                     // buffered visits (warp-uniform)
+
+    auto flush = [&]() {
+        __syncwarp();
+        if (lane < RB_ROWS && f_slot < nbuf) {
+            const float4 *row = reinterpret_cast<const float4 *>(buf + lane * RB_STRIDE);
+            float4 acc = row[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) { const float4 t = row[q]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+            const float sum = (acc.x + acc.y) + (acc.z + acc.w);
+            if (sum != 0.f) {
+                const uint32_t addr = a_rec + ((uint32_t)s_meta[warp][f_slot] << 6);
+                const float4 con = lds128(addr + 32);                      // A, B, C, 1/opacity
+                const uint32_t id = __float_as_uint(lds64(addr + 48).y);
+                if (f_kind == 0) atomicAdd(dL_dopacity + id, sum * con.w);
+                else if (f_kind == 1) { atomicAdd(dL_dmean2D + 3u * id, half_w * con.x * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * con.y * sum); }
+                else if (f_kind == 2) { atomicAdd(dL_dmean2D + 3u * id, half_w * con.y * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * con.z * sum); }
+                else if (f_kind < 6) atomicAdd(dL_dconic + 3u * id + (f_kind - 3), -0.5f * sum);
+                else atomicAdd(dL_dcolor + 3u * id + (f_kind - 6), sum);
+            }
+        }
+        __syncwarp();
+        nbuf = 0;
+    };
 
     // walk positions tile_last-1 .. 0 in batches, back to front; slot j holds position hi-1-j
     for (int hi = tile_last; hi > 0; hi -= BLEND_BATCH) {
         const int nb = min(BLEND_BATCH, hi);
-        __syncthreads();                        // every warp is done with the previous batch
+        __syncthreads();                        // every warp is done with the previous batch (and has flushed)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int j = h * BLEND_THREADS + (int)threadIdx.x;
@@ -315,17 +347,14 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const float e = p2 + k1.y;
                 const bool live = (hi - 1 - j) < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
                 if (!__any_sync(0xffffffffu, live)) continue;
-                const float2 bid = lds64(addr + 48);
-                float g[8], gS = 0.f;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) g[q] = 0.f;
+                float gS = 0.f, gx_ = 0.f, gy_ = 0.f, gxx = 0.f, gxy = 0.f, gyy = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f;
                 if (live) {
                     const float au = ex2_approx(e);            // o * G
                     const float alpha = fminf(0.99f, au);
                     const float rcp = rcp_approx(1.0f - alpha);         // 1 - alpha >= 0.01
                     T *= rcp;
                     const float dch = alpha * T;
-                    const float c0 = k1.z, c1 = k1.w, c2 = bid.x;
+                    const float c0 = k1.z, c1 = k1.w, c2 = lds64(addr + 48).x;
                     const float om = 1.f - last_alpha;
                     ar0 = fmaf(last_alpha, lc0, om * ar0); lc0 = c0;
                     ar1 = fmaf(last_alpha, lc1, om * ar1); lc1 = c1;
@@ -334,23 +363,21 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                     last_alpha = alpha;
                     dL_dalpha = fmaf(neg_Tf_bg, rcp, dL_dalpha);
                     gS = dL_dalpha * au;                       // D = dL/dG * G
-                    g[0] = gS * dx; g[1] = gS * dy;
-                    g[2] = g[0] * dx; g[3] = g[0] * dy; g[4] = g[1] * dy;
-                    g[5] = dch * dp0; g[6] = dch * dp1; g[7] = dch * dp2;
+                    gx_ = gS * dx; gy_ = gS * dy;
+                    gxx = gx_ * dx; gxy = gx_ * dy; gyy = gy_ * dy;
+                    gc0 = dch * dp0; gc1 = dch * dp1; gc2 = dch * dp2;
                 }
-                const float r8 = warp_reduce8(g, lane);
-                const float rS = warp_sum(gS);
-                const float other = __shfl_xor_sync(0xffffffffu, r8, 4);       // Sx <-> Sy for the two mean2D lanes
-                const float4 con = lds128(addr + 32);                          // A, B, C, 1/opacity
-                const uint32_t id = __float_as_uint(bid.y);
-                // owners of Sx / Sy combine them with the conic (cA own + cB other); every other owner has cA = 1, cB = 0
-                const float cA = ridx == 0 ? con.x : (ridx == 1 ? con.z : 1.0f);
-                const float cB = ridx < 2 ? con.y : 0.0f;
-                const float val = own_scale * fmaf(cA, r8, cB * other);
-                if ((lane & 3) == 0 && val != 0.f) atomicAdd(gdst + 3u * id, val);
-                if (lane == 1 && rS != 0.f) atomicAdd(dL_dopacity + id, rS * con.w);
+                // park the 9 partials of this visit in the warp's buffer (column = lane); the sums over the 32 lanes are
+                // taken row-wise, RB_SLOTS visits at a time, by flush()
+                float *col = buf + nbuf * 9 * RB_STRIDE + lane;
+                col[0 * RB_STRIDE] = gS; col[1 * RB_STRIDE] = gx_; col[2 * RB_STRIDE] = gy_;
+                col[3 * RB_STRIDE] = gxx; col[4 * RB_STRIDE] = gxy; col[5 * RB_STRIDE] = gyy;
+                col[6 * RB_STRIDE] = gc0; col[7 * RB_STRIDE] = gc1; col[8 * RB_STRIDE] = gc2;
+                if (lane == 0) s_meta[warp][nbuf] = j;
+                if (++nbuf == RB_SLOTS) flush();
             }
         }
+        if (nbuf) flush();                      // the records of this batch are about to be overwritten
     }
 }
 
@@ -390,7 +417,12 @@ extern "C" int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg
     ImgWs im = img_view(const_cast<void *>(image), H, W);
     BinWs b = bin_view(const_cast<void *>(binning), R);
     const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
-    blend_bwd_kernel<<<gx * gy, BLEND_THREADS, 0, (cudaStream_t)stream>>>(
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+        attr_set = true;
+    }
+    blend_bwd_kernel<<<gx * gy, BLEND_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
         im.ranges, b.vals[splatco_sorted_buffer_index(H, W)], reinterpret_cast<const float4 *>(geom), W, H, gx, bg,
         im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
     SPLATCO_CHECK_LAUNCH();
