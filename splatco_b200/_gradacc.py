@@ -26,9 +26,29 @@ _passes = {}          # device index -> {key: (flat buffer, offset in floats)}
 _ALIGN = 64           # floats (256 bytes): every carved buffer keeps the alignment of a fresh allocation
 
 
+_last = {}            # device index -> flat buffers of the most recent finished backward pass
+
+
 def _end_of_pass(index):
     with _lock:
-        _passes.pop(index, None)
+        table = _passes.pop(index, None)
+        if table is not None:
+            seen, flats = set(), []
+            for flat, _, _ in table.values():
+                if id(flat) not in seen:
+                    seen.add(id(flat))
+                    flats.append(flat)
+            _last[index] = flats
+
+
+def last_pass_buffers(device):
+    """Flat fp32 buffers that hold the shared gradients of the most recent backward pass on `device` (the
+    parameters' .grad are views of them).  Same sizes on every rank of a replicated model, so a multi-GPU caller
+    can all-reduce THEM in place instead of packing each .grad into a bucket (multiview.GradBucket)."""
+    device = torch.device(device)
+    index = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
+    with _lock:
+        return list(_last.get(index, ()))
 
 
 def acquire(device, requests, want_views=False):

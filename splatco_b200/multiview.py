@@ -64,11 +64,49 @@ class GradBucket:
             off += n
 
     def allreduce(self, group=None):
+        """Sum .grad over ranks.  Gradients that already live in the flat buffers of the last backward pass
+        (everything the decode / TriPlaneAttention kernels accumulate: anchors, planes, MLP weights -- see
+        _gradacc.py) are all-reduced IN PLACE, one collective per buffer and no copies; whatever else has a
+        gradient goes through the packed bucket."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        self.pack()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        self.unpack()
+        from . import _gradacc
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        flats = _gradacc.last_pass_buffers(dev) if dev.type == "cuda" else []
+        if dev.type == "cuda":
+            # every rank must issue the same collectives: agree on the buffer layout (a rank that rendered no view of
+            # this iteration has none), fall back to the packed bucket everywhere otherwise
+            sig = torch.tensor([len(flats), sum(f.numel() for f in flats)], dtype=torch.int64, device=dev)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+            if not torch.equal(lo, hi):
+                flats = []
+        owned = {f.untyped_storage().data_ptr() for f in flats}
+        rest = [p for p in self.params if p.grad is None or p.grad.untyped_storage().data_ptr() not in owned]
+        for f in flats:
+            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
+        if not flats:
+            self.pack()
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.unpack()
+        elif rest:
+            sizes = [p.numel() for p in rest]
+            small = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            off = 0
+            for p, n in zip(rest, sizes):
+                if p.grad is not None:
+                    small[off:off + n].copy_(p.grad.reshape(-1))
+                off += n
+            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
+            off = 0
+            for p, n in zip(rest, sizes):
+                seg = small[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = seg.clone()
+                else:
+                    p.grad.copy_(seg)
+                off += n
 
 
 def broadcast_last_view_stats(tensors: Iterable[torch.Tensor], num_views: int, group=None):

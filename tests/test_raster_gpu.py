@@ -237,3 +237,38 @@ def test_full_size_properties_c2():
     for k in ("means3D", "colors", "opacities", "scales", "rotations", "means2D"):
         want = (2.0 * b1[k] + b2[k]).cpu().numpy()
         assert rel_err(b3[k].cpu().numpy(), want) < 2e-3, k
+
+
+def test_large_image_binning_paths_agree():
+    """3840x2160 (32,400 tiles: the render-only sweep shape of BASELINE configs[4]) with 1.5 M Gaussians: the
+    tile-segmented binning and the literal radix composition must produce identical sorted keys, permutation and
+    ranges; the list must be sorted with stable ties and partition by tile."""
+    from splatco_b200 import _lib
+    from splatco_b200._lib import check, ptr
+    W, H, M = 3840, 2160, 1_500_000
+    cam, means, colors, opac, scales, rots = scene(M, W, H, 91, sigma_px=(0.5, 4.0))
+    color, radii, state, _ = gpu_forward(cam, means, colors, opac, scales, rots, [0.0, 0.0, 0.0])
+    g = unpack_state(state)
+    R = state.R
+    assert R == int(g["tiles"].astype(np.int64).sum()) and R > M
+    keys, pl = g["keys"], g["point_list"]
+    assert np.all(keys[1:] >= keys[:-1])
+    same = keys[1:] == keys[:-1]
+    assert np.all(pl[1:][same] > pl[:-1][same])
+    counts = np.bincount((keys >> np.uint64(32)).astype(np.int64), minlength=g["ranges"].shape[0])
+    assert np.array_equal(g["ranges"][:, 1] - g["ranges"][:, 0], counts)
+    L = _lib.lib()
+    binning = torch.zeros_like(state.binning)
+    image = torch.zeros_like(state.image)
+    check(L.splatco_binning_radix(state.P, R, H, W, ptr(state.radii_full), ptr(state.geom), ptr(binning), ptr(image),
+                                  torch.cuda.current_stream().cuda_stream), "splatco_binning_radix")
+    torch.cuda.synchronize()
+    bo = layout("binning", R)
+    sidx = L.splatco_sorted_buffer_index(H, W)
+    assert np.array_equal(chunk(binning, bo[0 + sidx], torch.int64, R).cpu().numpy().view(np.uint64), keys)
+    assert np.array_equal(chunk(binning, bo[2 + sidx], torch.int32, R).cpu().numpy().view(np.uint32), pl)
+    io = layout("image", H, W)
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    assert np.array_equal(chunk(image, io[0], torch.int32, 2 * T).view(T, 2).cpu().numpy(), g["ranges"])
+    img = color.cpu().numpy()
+    assert np.isfinite(img).all() and img.min() >= -1e-6 and img.max() <= 1.0 + 1e-5
