@@ -566,10 +566,14 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
 _noise_calls = 0
 
 
-def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, _raster_settings=None):
+def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, _raster_settings=None,
+                              _scaling=None):
     """Drop-in for gaussian_renderer.generate_neural_gaussians (reference :18-116).  `_raster_settings`
     is render()'s private hint: the GaussianRasterizationSettings it is about to rasterize the result
     with, which lets the decode queue the rasterizer's preprocess before its own row count is known."""
+    # the per-anchor inputs first (pc.get_scaling launches two kernels): collect_model ends by waiting for the
+    # prefilter's visible-anchor count, and everything queued before that wait overlaps with the GPU's backlog
+    scaling_in = _scaling if _scaling is not None else pc.get_scaling
     cfg, att, app_vec, params = collect_model(pc, viewpoint_camera, visible_mask)
     cfg.raster = _raster_settings
     # GaussianLearner.inference always passes Q = self.Q0 (0.03 while training, 0 in render.py):
@@ -583,7 +587,7 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
         _noise_calls += 1
         cfg.noise_q = Q
         cfg.noise_seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _noise_calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
-    outs = _FusedDecode.apply(cfg, pc._anchor_feat, pc.get_anchor, pc._offset, pc.get_scaling, att[0], att[1], att[2],
+    outs = _FusedDecode.apply(cfg, pc._anchor_feat, pc.get_anchor, pc._offset, scaling_in, att[0], att[1], att[2],
                               app_vec, *params)
     xyz, color, opacity, scaling, rot, neural_opacity, mask = outs
     if is_training:

@@ -10,6 +10,7 @@ plus the `GaussianModel` re-export render.py relies on (:16, render.py:34) when 
 from __future__ import annotations
 
 import math
+import weakref
 
 import torch
 
@@ -46,6 +47,26 @@ def _settings(viewpoint_camera, pipe, bg_color, scaling_modifier):
     )
 
 
+# prefilter_voxel and render() both read pc.get_scaling (= 1.0 * exp(pc._scaling), two launches plus two more in the
+# backward); when render() follows the prefilter of the same model state it reuses that tensor -- same values, same
+# autograd node -- instead of evaluating the accessor a second time.
+_scaling_stash = {"pc": None, "src": None, "version": -1, "grad": None, "value": None}
+
+
+def _get_scaling(pc, remember):
+    src = getattr(pc, "_scaling", None)
+    st = _scaling_stash
+    if (not remember and src is not None and st["value"] is not None and st["pc"] is not None and st["pc"]() is pc
+            and st["src"] is src and st["version"] == src._version and st["grad"] == torch.is_grad_enabled()):
+        value = st["value"]
+        st["value"] = None                      # single use: the next view's prefilter computes a fresh one
+        return value
+    value = pc.get_scaling
+    if remember and src is not None:
+        st.update(pc=weakref.ref(pc), src=src, version=src._version, grad=torch.is_grad_enabled(), value=value)
+    return value
+
+
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, visible_mask=None,
            retain_grad=False):
     """Render the scene.  Background tensor (bg_color) must be on GPU!"""
@@ -53,10 +74,12 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     settings = _settings(viewpoint_camera, pipe, bg_color, scaling_modifier)
     if is_training:
         xyz, color, opacity, scaling, rot, neural_opacity, mask = generate_neural_gaussians(
-            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings)
+            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings,
+            _scaling=_get_scaling(pc, remember=False))
     else:
         xyz, color, opacity, scaling, rot = generate_neural_gaussians(
-            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings)
+            viewpoint_camera, pc, visible_mask, is_training=is_training, _raster_settings=settings,
+            _scaling=_get_scaling(pc, remember=False))
 
     # zero tensor whose .grad receives the 2D (screen-space) mean gradients (reference :133-138)
     screenspace_points = torch.zeros_like(xyz, dtype=pc.get_anchor.dtype, requires_grad=True, device="cuda") + 0
@@ -97,7 +120,7 @@ def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_
         # the reference's branch is broken here (scales stays None and is then sliced, :233-240)
         cov3D_precomp = pc.get_covariance(scaling_modifier)
     else:
-        scales = pc.get_scaling
+        scales = _get_scaling(pc, remember=True)
         rotations = pc.get_rotation
     if cov3D_precomp is not None:
         radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales, rotations=rotations,

@@ -45,7 +45,7 @@ class _L1SSIM(torch.autograd.Function):
         L = _lib.lib()
         img, g, ws, lam, (C, H, W) = ctx.keep
         dev = img.device
-        gl = g_loss.detach().float().reshape(1).contiguous()
+        gl = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_contiguous()) else g_loss.detach().float().contiguous()
         with _lib.on_device(dev):
             dimg = torch.empty_like(img)
             with stage("l1_ssim_bwd"):
