@@ -28,7 +28,7 @@ constexpr int BLEND_BATCH = 2 * BLEND_THREADS;   // splats staged per barrier (t
                                                  // 256-splat batch, and the per-warp work imbalance averages out better
 constexpr int BLEND_WORDS = BLEND_BATCH / 32;    // 16 mask words per patch warp
 constexpr int RB_SLOTS = 3, RB_ROWS = 9 * RB_SLOTS, RB_STRIDE = 36;     // backward reduction buffer (see blend_bwd_kernel)
-constexpr size_t BWD_SMEM = (size_t)BLEND_BATCH * 64 + (size_t)(BLEND_THREADS / 32) * RB_ROWS * RB_STRIDE * sizeof(float);
+constexpr size_t BWD_SMEM = (size_t)BLEND_BATCH * 48 + (size_t)(BLEND_THREADS / 32) * RB_ROWS * RB_STRIDE * sizeof(float);
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLog2Inv255 = -7.994353436858858f;     // log2(1/255)
 
@@ -222,8 +222,9 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
     return v;
 }
 
-// Staged splat record of the backward: 64 bytes = 4 x float4
-//   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] conA, conB, conC, 1/opacity   [3] b, id(bits), 0, 0
+// Staged splat record of the backward: 48 bytes = 3 x float4  (the conic itself is recovered from its log2-domain
+// form at flush time: A = a2 * (-2 / log2 e), B = -b2 / log2 e, C = c2 * (-2 / log2 e))
+//   [0] sx, sy, a2, b2   [1] c2, log2(op), r, g   [2] b, id(bits), 1/opacity, 0
 //
 // Per (pixel, splat) pair the lanes only form the six moments of D = dL/dG * G about the splat centre
 // (D, D dx, D dy, D dx^2, D dx dy, D dy^2) and the three colour terms; D = dL/dalpha * ex2(e) because
@@ -243,8 +244,8 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     // gradient partials: RB_SLOTS buffered (warp, splat) visits x 9 sums x 32 lanes, rows padded to 36 floats so
     // that both the lane-wise stores and the row-wise 16-byte loads are bank-conflict free
     extern __shared__ float4 s_dyn4[];
-    float4 *const s_rec = s_dyn4;                                             // [BLEND_BATCH * 4]
-    float *const s_buf_all = reinterpret_cast<float *>(s_dyn4 + BLEND_BATCH * 4);   // [8][RB_ROWS * RB_STRIDE]
+    float4 *const s_rec = s_dyn4;                                             // [BLEND_BATCH * 3]
+    float *const s_buf_all = reinterpret_cast<float *>(s_dyn4 + BLEND_BATCH * 3);   // [8][RB_ROWS * RB_STRIDE]
     __shared__ uint32_t s_mask[8][BLEND_WORDS];
     __shared__ int s_max[BLEND_THREADS / 32];
     __shared__ int s_meta[BLEND_THREADS / 32][RB_SLOTS];
@@ -291,12 +292,17 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
             for (int q = 1; q < 8; ++q) { const float4 t = row[q]; acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
             const float sum = (acc.x + acc.y) + (acc.z + acc.w);
             if (sum != 0.f) {
-                const uint32_t addr = a_rec + ((uint32_t)s_meta[warp][f_slot] << 6);
-                const float4 con = lds128(addr + 32);                      // A, B, C, 1/opacity
-                const uint32_t id = __float_as_uint(lds64(addr + 48).y);
-                if (f_kind == 0) atomicAdd(dL_dopacity + id, sum * con.w);
-                else if (f_kind == 1) { atomicAdd(dL_dmean2D + 3u * id, half_w * con.x * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * con.y * sum); }
-                else if (f_kind == 2) { atomicAdd(dL_dmean2D + 3u * id, half_w * con.y * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * con.z * sum); }
+                const uint32_t addr = a_rec + (uint32_t)s_meta[warp][f_slot] * 48u;
+                const float4 q2 = lds128(addr + 32);                       // b, id, 1/opacity, -
+                const uint32_t id = __float_as_uint(q2.y);
+                if (f_kind == 0) atomicAdd(dL_dopacity + id, sum * q2.z);
+                else if (f_kind < 3) {
+                    const float4 q0 = lds128(addr);                        // sx, sy, a2, b2
+                    const float conA = q0.z * (-2.0f / kLog2e), conB = q0.w * (-1.0f / kLog2e);
+                    const float conC = lds128(addr + 16).x * (-2.0f / kLog2e);
+                    if (f_kind == 1) { atomicAdd(dL_dmean2D + 3u * id, half_w * conA * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * conB * sum); }
+                    else { atomicAdd(dL_dmean2D + 3u * id, half_w * conB * sum); atomicAdd(dL_dmean2D + 3u * id + 1, half_h * conC * sum); }
+                }
                 else if (f_kind < 6) atomicAdd(dL_dconic + 3u * id + (f_kind - 3), -0.5f * sum);
                 else atomicAdd(dL_dcolor + 3u * id + (f_kind - 6), sum);
             }
@@ -318,9 +324,8 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
                 const float sx = r0.x - cx, sy = r0.y - cy;
                 const SplatCoef sc = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
-                s_rec[4 * j] = sc.k0; s_rec[4 * j + 1] = sc.k1;
-                s_rec[4 * j + 2] = make_float4(r0.z, r0.w, r1.x, r1.y > 0.f ? 1.0f / r1.y : 0.f);
-                s_rec[4 * j + 3] = make_float4(r2.x, __uint_as_float(id), 0.f, 0.f);
+                s_rec[3 * j] = sc.k0; s_rec[3 * j + 1] = sc.k1;
+                s_rec[3 * j + 2] = make_float4(r2.x, __uint_as_float(id), r1.y > 0.f ? 1.0f / r1.y : 0.f, 0.f);
                 mask8 = sc.mask8;
             }
             publish_masks(mask8, s_mask, h * 8 + warp);
@@ -339,7 +344,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
             while (bits) {
                 const int j = lo + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const uint32_t addr = a_rec + ((uint32_t)j << 6);
+                const uint32_t addr = a_rec + (uint32_t)j * 48u;
                 const float4 k0 = lds128(addr);
                 const float4 k1 = lds128(addr + 16);
                 float dx, dy;
@@ -354,7 +359,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                     const float rcp = rcp_approx(1.0f - alpha);         // 1 - alpha >= 0.01
                     T *= rcp;
                     const float dch = alpha * T;
-                    const float c0 = k1.z, c1 = k1.w, c2 = lds64(addr + 48).x;
+                    const float c0 = k1.z, c1 = k1.w, c2 = lds64(addr + 32).x;
                     const float om = 1.f - last_alpha;
                     ar0 = fmaf(last_alpha, lc0, om * ar0); lc0 = c0;
                     ar1 = fmaf(last_alpha, lc1, om * ar1); lc1 = c1;
