@@ -94,3 +94,42 @@ def test_one_backward_over_summed_views_equals_sum_of_separate_backwards():
         assert (a - b).abs().max().item() <= 1e-4 * scale + 1e-9, (tuple(p.shape), (a - b).abs().max().item(), scale)
     for a, b in zip(vp, vp2):
         assert (a - b).abs().max().item() <= 1e-4 * max(b.abs().max().item(), 1e-12) + 1e-9
+
+
+def test_render_with_nothing_visible_returns_background():
+    """A camera looking away from the scene: the prefilter leaves no anchor (V = 0).  The reference would raise inside
+    BatchNorm; here render() returns the background image, empty per-Gaussian outputs, and backward is a no-op."""
+    import math
+    from splatco_b200.gaussian_renderer import prefilter_voxel, render
+    from splatco_b200.synthetic import look_at_camera
+    pc = _model(N=1500, seed=2)
+    W, H = 96, 64
+    cam = look_at_camera(0, (3.0, 0.0, 0.5), (6.0, 0.0, 0.5), W, H, 2.0 * math.atan(0.5 / 1.2)).to("cuda")   # scene is behind it
+    bg = torch.tensor([0.2, 0.4, 0.6], device="cuda")
+    vm = prefilter_voxel(cam, pc, PIPE, bg)
+    assert vm.dtype == torch.bool and int(vm.sum()) == 0
+    pkg = render(cam, pc, PIPE, bg, visible_mask=vm, retain_grad=True)
+    assert pkg["radii"].numel() == 0 and pkg["selection_mask"].numel() == 0 and pkg["neural_opacity"].numel() == 0
+    assert torch.allclose(pkg["render"], bg.view(3, 1, 1).expand(3, H, W))
+    loss = pkg["render"].mean() + pkg["scaling"].sum()
+    loss.backward()          # must not raise
+    for p in pc.parameters():
+        assert p.grad is None or float(p.grad.abs().max()) == 0.0
+
+
+def test_eval_mode_render_matches_training_forward():
+    """render.py path: MLP heads in eval mode, torch.no_grad(); feat_planes stays in train mode in the reference
+    (scene/gaussian_model.py:350-357), so the image must equal the training-mode forward."""
+    from splatco_b200.gaussian_renderer import prefilter_voxel, render
+    pc = _model(N=3000, seed=6)
+    cam = _cams(160, 112)[1]
+    bg = torch.zeros(3, device="cuda")
+    vm = prefilter_voxel(cam, pc, PIPE, bg)
+    img_train = render(cam, pc, PIPE, bg, visible_mask=vm)["render"].detach().clone()
+    pc.eval()
+    with torch.no_grad():
+        vm2 = prefilter_voxel(cam, pc, PIPE, bg)
+        pkg = render(cam, pc, PIPE, bg, visible_mask=vm2)
+    pc.train()
+    assert set(pkg) == {"render", "viewspace_points", "visibility_filter", "radii"}
+    assert torch.equal(pkg["render"], img_train)
