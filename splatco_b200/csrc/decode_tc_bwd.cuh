@@ -5,8 +5,9 @@
 //   3  dxhat[128, DP | 71] = dgeo_p * (gamma W)_planes | dgeo_c * (gamma W)_context
 // and, in the epilogues, the three column sums the parameter gradients need (gb2 = colsum dZ,
 // gb1 = colsum dH, S0 = colsum dgeo), reduced with a warp butterfly and added with fp32 REDs.
-// The reductions over anchors that produce weight gradients (H^T dZ, X100^T dH, dgeo^T X) stay in the
-// split-K SGEMM (decode.cu): their operands would have to be transposed through shared memory.
+// The reductions over anchors that produce weight gradients (H^T dZ, X100^T dH, dgeo^T X) run in
+// dec_wgrad_kernel below (each CTA keeps a whole output in registers); on tensor cores they need MN-major operand
+// tiles of both the forward and the backward activations, which do not fit next to this chain's operands.
 //
 // Shared memory map: A hi [0, 57344) 28 chunks | A lo [57344, 114688) | weights [114688, 200704)
 #pragma once
