@@ -50,6 +50,8 @@ WORKLOADS = {
                desc="C2 Tanks&Temples-shaped 100k anchors x10 offsets (~1M Gaussians), 980x545, mv=4"),
     "c3": dict(N=500_000, K=10, W=1152, H=864, mv=4, plane_size=2800, C=15,
                desc="C3 Mill19-Rubble-shaped 500k anchors x10 (~5M Gaussians), 1152x864, plane_size 2800, mv=4"),
+    "c4": dict(N=1_000_000, K=10, W=1920, H=1080, mv=1, plane_size=2800, C=15,
+               desc="C4 MatrixCity-Aerial-shaped 1M anchors x10 (~10M Gaussians), 1920x1080, one view per GPU (mv=8 over 8 GPUs)"),
 }
 SCALE_FACTOR = 0.5       # anchor scale = 0.5 / N^(1/3): projected sigma ~0.5-4 px at these resolutions
 LEVEL = 2                # activate_level in steady state (train.py:305-307)

@@ -98,7 +98,7 @@ __device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)
     if (lane < 8) s_mask[lane][word] = mine;
 }
 
-__global__ void __launch_bounds__(BLEND_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, 6)
 blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
                  float *__restrict__ out_color, float *__restrict__ final_T,
