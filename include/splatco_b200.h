@@ -252,6 +252,53 @@ int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const float *gt, 
 int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, const void *ws,
                         const float *grad_loss, float *dL_dimg, void *stream);
 
+/* ---- cross-view consistency term of the multi-view batch ----------------
+ * Replaces the pair loop of train.py:199-216 (+ align_images, train.py:79-96; summed in at train.py:237-239):
+ *   for i < j:  s = ssim(real_i, real_j);  loss_ij = s * |l1_loss(real_i - real_j, gen_i - gen_j)| if s > gate else 0
+ * The crop is per pair (align_images crops the pair's four images to their common top-left region).
+ * gen[i], real[i]: host arrays of n_views device pointers to contiguous [C, img_h[i], img_w[i]] fp32 images (a view's
+ * rendered and ground-truth image have the same size).  pair_ssim [n(n-1)/2] (device): ssim(real_i, real_j) on the pair's
+ * crop, in (0,1),(0,2),...,(n-2,n-1) order (splatco_l1_ssim_fwd with lambda 1 gives it).  fwd writes out[0] = sum_ij loss_ij
+ * and out[1 + p] = loss of pair p; bwd writes every view's full dL/dgen_i = *grad_loss * d out[0] / d gen_i. */
+#define SPLATCO_MVC_MAX_VIEWS 8
+size_t splatco_mv_consistency_ws_bytes(int n_views);
+int splatco_mv_consistency_fwd(int n_views, int C, const float *const *gen, const float *const *real, const int *img_h,
+                               const int *img_w, const float *pair_ssim, float ssim_gate, void *ws, float *out,
+                               void *stream);
+int splatco_mv_consistency_bwd(int n_views, int C, const float *const *gen, const float *const *real, float *const *dgen,
+                               const int *img_h, const int *img_w, const void *ws, const float *grad_loss, void *stream);
+
+/* ---- plane total-variation regulariser -----------------------------------------
+ * Replaces PlaneGrid.total_variation_add_grad (scene/grids.py:240-250; GaussianLearner.tv_loss,
+ * scene/gaussian_model.py:217-220; train.py:242-243) for ONE plane [C,H,W]:
+ *   grad += d/dplane [ w/6 * (smooth_l1(p[:,1:,:], p[:,:-1,:], sum) + smooth_l1(p[:,:,1:], p[:,:,:-1], sum)) ]
+ * (the reference's six terms are these two for each of the three planes).  grad is the plane's .grad, updated in place. */
+int splatco_tv_add_grad(int C, int H, int W, const float *plane, float *grad, float w, void *stream);
+
+/* ---- anchor growing -------------------------------------------------------------
+ * Replaces one pass of the loop of GaussianModel.anchor_growing (scene/gaussian_model.py:832-925).
+ * Offset slot t = anchor * K + k, t < n_stat (= rows of the statistics; anchors grown by an earlier pass have none).
+ * A slot is a candidate if cand_mask[t] (when cand_mask != NULL) or else if
+ *   grads[t] >= threshold && offset_mask[t] && rand[t] > rand_cut            (gaussian_model.py:839-846).
+ * Its position anchor + offset * scaling[:, :3] is rounded to the voxel grid of size cur_size (div_mode 0: multiply by
+ * the fp32 reciprocal like torch's CUDA `tensor / scalar`; 1: true division like torch's CPU kernel); voxels that already
+ * hold one of the N anchors are dropped; the new anchors are the remaining distinct voxels in torch.unique(dim=0)'s
+ * row order (x, y, z signed-lexicographic) times cur_size, and new_feat is the per-voxel channel-wise maximum of the
+ * candidates' anchor features (torch_scatter.scatter_max).  Three calls with two 4-byte read-backs in between:
+ *   splatco_grow_count  -> counts[0] = number of candidates                 (host reads it, allocates ws)
+ *   splatco_grow_unique -> counts[2] = number of new anchors                (host reads it, allocates outputs)
+ *   splatco_grow_emit   -> new_anchor [n_new,3], new_feat [n_new,F]
+ * counts: 4 x uint32 on the device.  scaling: activated (exp), row stride scale_stride floats. */
+size_t splatco_grow_ws_bytes(int64_t n_cand);
+int splatco_grow_count(int64_t n_stat, const uint8_t *cand_mask, const float *grads, float threshold,
+                       const uint8_t *offset_mask, const float *rand, float rand_cut, uint32_t *counts, void *stream);
+int splatco_grow_unique(int N, int K, int64_t n_stat, const float *anchors, const float *offsets, const float *scaling,
+                        int scale_stride, const uint8_t *cand_mask, const float *grads, float threshold,
+                        const uint8_t *offset_mask, const float *rand, float rand_cut, float cur_size, int div_mode,
+                        int64_t n_cand, void *ws, uint32_t *counts, void *stream);
+int splatco_grow_emit(int K, int F, float cur_size, int64_t n_cand, int64_t n_new, void *ws, const float *anchor_feat,
+                      float *new_anchor, float *new_feat, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:
  * C[M,N] = A[M,K] * B[N,K]^T (row-major fp32, N <= 112, K <= 136).  variant bit0: swapped LBO/SBO

@@ -57,6 +57,14 @@ SIGNATURES = {
     "splatco_loss_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_l1_ssim_fwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "splatco_l1_ssim_bwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "splatco_mv_consistency_ws_bytes": (_sz, [_i]),
+    "splatco_mv_consistency_fwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "splatco_mv_consistency_bwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_tv_add_grad": (_i, [_i, _i, _i, _vp, _vp, _f, _vp]),
+    "splatco_grow_ws_bytes": (_sz, [_i64]),
+    "splatco_grow_count": (_i, [_i64, _vp, _vp, _f, _vp, _vp, _f, _vp, _vp]),
+    "splatco_grow_unique": (_i, [_i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i64, _vp, _vp, _vp]),
+    "splatco_grow_emit": (_i, [_i, _i, _f, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "splatco_training_statis": (_i, [_i, _i] + [_vp] * 11),
     "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }

@@ -603,31 +603,38 @@ extern "C" int splatco_duplicate_with_keys(int P, int64_t R, int H, int W, const
     return 0;
 }
 
+// Stable LSD radix sort of (64-bit key, 32-bit value) pairs on key bits [0, bits): 8-bit digits, ping-pong between the
+// two key/value buffers of a binning workspace.  Returns the index of the buffer holding the result in *cur.
+// Shared with the densification path (csrc/densify.cu), which sorts voxel coordinates with it.
+int splatco::radix_sort_pairs(const BinWs &b, uint32_t n, int bits, int *cur_io, cudaStream_t st) {
+    const int passes = (bits + 7) / 8;
+    const int nblocks = (int)ceil_div64((int64_t)n, SORT_TILE);
+    int cur = *cur_io;
+    for (int p = 0; p < passes && n > 0; ++p) {
+        const int shift = 8 * p;
+        const int nb = bits - shift < 8 ? bits - shift : 8;
+        const uint32_t mask = (1u << nb) - 1u;
+        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(b.keys[cur], n, shift, mask, b.hist, nblocks);
+        SPLATCO_CHECK_LAUNCH();
+        sort_scan_kernel<<<256, 256, 0, st>>>(b.hist, nblocks, b.bin_totals);
+        SPLATCO_CHECK_LAUNCH();
+        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1],
+                                                              n, shift, mask, b.hist, nblocks, b.bin_totals);
+        SPLATCO_CHECK_LAUNCH();
+        cur ^= 1;
+    }
+    *cur_io = cur;
+    return 0;
+}
+
 extern "C" int splatco_sort_pairs(int64_t R, int H, int W, void *binning, void *stream) {
     if (check_R(R)) return -1;
     if (R == 0) return 0;
     SPLATCO_REQUIRE(binning, "sort_pairs: null pointer");
     BinWs b = bin_view(binning, R);
-    cudaStream_t st = (cudaStream_t)stream;
     const int T = ceil_div(W, TILE) * ceil_div(H, TILE);
-    const int bits = 32 + tile_bits(T);
-    const int passes = (bits + 7) / 8;
-    const int nblocks = (int)ceil_div64(R, SORT_TILE);
     int cur = 0;
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        const int nb = bits - shift < 8 ? bits - shift : 8;
-        const uint32_t mask = (1u << nb) - 1u;
-        sort_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(b.keys[cur], (uint32_t)R, shift, mask, b.hist, nblocks);
-        SPLATCO_CHECK_LAUNCH();
-        sort_scan_kernel<<<256, 256, 0, st>>>(b.hist, nblocks, b.bin_totals);
-        SPLATCO_CHECK_LAUNCH();
-        sort_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(b.keys[cur], b.vals[cur], b.keys[cur ^ 1], b.vals[cur ^ 1],
-                                                              (uint32_t)R, shift, mask, b.hist, nblocks, b.bin_totals);
-        SPLATCO_CHECK_LAUNCH();
-        cur ^= 1;
-    }
-    return 0;
+    return radix_sort_pairs(b, (uint32_t)R, 32 + tile_bits(T), &cur, (cudaStream_t)stream);
 }
 
 extern "C" int splatco_sorted_buffer_index(int H, int W) { return sort_passes(H, W) & 1; }

@@ -73,6 +73,7 @@ size_t img_offsets(int H, int W, size_t off[9]);
 GeomWs geom_view(void *base, int P);
 BinWs bin_view(void *base, int64_t R);
 ImgWs img_view(void *base, int H, int W);
+int radix_sort_pairs(const BinWs &b, uint32_t n, int bits, int *cur_io, cudaStream_t st);   // csrc/binning.cu
 
 inline int tile_bits(int T) { int b = 1; while ((1 << b) < T) ++b; return b; }   // bits to hold T-1
 inline int sort_passes(int H, int W) {

@@ -151,6 +151,129 @@ l1_ssim_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
     dimg[o] = __ldg(g_loss) * (c_l1 * sgn - c_ssim * dssim);
 }
 
+
+// ---- cross-view consistency term of the mv batch (train.py:199-216,237-239) ------------------------------------
+// For every pair i < j of the iteration's views the reference evaluates, after cropping the pair's four images to their
+// common size (align_images, train.py:79-96),
+//     s = ssim(real_i, real_j);   loss_ij = s * | l1_loss(real_i - real_j, gen_i - gen_j) |   if s > 0.6 else 0
+// and adds 0.05 * sum_ij loss_ij to the summed loss: per pair 2 SSIMs (10 grouped convolutions), 3 elementwise passes
+// and a host sync for the `if`.  Here one pass over the mv generated + mv real images forms all mv(mv-1)/2 sums
+// (2 mv loads per pixel instead of 4 per pair), the gate is applied on the device, and the backward writes every
+// view's dL/dgen in one pass.  s only depends on the ground-truth images; the caller supplies it (splatco_l1_ssim_fwd).
+// A pixel belongs to pair (i, j) when it lies inside both images, i.e. inside the pair's crop.
+constexpr int MVC_MAX = SPLATCO_MVC_MAX_VIEWS, MVC_PAIRS = MVC_MAX * (MVC_MAX - 1) / 2;
+
+struct MvcViews {
+    const float *gen[MVC_MAX], *real[MVC_MAX];
+    float *dgen[MVC_MAX];
+    int h[MVC_MAX], w[MVC_MAX];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+mvc_fwd_kernel(int H, int W, int64_t total, MvcViews v, double *__restrict__ sums) {
+    constexpr int NP = NV * (NV - 1) / 2;
+    float acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] = 0.f;
+    const int64_t hw = (int64_t)H * W;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t c = e / hw, r = e - c * hw;
+        const int y = (int)(r / W), x = (int)(r - (int64_t)y * W);
+        float g[NV], t[NV];
+        bool in[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            in[i] = y < v.h[i] && x < v.w[i];
+            const int64_t o = (c * v.h[i] + y) * (int64_t)v.w[i] + x;
+            g[i] = in[i] ? __ldg(v.gen[i] + o) : 0.f; t[i] = in[i] ? __ldg(v.real[i] + o) : 0.f;
+        }
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = i + 1; j < NV; ++j, ++p)
+                if (in[i] && in[j]) acc[p] += fabsf((t[i] - t[j]) - (g[i] - g[j]));
+    }
+    __shared__ float s_red[8][NP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        float a = acc[p];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+        if (lane == 0) s_red[warp][p] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < NP) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += (double)s_red[w][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, a);
+    }
+}
+
+struct MvcCounts { double n[MVC_PAIRS]; };
+
+// w_p = s_p if s_p > gate else 0;  out[1+p] = w_p * mean_p,  out[0] = their sum;  weights[p] = w_p / count_p (backward)
+__global__ void mvc_finish_kernel(int NP, const double *__restrict__ sums, const float *__restrict__ pair_ssim, float gate, MvcCounts cnt,
+                                  float *__restrict__ weights, float *__restrict__ out) {
+    float tot = 0.f;
+    for (int p = 0; p < NP; ++p) {
+        const float s = pair_ssim[p];
+        const float w = s > gate ? s : 0.f;
+        const float l = w * (float)(sums[p] / cnt.n[p]);
+        weights[p] = (float)((double)w / cnt.n[p]); out[1 + p] = l; tot += l;
+    }
+    out[0] = tot;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+mvc_bwd_kernel(int H, int W, int64_t total, MvcViews v, const float *__restrict__ weights, const float *__restrict__ g_loss) {
+    constexpr int NP = NV * (NV - 1) / 2;
+    const int64_t hw = (int64_t)H * W;
+    const float gl = __ldg(g_loss);
+    float wp[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) wp[p] = __ldg(weights + p);
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t c = e / hw, r = e - c * hw;
+        const int y = (int)(r / W), x = (int)(r - (int64_t)y * W);
+        float g[NV], t[NV], d[NV];
+        int64_t o[NV];
+        bool in[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            in[i] = y < v.h[i] && x < v.w[i];
+            o[i] = (c * v.h[i] + y) * (int64_t)v.w[i] + x;
+            g[i] = in[i] ? __ldg(v.gen[i] + o[i]) : 0.f; t[i] = in[i] ? __ldg(v.real[i] + o[i]) : 0.f; d[i] = 0.f;
+        }
+        int p = 0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = i + 1; j < NV; ++j, ++p) {
+                const float e_ij = (t[i] - t[j]) - (g[i] - g[j]);
+                const float sg = (in[i] && in[j]) ? (e_ij > 0.f ? 1.f : (e_ij < 0.f ? -1.f : 0.f)) : 0.f;
+                const float w = wp[p] * sg;
+                d[i] -= w; d[j] += w;
+            }
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (in[i]) v.dgen[i][o[i]] = gl * d[i];
+    }
+}
+
+template <int NV> struct MvcLaunch {
+    static void fwd(int grid, cudaStream_t st, int H, int W, int64_t total, const MvcViews &v, double *sums) {
+        mvc_fwd_kernel<NV><<<grid, 256, 0, st>>>(H, W, total, v, sums);
+    }
+    static void bwd(int grid, cudaStream_t st, int H, int W, int64_t total, const MvcViews &v, const float *weights, const float *g) {
+        mvc_bwd_kernel<NV><<<grid, 256, 0, st>>>(H, W, total, v, weights, g);
+    }
+};
+
 }  // namespace splatco
 
 using namespace splatco;
@@ -194,6 +317,93 @@ extern "C" int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const 
     l1_ssim_bwd_kernel<<<grid, LS_T * LS_T, 0, (cudaStream_t)stream>>>(H, W, img, gt, win, (const float *)b, (const float *)(b + map),
                                                                       (const float *)(b + 2 * map), grad_loss,
                                                                       (1.f - lambda_dssim) / count, lambda_dssim / count, dL_dimg);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+static int mvc_fill(int n_views, int C, const float *const *gen, const float *const *real, float *const *dgen,
+                    const int *img_h, const int *img_w, MvcViews *v, int *Hmax, int *Wmax) {
+    SPLATCO_REQUIRE(n_views >= 2 && n_views <= MVC_MAX, "mv_consistency: 2..%d views supported, got %d", MVC_MAX, n_views);
+    SPLATCO_REQUIRE(C >= 1, "mv_consistency: bad channel count %d", C);
+    SPLATCO_REQUIRE(gen && real && img_h && img_w, "mv_consistency: null pointer");
+    memset(v, 0, sizeof(*v));
+    *Hmax = *Wmax = 0;
+    for (int i = 0; i < n_views; ++i) {
+        SPLATCO_REQUIRE(gen[i] && real[i] && (!dgen || dgen[i]), "mv_consistency: null image pointer (view %d)", i);
+        SPLATCO_REQUIRE(img_h[i] >= 1 && img_w[i] >= 1, "mv_consistency: view %d has size %dx%d", i, img_h[i], img_w[i]);
+        v->gen[i] = gen[i]; v->real[i] = real[i]; v->dgen[i] = dgen ? dgen[i] : nullptr;
+        v->h[i] = img_h[i]; v->w[i] = img_w[i];
+        if (img_h[i] > *Hmax) *Hmax = img_h[i];
+        if (img_w[i] > *Wmax) *Wmax = img_w[i];
+    }
+    return 0;
+}
+
+static int mvc_grid(int64_t total) {
+    const int64_t want = (total + 256 * 4 - 1) / (256 * 4);      // ~4 pixels per thread
+    const int64_t cap = 148 * 8;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+extern "C" size_t splatco_mv_consistency_ws_bytes(int n_views) {
+    const size_t np = (size_t)n_views * (n_views - 1) / 2;
+    return align_up(np * sizeof(double)) + align_up(np * sizeof(float));
+}
+
+extern "C" int splatco_mv_consistency_fwd(int n_views, int C, const float *const *gen, const float *const *real, const int *img_h,
+                                          const int *img_w, const float *pair_ssim, float ssim_gate, void *ws, float *out,
+                                          void *stream) {
+    MvcViews v;
+    int H, W;
+    if (mvc_fill(n_views, C, gen, real, nullptr, img_h, img_w, &v, &H, &W)) return -1;
+    SPLATCO_REQUIRE(pair_ssim && ws && out, "mv_consistency_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = n_views * (n_views - 1) / 2;
+    double *sums = (double *)ws;
+    float *weights = (float *)((char *)ws + align_up(np * sizeof(double)));
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, np * sizeof(double), st));
+    MvcCounts cnt;
+    for (int i = 0, p = 0; i < n_views; ++i)
+        for (int j = i + 1; j < n_views; ++j, ++p)
+            cnt.n[p] = (double)C * (img_h[i] < img_h[j] ? img_h[i] : img_h[j]) * (img_w[i] < img_w[j] ? img_w[i] : img_w[j]);
+    const int64_t total = (int64_t)C * H * W;
+    const int grid = mvc_grid(total);
+    switch (n_views) {
+        case 2: MvcLaunch<2>::fwd(grid, st, H, W, total, v, sums); break;
+        case 3: MvcLaunch<3>::fwd(grid, st, H, W, total, v, sums); break;
+        case 4: MvcLaunch<4>::fwd(grid, st, H, W, total, v, sums); break;
+        case 5: MvcLaunch<5>::fwd(grid, st, H, W, total, v, sums); break;
+        case 6: MvcLaunch<6>::fwd(grid, st, H, W, total, v, sums); break;
+        case 7: MvcLaunch<7>::fwd(grid, st, H, W, total, v, sums); break;
+        default: MvcLaunch<8>::fwd(grid, st, H, W, total, v, sums); break;
+    }
+    SPLATCO_CHECK_LAUNCH();
+    mvc_finish_kernel<<<1, 1, 0, st>>>(np, sums, pair_ssim, ssim_gate, cnt, weights, out);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_mv_consistency_bwd(int n_views, int C, const float *const *gen, const float *const *real, float *const *dgen,
+                                          const int *img_h, const int *img_w, const void *ws, const float *grad_loss, void *stream) {
+    MvcViews v;
+    int H, W;
+    SPLATCO_REQUIRE(dgen, "mv_consistency_bwd: null pointer");
+    if (mvc_fill(n_views, C, gen, real, dgen, img_h, img_w, &v, &H, &W)) return -1;
+    SPLATCO_REQUIRE(ws && grad_loss, "mv_consistency_bwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int np = n_views * (n_views - 1) / 2;
+    const float *weights = (const float *)((const char *)ws + align_up(np * sizeof(double)));
+    const int64_t total = (int64_t)C * H * W;
+    const int grid = mvc_grid(total);
+    switch (n_views) {
+        case 2: MvcLaunch<2>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        case 3: MvcLaunch<3>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        case 4: MvcLaunch<4>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        case 5: MvcLaunch<5>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        case 6: MvcLaunch<6>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        case 7: MvcLaunch<7>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+        default: MvcLaunch<8>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
+    }
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

@@ -73,3 +73,87 @@ def ssim(img1, img2, window_size=11, size_average=True):
     if window_size != 11 or not size_average:
         raise NotImplementedError("splatco_b200 ssim: window_size=11, size_average=True only")
     return 1.0 - l1_ssim_loss(img1, img2, 1.0)
+
+
+# ---- cross-view consistency term of the mv batch (train.py:199-216, summed in at :237-239) ----------------------
+import ctypes as _C
+
+
+def _pair_list(n):
+    return [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def pair_ssim(real_imgs):
+    """ssim(real_i, real_j) of every pair i < j on the pair's common crop (align_images, train.py:79-96), as a device
+    tensor [n(n-1)/2] (no host sync).  It depends on the ground-truth images only, so a caller that keeps its cameras
+    can cache it per camera pair."""
+    vals = []
+    with torch.no_grad():
+        for i, j in _pair_list(len(real_imgs)):
+            H = min(int(real_imgs[i].shape[1]), int(real_imgs[j].shape[1]))
+            W = min(int(real_imgs[i].shape[2]), int(real_imgs[j].shape[2]))
+            vals.append(l1_ssim_loss(real_imgs[i][:, :H, :W], real_imgs[j][:, :H, :W], 1.0, return_parts=True)[1][2:3])
+    return torch.cat(vals)
+
+
+class _MVConsistency(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, pssim, n, *imgs):
+        L = _lib.lib()
+        gen, real = imgs[:n], imgs[n:]
+        dev = gen[0].device
+        for t in imgs:
+            if not t.is_cuda or t.dim() != 3 or t.shape[0] != gen[0].shape[0]:
+                raise RuntimeError("splatco_b200 multiview_consistency_loss needs [C,H,W] CUDA images (no CPU fallback)")
+        gen_c = [t.detach().float().contiguous() for t in gen]
+        real_c = [t.detach().float().contiguous() for t in real]
+        C = int(gen_c[0].shape[0])
+        for g_, r_ in zip(gen_c, real_c):
+            if g_.shape != r_.shape:
+                raise RuntimeError("multiview_consistency_loss: a view's rendered and ground-truth images differ in size")
+        PA = _C.c_void_p * n
+        IA = _C.c_int * n
+        views = dict(gen=PA(*[t.data_ptr() for t in gen_c]), real=PA(*[t.data_ptr() for t in real_c]),
+                     h=IA(*[int(t.shape[1]) for t in gen_c]), w=IA(*[int(t.shape[2]) for t in gen_c]))
+        with _lib.on_device(dev):
+            ws = torch.empty(L.splatco_mv_consistency_ws_bytes(n), dtype=torch.uint8, device=dev)
+            out = torch.empty(1 + n * (n - 1) // 2, dtype=torch.float32, device=dev)
+            ps = pssim.detach().float().contiguous()
+            with stage("mv_consistency_fwd"):
+                check(L.splatco_mv_consistency_fwd(n, C, views["gen"], views["real"], views["h"], views["w"], ptr(ps),
+                                                   float(gate), ptr(ws), ptr(out), _lib.raw_stream(dev)), "splatco_mv_consistency_fwd")
+        ctx.keep = (gen_c, real_c, views, ws, n, C)
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_parts):
+        L = _lib.lib()
+        gen_c, real_c, views, ws, n, C = ctx.keep
+        dev = gen_c[0].device
+        gl = g_loss if (g_loss.dtype == torch.float32 and g_loss.is_contiguous()) else g_loss.detach().float().contiguous()
+        with _lib.on_device(dev):
+            dgen = [torch.empty_like(t) for t in gen_c]
+            DA = (_C.c_void_p * n)(*[t.data_ptr() for t in dgen])
+            with stage("mv_consistency_bwd"):
+                check(L.splatco_mv_consistency_bwd(n, C, views["gen"], views["real"], DA, views["h"], views["w"], ptr(ws),
+                                                   ptr(gl), _lib.raw_stream(dev)), "splatco_mv_consistency_bwd")
+        return (None, None, None) + tuple(dgen) + (None,) * n
+
+
+def multiview_consistency_loss(gen_imgs, real_imgs, ssim_threshold=0.6, pair_ssim_values=None, return_parts=False):
+    """`muiti_con_loss` of train.py:199-236 (without the CVPM pruning call inside that loop): the sum over view pairs
+    i < j of  ssim(real_i, real_j) * |l1_loss(real_i - real_j, gen_i - gen_j)|  for pairs whose ground-truth SSIM
+    exceeds `ssim_threshold`, each pair on its common crop.  train.py adds 0.05 * this to the summed loss.
+    Gradients flow to the generated images only.  2 <= len(gen_imgs) <= 8."""
+    n = len(gen_imgs)
+    if n != len(real_imgs):
+        raise RuntimeError("multiview_consistency_loss: need as many ground-truth as generated images")
+    if n < 2:
+        z = gen_imgs[0].new_zeros(())
+        return (z, z.reshape(1)) if return_parts else z
+    if n > 8:
+        raise NotImplementedError("splatco_b200 multiview_consistency_loss: at most 8 views per batch")
+    ps = pair_ssim(real_imgs) if pair_ssim_values is None else pair_ssim_values
+    loss, parts = _MVConsistency.apply(float(ssim_threshold), ps, n, *gen_imgs, *real_imgs)
+    return (loss, parts) if return_parts else loss
