@@ -206,13 +206,16 @@ def run_ours(args):
         return float(total.item()) if host_inputs else total
 
     def timed(n, host_inputs):
+        return _timed_fn(step, n, host_inputs)
+
+    def _timed_fn(fn, n, host_inputs):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
-            step(host_inputs)
+            fn(host_inputs)
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -240,6 +243,20 @@ def run_ours(args):
     with profiling.collect() as prof:
         ms_stage = timed(args.steps, host_inputs=False)
     stage_sum = prof.summary()
+    # whole training iteration (BASELINE metric "train it/s"): the same step + the optimizer update the reference performs
+    # at train.py:310-312 (Adam over every parameter group, eps 1e-15, scene/gaussian_model.py:519-572), fused
+    from splatco_b200.optim import FusedAdam
+    opt = FusedAdam([{"params": [p], "lr": 1e-6, "name": f"p{i}"} for i, p in enumerate(params) if p.requires_grad], lr=0.0, eps=1e-15)
+
+    def train_iter(host_inputs):
+        loss = step(host_inputs)
+        opt.step()
+        return loss
+    for _ in range(2):
+        train_iter(False)
+    launches_t0 = L.splatco_launch_count()
+    ms_train = _timed_fn(train_iter, args.steps, True)
+    launches_train = L.splatco_launch_count() - launches_t0
 
     views = mv * world
     ms_step = ms_dev / args.steps
@@ -319,6 +336,10 @@ def run_ours(args):
         "e2e": {"value": round((ms_e2e / args.steps) / views, 4), "unit": "ms/view",
                 "h2d_bytes_per_step": int(mv * 3 * HW * 4), "d2h_bytes_per_step": 4 + 8 * mv},
         "gpu_launches": int(launches),
+        "train": {"it_per_s": round(1000.0 * args.steps / ms_train, 3), "ms_per_iter": round(ms_train / args.steps, 4),
+                  "gpu_launches": int(launches_train),
+                  "includes": "the e2e step (H2D ground truth, mv views fwd+bwd, loss read-back" + (", NCCL grad all-reduce" if world > 1 else "") +
+                              ") + FusedAdam update of every parameter (train.py:310-312), lr 1e-6"},
         "roofline": roof, "decode_mlp": mlp, "stages": stages, "clocks": clocks,
     }
     if bucket is not None:

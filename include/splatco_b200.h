@@ -299,6 +299,34 @@ int splatco_grow_unique(int N, int K, int64_t n_stat, const float *anchors, cons
 int splatco_grow_emit(int K, int F, float cur_size, int64_t n_cand, int64_t n_new, void *ws, const float *anchor_feat,
                       float *new_anchor, float *new_feat, void *stream);
 
+/* ---- CVPM pruning mask ---------------------------------------------------------
+ * Replaces the point-cloud half of GaussianModel.compute_fast_loss_with_key_points (scene/gaussian_model.py:1163-1165,
+ * 1178-1216; train.py:218-234): mask[i] = anchor i lies within distance_threshold of the line through t1 and t2 AND
+ * (is closer than min_cam_distance to t1 or t2, OR is a sigma_threshold-sigma outlier of the cloud on some axis).
+ * points [N,3]; t1, t2: 3 floats each and ssim: 1 float (ssim(real_1, real_2); NULL = no gate), all on the DEVICE —
+ * the mask is all-false when *ssim < ssim_threshold, without a host sync.  mask [N] uint8, count [1] = its sum. */
+size_t splatco_cvpm_ws_bytes(void);
+int splatco_cvpm_mask(int N, const float *points, const float *t1, const float *t2, const float *ssim,
+                      float ssim_threshold, float distance_threshold, float sigma_threshold, float min_cam_distance,
+                      void *ws, uint8_t *mask, int32_t *count, void *stream);
+
+/* ---- fused multi-tensor Adam step ------------------------------------------------
+ * Replaces `gaussians.optimizer.step()` (train.py:310-312; optimizer of scene/gaussian_model.py:519-572:
+ * torch.optim.Adam, eps 1e-15, betas (0.9, 0.999), no weight decay / amsgrad, per-group lr) for fp32 tensors:
+ *   m += (g - m)(1 - beta1);  v = v beta2 + (1 - beta2) g^2;  p -= lr / (1 - beta1^step) * m / (sqrt(v) / sqrt(1 - beta2^step) + eps)
+ * `tensors` is a HOST array; step is the value AFTER this update's increment (>= 1).  One pass, up to 64 tensors per launch. */
+typedef struct splatco_adam_tensor {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    int64_t numel;
+    int64_t step;
+    float lr;
+    float reserved;
+} splatco_adam_tensor;
+int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, float beta1, float beta2, float eps, void *stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:
  * C[M,N] = A[M,K] * B[N,K]^T (row-major fp32, N <= 112, K <= 136).  variant bit0: swapped LBO/SBO

@@ -136,3 +136,32 @@ def anchor_growing(anchor, offset, log_scaling, anchor_feat, grads, threshold, o
         log_scaling = np.concatenate([log_scaling, np.log(np.full((U, 6), cur_size, np.float32))])
         anchor_feat = np.concatenate([anchor_feat, new_feat])
     return anchor, offset, log_scaling, anchor_feat, added
+
+
+# ---- CVPM pruning mask ----------------------------------------------------------------------------------------------
+def cvpm_mask(points, t1, t2, ssim_value=None, distance_threshold=0.01, overall_ssim_threshold=0.6, sigma_threshold=3.0,
+              min_cam_distance=0.5):
+    """scene/gaussian_model.py:1163-1165,1178-1210 in fp32 numpy (same operation order as the reference's torch ops)."""
+    P = points.astype(np.float32)
+    N = P.shape[0]
+    if ssim_value is not None and ssim_value < overall_ssim_threshold:
+        return np.zeros(N, bool)
+    f = np.float32
+    c1, c2 = t1.astype(f).reshape(3), t2.astype(f).reshape(3)
+    d1 = c2 - c1
+    d2 = c1 - c2
+    d1 = d1 / np.sqrt((d1 * d1).sum(dtype=f))
+    d2 = d2 / np.sqrt((d2 * d2).sum(dtype=f))
+
+    def line_dist(c, d):
+        dots = ((P - c) @ d.reshape(3, 1)).astype(f)
+        proj = c + d * dots
+        return np.sqrt(((P - proj) ** 2).sum(axis=1, dtype=f))
+
+    valid = (line_dist(c1, d1) < f(distance_threshold)) & (line_dist(c2, d2) < f(distance_threshold))
+    cam = lambda c: np.sqrt(((P - c) ** 2).sum(axis=1, dtype=f))
+    close = (cam(c1) < f(min_cam_distance)) | (cam(c2) < f(min_cam_distance))
+    mean = P.astype(np.float64).mean(axis=0).astype(f)
+    std = P.astype(np.float64).std(axis=0, ddof=1).astype(f) if N > 1 else np.full(3, np.nan, f)
+    outlier = ~np.all(np.abs(P - mean) < f(sigma_threshold) * std, axis=1)
+    return valid & (close | outlier)

@@ -193,9 +193,39 @@ def grow_fixtures(gm, out):
         print(f"grow case {case}: N {N} -> grown {out[f'grow.c{case}.grown._anchor'].shape[0]} -> adjusted {me._anchor.shape[0]}")
 
 
+def cvpm_fixtures(gm, out):
+    """GaussianModel.compute_fast_loss_with_key_points (:1112-1219), unmodified (it never touches self), device='cpu'."""
+    g = torch.Generator().manual_seed(61)
+    t1, t2 = torch.tensor([-1.5, 0.2, 0.1]), torch.tensor([1.2, -0.3, 0.4])
+    d = (t2 - t1) / (t2 - t1).norm()
+    N = 30000
+    cloud = torch.rand(N, 3, generator=g) * 4 - 2
+    s = torch.rand(4000, 1, generator=g) * 16 - 8                       # along the line, far beyond both cameras (3-sigma outliers)
+    cloud[:4000] = t1 + d * s + torch.randn(4000, 3, generator=g) * 0.03
+    cloud[4000:4500] = (t1 if True else t2) + torch.randn(500, 3, generator=g) * 0.2
+    cloud[4500:5000] = t2 + torch.randn(500, 3, generator=g) * 0.2
+    base = torch.rand(3, 40, 52, generator=g)
+    real1 = (base + 0.03 * torch.randn(3, 40, 52, generator=g)).clamp(0, 1)
+    real2 = (base[:, :38, :50] + 0.03 * torch.randn(3, 38, 50, generator=g)).clamp(0, 1)
+    other = torch.rand(3, 38, 50, generator=g)
+    gen1, gen2 = (real1 + 0.1 * torch.randn(3, 40, 52, generator=g)).clamp(0, 1), (real2 + 0.1 * torch.randn(3, 38, 50, generator=g)).clamp(0, 1)
+    K = R = torch.eye(3)
+    out.update({"cvpm.cloud": cloud.numpy(), "cvpm.t1": t1.numpy(), "cvpm.t2": t2.numpy(), "cvpm.real1": real1.numpy(), "cvpm.real2": real2.numpy(),
+                "cvpm.other": other.numpy(), "cvpm.gen1": gen1.numpy(), "cvpm.gen2": gen2.numpy()})
+    for name, r2, thr in (("open", real2, 0.05), ("tight", real2, 0.004), ("gated", other, 0.05)):
+        a, b, pts, mask = gm.GaussianModel.compute_fast_loss_with_key_points(None, real1, r2, gen1, gen2, K, R, t1.clone(), K, R, t2.clone(), cloud,
+                                                                             distance_threshold=thr, overall_ssim_threshold=0.6, device="cpu")
+        out[f"cvpm.{name}.thr"] = thr
+        out[f"cvpm.{name}.gen_l1"], out[f"cvpm.{name}.cross_l1"] = float(a), float(b)
+        out[f"cvpm.{name}.mask"] = np.packbits(mask.numpy())
+        out[f"cvpm.{name}.n_points"] = int(pts.shape[0])
+        print(f"cvpm {name}: mask.sum() = {int(mask.sum())}, losses {float(a):.6f} {float(b):.6f}")
+
+
 def main():
     _, gm = import_reference()
     out = {}
+    cvpm_fixtures(gm, out)
     tv_fixtures(gm, out)
     mvc_fixtures(out)
     grow_fixtures(gm, out)

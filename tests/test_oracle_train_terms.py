@@ -60,3 +60,17 @@ def test_anchor_growing_oracle_matches_reference():
             d[f"{p}.in._anchor"], d[f"{p}.in._offset"], d[f"{p}.in._scaling"], d[f"{p}.in._anchor_feat"], d[f"{p}.grads_norm"], 0.0002,
             d[f"{p}.offset_mask"], rands, float(d[f"{p}.voxel_size"]), div_mode=0)
         assert np.array_equal(a2, anchor) and np.array_equal(f2, feat)
+
+
+def test_cvpm_mask_oracle_matches_reference():
+    d = np.load(GOLD)
+    cloud, t1, t2 = d["cvpm.cloud"], d["cvpm.t1"], d["cvpm.t2"]
+    s_open = O.ssim(d["cvpm.real1"][:, :38, :50], d["cvpm.real2"])
+    s_gated = O.ssim(d["cvpm.real1"][:, :38, :50], d["cvpm.other"])
+    assert s_open > 0.6 > s_gated
+    for name, s in (("open", s_open), ("tight", s_open), ("gated", s_gated)):
+        want = np.unpackbits(d[f"cvpm.{name}.mask"])[: cloud.shape[0]].astype(bool)
+        got = O.cvpm_mask(cloud, t1, t2, s, float(d[f"cvpm.{name}.thr"]))
+        assert int(got.sum()) == int(want.sum()) == int(d[f"cvpm.{name}.n_points"])
+        assert np.array_equal(got, want), name
+    assert int(np.unpackbits(d["cvpm.open.mask"]).sum()) > 500 and int(np.unpackbits(d["cvpm.gated.mask"]).sum()) == 0

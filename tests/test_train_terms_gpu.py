@@ -226,3 +226,44 @@ def test_grow_pass_edge_cases():
     assert a.cpu().tolist() == [[-1.0, 2.0, 0.5]] and torch.equal(f[0], feat[N - 1])
     with pytest.raises(RuntimeError):
         grow_pass(anchor.cpu(), offset.cpu(), scaling.cpu(), feat.cpu(), 0.5, candidate_mask=allc.cpu())
+
+
+# ---- CVPM pruning mask -----------------------------------------------------------------------------------------------
+def test_cvpm_matches_reference():
+    from splatco_b200.cvpm import compute_fast_loss_with_key_points
+    d = np.load(GOLD)
+    c = lambda k: torch.from_numpy(d[k]).cuda()
+    cloud, eye = c("cvpm.cloud"), torch.eye(3)
+    for name, r2 in (("open", "cvpm.real2"), ("tight", "cvpm.real2"), ("gated", "cvpm.other")):
+        a, b, pts, mask = compute_fast_loss_with_key_points(None, c("cvpm.real1"), c(r2), c("cvpm.gen1"), c("cvpm.gen2"), eye, eye,
+                                                            torch.from_numpy(d["cvpm.t1"]), eye, eye, torch.from_numpy(d["cvpm.t2"]), cloud,
+                                                            distance_threshold=float(d[f"cvpm.{name}.thr"]), overall_ssim_threshold=0.6)
+        want = np.unpackbits(d[f"cvpm.{name}.mask"])[: cloud.shape[0]].astype(bool)
+        assert int(mask.sum()) == int(want.sum()) == int(pts.shape[0])               # the count train.py prunes by
+        assert np.array_equal(mask.cpu().numpy(), want), name
+        assert abs(float(a) - float(d[f"cvpm.{name}.gen_l1"])) < 2e-6 and abs(float(b) - float(d[f"cvpm.{name}.cross_l1"])) < 2e-6
+
+
+def test_cvpm_large_vs_oracle_and_edges():
+    from oracle import train_terms_oracle as O
+    from splatco_b200.cvpm import cvpm_mask
+    g = torch.Generator().manual_seed(5)
+    N = 1_000_000
+    t1, t2 = torch.tensor([0.5, -2.0, 1.0]), torch.tensor([-1.0, 1.5, 0.3])
+    d = (t2 - t1) / (t2 - t1).norm()
+    cloud = torch.rand(N, 3, generator=g) * 6 - 3
+    cloud[:100_000] = t1 + d * (torch.rand(100_000, 1, generator=g) * 20 - 10) + torch.randn(100_000, 3, generator=g) * 0.01
+    want = O.cvpm_mask(cloud.numpy(), t1.numpy(), t2.numpy(), None, 0.01)
+    mask, count = cvpm_mask(cloud.cuda(), t1, t2, None, 0.01)
+    got = mask.cpu().numpy()
+    assert int(count.item()) == int(got.sum())
+    # fp32 distances within an ulp of a threshold may fall either side (the dot product is an FMA chain here, a BLAS call
+    # in torch): allow a handful of flips out of a million, none of them far from a threshold
+    assert int((got != want).sum()) <= 3 and int(want.sum()) > 10_000
+    one = cloud[:1].cuda()
+    m1, c1 = cvpm_mask(one, t1, t2, None, 100.0)           # a single point: std is NaN -> every point is an "outlier", like torch
+    assert bool(m1[0]) and int(c1.item()) == 1
+    m0, c0 = cvpm_mask(cloud[:0].cuda(), t1, t2, None, 0.01)
+    assert m0.shape == (0,) and int(c0.item()) == 0
+    mg, cg = cvpm_mask(cloud[:1000].cuda(), t1, t2, torch.tensor(0.3).cuda(), 100.0)
+    assert int(cg.item()) == 0 and not bool(mg.any())
