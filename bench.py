@@ -146,7 +146,7 @@ def run_ours(args):
     import torch.distributed as dist
     from splatco_b200 import _lib, profiling
     from splatco_b200.gaussian_renderer import prefilter_voxel, render
-    from splatco_b200.loss import l1_ssim_loss
+    from splatco_b200.loss import l1_ssim_loss, scaling_reg
     from splatco_b200.multiview import GradBucket
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +196,7 @@ def run_ours(args):
             else:
                 gt = gts_dev[v]
             # the reference's per-view loss (train.py:192-196, lambda_dssim = 0.2 from arguments/__init__.py), image part fused
-            loss = l1_ssim_loss(pkg["render"], gt, 0.2) + 0.01 * pkg["scaling"].prod(dim=1).mean()
+            loss = l1_ssim_loss(pkg["render"], gt, 0.2) + 0.01 * (pkg["scaling"].prod(dim=1).mean() if args.torch_scaling_reg else scaling_reg(pkg["scaling"]))
             total = loss if total is None else total + loss
             Ms.append(pkg["radii"].shape[0]); Vs.append(pkg["selection_mask"].shape[0] // cfg["K"])
         total.backward()
@@ -329,7 +329,7 @@ def run_ours(args):
         "config": {"workload": cfg["desc"], "path": "prefilter_voxel + render() drop-in: decode, preprocess, binning, blend, fwd+bwd",
                    "anchors": N, "visible_anchors": int(V), "gaussians": int(M), "instances_R": int(R),
                    "activate_level": LEVEL, "plane_size": cfg["plane_size"], "num_channels": cfg["C"], "Q0": 0.03,
-                   "mv": mv, "views_per_step": views, "loss": "0.8*L1 + 0.2*(1-SSIM) (fused kernels) + 0.01*mean(prod(scaling)), train.py:192-196",
+                   "mv": mv, "views_per_step": views, "loss": "0.8*L1 + 0.2*(1-SSIM) (fused kernels) + 0.01*mean(prod(scaling)) (" + ("torch ops" if args.torch_scaling_reg else "splatco scaling_reg kernel, no host sync in its backward") + "), train.py:192-196",
                    "l2": "per-step working set (planes + workspaces) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"view-sharded dp{world}, NCCL grad all-reduce" if world > 1 else "single GPU"},
         "it_per_s": round(1000.0 / ms_step, 3),
@@ -444,6 +444,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--torch-scaling-reg", action="store_true",
+                    help="scaling regulariser with torch ops as train.py:195 writes it (its prod backward syncs with the host every view)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

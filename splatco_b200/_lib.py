@@ -57,6 +57,8 @@ SIGNATURES = {
     "splatco_loss_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_l1_ssim_fwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "splatco_l1_ssim_bwd": (_i, [_i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "splatco_scaling_reg_fwd": (_i, [_i, _vp, _vp, _vp, _vp]),
+    "splatco_scaling_reg_bwd": (_i, [_i, _vp, _vp, _vp, _vp]),
     "splatco_mv_consistency_ws_bytes": (_sz, [_i]),
     "splatco_mv_consistency_fwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "splatco_mv_consistency_bwd": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -274,6 +274,40 @@ template <int NV> struct MvcLaunch {
     }
 };
 
+
+// ---- scaling regulariser of the per-view loss: mean_i prod_j scaling[i, j]  (train.py:195) -----------------------
+// torch's `scaling.prod(dim=1).mean()` is three launches forward, and its backward (prod_backward) counts the zeros of
+// its input with `.item()` — a device-to-host sync at the START of every view's backward, which keeps the host from
+// queueing the view's blend / decode backward until the previous view's has drained.  Here: one reduction forward
+// (fp64 accumulator), one elementwise backward  d/ds[i,j] = g / M * prod_{k != j} s[i,k]  (exact with zeros, no sync).
+__global__ void __launch_bounds__(256)
+scaling_reg_fwd_kernel(int M, const float *__restrict__ s, double *__restrict__ sum) {
+    float a = 0.f;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < M; i += gridDim.x * 256)
+        a += s[3 * (size_t)i] * s[3 * (size_t)i + 1] * s[3 * (size_t)i + 2];
+    __shared__ float red[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)red[w];
+        atomicAdd(sum, t);
+    }
+}
+
+__global__ void scaling_reg_finish_kernel(int M, const double *__restrict__ sum, float *__restrict__ out) { out[0] = (float)(sum[0] / (double)M); }
+
+__global__ void __launch_bounds__(256)
+scaling_reg_bwd_kernel(int M, const float *__restrict__ s, const float *__restrict__ g_loss, float *__restrict__ ds) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    const float g = __ldg(g_loss) / (float)M;
+    const float a = s[3 * (size_t)i], b = s[3 * (size_t)i + 1], c = s[3 * (size_t)i + 2];
+    ds[3 * (size_t)i] = g * (b * c); ds[3 * (size_t)i + 1] = g * (a * c); ds[3 * (size_t)i + 2] = g * (a * b);
+}
+
 }  // namespace splatco
 
 using namespace splatco;
@@ -404,6 +438,26 @@ extern "C" int splatco_mv_consistency_bwd(int n_views, int C, const float *const
         case 7: MvcLaunch<7>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
         default: MvcLaunch<8>::bwd(grid, st, H, W, total, v, weights, grad_loss); break;
     }
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_scaling_reg_fwd(int M, const float *scaling, void *ws, float *out, void *stream) {
+    SPLATCO_REQUIRE(M >= 1, "scaling_reg_fwd: needs at least one row (mean of an empty tensor is NaN in the reference), M=%d", M);
+    SPLATCO_REQUIRE(scaling && ws && out, "scaling_reg_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double), st));
+    const int grid = ceil_div(M, 256 * 8) < 148 * 4 ? ceil_div(M, 256 * 8) : 148 * 4;
+    scaling_reg_fwd_kernel<<<grid, 256, 0, st>>>(M, scaling, (double *)ws);
+    SPLATCO_CHECK_LAUNCH();
+    scaling_reg_finish_kernel<<<1, 1, 0, st>>>(M, (const double *)ws, out);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int splatco_scaling_reg_bwd(int M, const float *scaling, const float *grad_loss, float *d_scaling, void *stream) {
+    SPLATCO_REQUIRE(M >= 1 && scaling && grad_loss && d_scaling, "scaling_reg_bwd: bad arguments");
+    scaling_reg_bwd_kernel<<<ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(M, scaling, grad_loss, d_scaling);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

@@ -75,6 +75,44 @@ def ssim(img1, img2, window_size=11, size_average=True):
     return 1.0 - l1_ssim_loss(img1, img2, 1.0)
 
 
+class _ScalingReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scaling):
+        L = _lib.lib()
+        if not scaling.is_cuda or scaling.dim() != 2 or scaling.shape[1] != 3:
+            raise RuntimeError(f"splatco_b200 scaling_reg needs a CUDA [M,3] tensor (no CPU fallback), got {tuple(scaling.shape)} on {scaling.device}")
+        s = scaling.detach()
+        if s.dtype != torch.float32 or not s.is_contiguous():
+            s = s.float().contiguous()
+        M = int(s.shape[0])
+        dev = s.device
+        with _lib.on_device(dev):
+            ws = torch.empty(8, dtype=torch.uint8, device=dev)
+            out = torch.empty(1, dtype=torch.float32, device=dev)
+            with stage("scaling_reg_fwd"):
+                check(L.splatco_scaling_reg_fwd(M, ptr(s), ptr(ws), ptr(out), _lib.raw_stream(dev)), "splatco_scaling_reg_fwd")
+        ctx.keep = (s, M)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        s, M = ctx.keep
+        dev = s.device
+        gl = g if (g.dtype == torch.float32 and g.is_contiguous()) else g.detach().float().contiguous()
+        with _lib.on_device(dev):
+            ds = torch.empty_like(s)
+            with stage("scaling_reg_bwd"):
+                check(L.splatco_scaling_reg_bwd(M, ptr(s), ptr(gl), ptr(ds), _lib.raw_stream(dev)), "splatco_scaling_reg_bwd")
+        return ds
+
+
+def scaling_reg(scaling):
+    """`scaling.prod(dim=1).mean()` of train.py:195 (the per-view loss adds 0.01 * this) for the [M,3] `render()["scaling"]`.
+    torch's prod backward reads a zero count back to the host at the start of every view's backward; this one does not."""
+    return _ScalingReg.apply(scaling)
+
+
 # ---- cross-view consistency term of the mv batch (train.py:199-216, summed in at :237-239) ----------------------
 import ctypes as _C
 

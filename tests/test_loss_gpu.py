@@ -48,3 +48,23 @@ def test_l1_ssim_scales_with_upstream_gradient_and_large_image():
     l1_ssim_loss(img, gt, 1.0).backward()
     ana = (img.grad.double() * v.double()).sum().item()
     assert abs((lp - lm) / (2 * eps) - ana) <= 5e-2 * abs(ana) + 1e-7
+
+
+def test_scaling_reg_matches_torch_prod_mean():
+    """train.py:195 `scaling.prod(dim=1).mean()`: value and gradient, including rows with zeros (where torch's backward takes
+    its slow exact path) and a non-unit upstream gradient."""
+    from splatco_b200.loss import scaling_reg
+    g = torch.Generator(device="cuda").manual_seed(11)
+    s = torch.rand(700_001, 3, device="cuda", generator=g) * 0.05
+    s[::1000, 1] = 0.0
+    s[5::2000] = 0.0
+    a = s.clone().requires_grad_()
+    b = s.clone().requires_grad_()
+    la = 0.01 * scaling_reg(a)
+    lb = 0.01 * b.prod(dim=1).mean()
+    la.backward()
+    lb.backward()
+    assert abs(la.item() - lb.item()) <= 1e-6 * abs(lb.item())
+    assert torch.allclose(a.grad, b.grad, rtol=1e-6, atol=1e-20)
+    with pytest.raises(RuntimeError):
+        scaling_reg(torch.rand(4, 3))

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     a = ap.parse_args()
     from splatco_b200.gaussian_renderer import prefilter_voxel, render
-    from splatco_b200.loss import l1_ssim_loss
+    from splatco_b200.loss import l1_ssim_loss, scaling_reg
     dev = torch.device("cuda", 0)
     cfg = bench.WORKLOADS[a.workload]
     pc = bench.build_model(cfg, dev)
@@ -41,7 +41,7 @@ def main():
         for v in range(cfg["mv"]):
             vm = prefilter_voxel(cams[v], pc, bench.PIPE, bg)
             pkg = render(cams[v], pc, bench.PIPE, bg, visible_mask=vm, retain_grad=True)
-            loss = l1_ssim_loss(pkg["render"], gts[v], 0.2) + 0.01 * pkg["scaling"].prod(dim=1).mean()
+            loss = l1_ssim_loss(pkg["render"], gts[v], 0.2) + 0.01 * scaling_reg(pkg["scaling"])
             total = loss if total is None else total + loss
         t_f = time.perf_counter()
         total.backward()
