@@ -18,6 +18,7 @@ import torch
 
 from . import _lib
 from ._lib import check
+from .profiling import stage
 
 
 class _AdamTensor(C.Structure):
@@ -40,8 +41,11 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         L = _lib.lib()
         by_cfg = {}
+        keep = []
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
+            lr = float(group["lr"])
+            items = None
             for p in group["params"]:
                 g = p.grad
                 if g is None:
@@ -52,26 +56,31 @@ class FusedAdam(torch.optim.Optimizer):
                     raise RuntimeError("splatco_b200 FusedAdam: contiguous fp32 parameters and dense fp32 gradients only")
                 if not g.is_contiguous():
                     g = g.contiguous()
+                    keep.append(g)
                 state = self.state[p]
                 if len(state) == 0:
-                    state["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    state["step"] = 0
                     state["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     state["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                state["step"] += 1
+                # `step` is kept as a Python int (torch.optim.Adam accepts and converts such checkpoints); a tensor
+                # loaded from a torch checkpoint is converted here
+                step = state["step"] = int(state["step"]) + 1
                 m, v = state["exp_avg"], state["exp_avg_sq"]
                 if not (m.is_contiguous() and v.is_contiguous()):
                     m = state["exp_avg"] = m.contiguous()
                     v = state["exp_avg_sq"] = v.contiguous()
-                by_cfg.setdefault((p.device, float(beta1), float(beta2), float(group["eps"])), []).append(
-                    (p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), int(state["step"].item()), float(group["lr"]), g))
+                if items is None:
+                    items = by_cfg.setdefault((p.device, float(beta1), float(beta2), float(group["eps"])), [])
+                items.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), step, lr))
         for (dev, beta1, beta2, eps), items in by_cfg.items():
             n = len(items)
             if self._table is None or len(self._table) < n:
                 self._table = (_AdamTensor * max(n, 128))()
             tab = self._table
-            for i, (pp, gp, mp, vp, numel, step, lr, _keep) in enumerate(items):
+            for i, it in enumerate(items):
                 e = tab[i]
-                e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.numel, e.step, e.lr = pp, gp, mp, vp, numel, step, lr
+                e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.numel, e.step, e.lr = it
             with _lib.on_device(dev):
-                check(L.splatco_adam_step(n, C.byref(tab), beta1, beta2, eps, _lib.raw_stream(dev)), "splatco_adam_step")
+                with stage("adam_step"):
+                    check(L.splatco_adam_step(n, C.byref(tab), beta1, beta2, eps, _lib.raw_stream(dev)), "splatco_adam_step")
         return loss
