@@ -331,7 +331,7 @@ typedef struct splatco_adam_tensor {
     float lr;
     float reserved;
 } splatco_adam_tensor;
-int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, float beta1, float beta2, float eps, void *stream);
+int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, double beta1, double beta2, double eps, void *stream);
 
 /* ---- diagnostics --------------------------------------------------------------------------------
  * Self-test of the tcgen05 3xTF32 tile-GEMM primitives the decode kernels are built on:

@@ -69,7 +69,7 @@ SIGNATURES = {
     "splatco_grow_emit": (_i, [_i, _i, _f, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "splatco_cvpm_ws_bytes": (_sz, []),
     "splatco_cvpm_mask": (_i, [_i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp]),
-    "splatco_adam_step": (_i, [_i, _vp, _f, _f, _f, _vp]),
+    "splatco_adam_step": (_i, [_i, _vp, C.c_double, C.c_double, C.c_double, _vp]),
     "splatco_training_statis": (_i, [_i, _i] + [_vp] * 11),
     "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
 }

@@ -75,7 +75,7 @@ adam_kernel(const __grid_constant__ AdamBatch b, float w1, float b2, float w2, f
 
 using namespace splatco;
 
-extern "C" int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, float beta1, float beta2, float eps,
+extern "C" int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, double beta1, double beta2, double eps,
                                  void *stream) {
     SPLATCO_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || tensors), "adam_step: bad tensor list");
     cudaStream_t st = (cudaStream_t)stream;
@@ -92,7 +92,7 @@ extern "C" int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tenso
             const int64_t c = (t.numel + ADAM_CHUNK - 1) / ADAM_CHUNK;
             SPLATCO_REQUIRE(c < (1 << 30) - chunks, "adam_step: tensor %d too large", done);
             b.p[k] = t.param; b.g[k] = t.grad; b.m[k] = t.exp_avg; b.v[k] = t.exp_avg_sq; b.n[k] = t.numel;
-            const double bc1 = 1.0 - pow((double)beta1, (double)t.step), bc2 = 1.0 - pow((double)beta2, (double)t.step);
+            const double bc1 = 1.0 - pow(beta1, (double)t.step), bc2 = 1.0 - pow(beta2, (double)t.step);
             b.step_size[k] = (float)((double)t.lr / bc1);
             b.bc2_sqrt[k] = (float)sqrt(bc2);
             b.first_chunk[k] = chunks;
@@ -102,7 +102,8 @@ extern "C" int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tenso
         b.first_chunk[k] = chunks;
         b.count = k;
         if (k == 0) continue;
-        adam_kernel<<<chunks, 256, 0, st>>>(b, 1.0f - beta1, beta2, 1.0f - beta2, eps);
+        // 1 - beta in double, then rounded: torch passes `1 - beta2` as a double scalar (1 - 0.999f would be off by 1.3e-5)
+        adam_kernel<<<chunks, 256, 0, st>>>(b, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), (float)eps);
         SPLATCO_CHECK_LAUNCH();
     }
     return 0;
