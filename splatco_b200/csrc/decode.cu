@@ -1054,7 +1054,7 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
             attr_set = true;
         }
         const int ntiles = ceil_div(V, TC_ROWS);
-        dec_tc_fwd_kernel<<<min(ntiles, 148), TC_ROWS, TC_SMEM, st>>>(V, dd.DP, f.XT, f.BA, f.W1B, f.W2B, f.bgeo, f.b1e, f.b2,
+        dec_tc_fwd_kernel<<<min(ntiles, 148), TC_THREADS, TC_SMEM, st>>>(V, dd.DP, f.XT, f.BA, f.W1B, f.W2B, f.bgeo, f.b1e, f.b2,
                                                                      f.XIN, f.H, f.Z, neural_opacity, mask, f.maskbits, f.bsum);
         SPLATCO_CHECK_LAUNCH();
     } else {
@@ -1129,7 +1129,7 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
             SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCB_SMEM));
             attr_set = true;
         }
-        dec_tc_bwd_kernel<<<min(ceil_div(V, TC_ROWS), 148), TC_ROWS, TCB_SMEM, st>>>(V, DP, LDX, b.DZ, f.H, f.W2R, f.W1R, f.WPCR,
+        dec_tc_bwd_kernel<<<min(ceil_div(V, TC_ROWS), 148), TC_THREADS, TCB_SMEM, st>>>(V, DP, LDX, b.DZ, f.H, f.W2R, f.W1R, f.WPCR,
                                                                                     b.DH, b.DX, b.DXH, b.gb2, b.gb1, b.S0);
         SPLATCO_CHECK_LAUNCH();
     } else {

@@ -1,9 +1,11 @@
 // Fused anchor-decode forward on 5th-gen tensor cores (tcgen05, TMEM accumulators, 3xTF32).
 // Included by decode.cu after its constants (KO, FD, GD, XI, HD, ZD).
 //
-// One persistent CTA per SM, 128 visible anchors per tile (UMMA M = 128 = TMEM lanes), 128 threads
-// (thread t <-> anchor row t <-> TMEM lane t).  Per tile, three chained GEMM stages whose accumulators
-// never leave the SM:
+// One persistent CTA per SM, 128 visible anchors per tile (UMMA M = 128 = TMEM lanes), 512 threads: warp w
+// works on anchor rows (= TMEM lanes) 32 (w & 3) .. +31 -- the lane quarter a warp may read with tcgen05.ld -- and on
+// column group w >> 2 of every operand load and epilogue, so four warps share each row block and the global loads /
+// TMEM read-outs / stores of a tile run four-wide (the chain is latency bound: with one warp per lane quarter a tile
+// took ~24 us).  Per tile, three chained GEMM stages whose accumulators never leave the SM:
 //   A  geo[128,64]  = [P | g] * [Wp' | Wc']          (BatchNorm folded into the weights by dec_fold_kernel)
 //   B  H  [128,96]  = relu([feat | dir,dist | geo] * W1 + b1)
 //   C  Z  [128,112] = H * W2(block-diagonal) + b2  -> tanh / sigmoid / mask bits in the epilogue
@@ -23,6 +25,7 @@
 namespace splatco {
 
 constexpr int TC_ROWS = 128;
+constexpr int TC_THREADS = 512;                             // 4 column groups x 4 TMEM lane quarters
 constexpr int TC_NP = 16;                                   // P chunks in shared memory (3*rc real ones)
 constexpr int TC_ACH = 36;                                  // chunks per A region
 constexpr uint32_t TC_CHUNK = TC_ROWS * 16;                 // 2048
@@ -86,7 +89,7 @@ __device__ __forceinline__ void tc_store_split(uint8_t *sm, int chunk, int row, 
     *reinterpret_cast<float4 *>(sm + TC_AREG + off) = make_float4(v4[0] - h.x, v4[1] - h.y, v4[2] - h.z, v4[3] - h.w);
 }
 
-__global__ void __launch_bounds__(TC_ROWS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__restrict__ BA,
                   const uint8_t *__restrict__ W1B, const uint8_t *__restrict__ W2B, const float *__restrict__ bgeo,
                   const float *__restrict__ b1e, const float *__restrict__ b2, float *__restrict__ XIN,
@@ -97,14 +100,15 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
     __shared__ uint32_t tmem_s;
     __shared__ float s_bias[64 + HD + ZD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & (TC_ROWS - 1), grp = tid >> 7;       // row within the tile (= TMEM lane), column group 0..3
     if (warp == 0) tc::tmem_alloc<128>(&tmem_s);
     if (tid == 0) { tc::mbar_init(&barL, 1); tc::mbar_init(&barM, 1); tc::fence_barrier_init(); }
-    for (int i = tid; i < 64 + HD + ZD; i += TC_ROWS) s_bias[i] = i < 64 ? bgeo[i] : (i < 64 + HD ? b1e[i - 64] : b2[i - 64 - HD]);
+    for (int i = tid; i < 64 + HD + ZD; i += TC_THREADS) s_bias[i] = i < 64 ? bgeo[i] : (i < 64 + HD ? b1e[i - 64] : b2[i - 64 - HD]);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t a_hi = tc::smem_u32(sm), a_lo = a_hi + TC_AREG;
     const uint32_t b_hi = a_hi + TC_OFF_B;
     const uint32_t w2_hi = a_hi + TC_OFF_W2;
@@ -116,7 +120,7 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row = tile * TC_ROWS + tid;
+        const int row = tile * TC_ROWS + r;
         const bool valid = row < V;
         // ---- operands of stage A ----------------------------------------------------------------------
         if (tid == 0) {
@@ -124,26 +128,26 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
             tc::bulk_g2s(sm + TC_OFF_B, BA, 2 * TC_BA_HALF, &barL);
         }
         const float4 *xt = reinterpret_cast<const float4 *>(XT) + (size_t)tile * nch * TC_ROWS;
-        // 8 independent 16-byte loads in flight per thread (one dependent load per chunk made this loop the
-        // kernel's critical path: ~34 serialized L2 round trips per tile)
-#pragma unroll 1
-        for (int c0 = 0; c0 < nch; c0 += 8) {
-            float4 x[8];
+        // column group g takes chunks g, g + 4, ...: all (at most 9) 16-byte loads of a thread are independent and in
+        // flight together (one dependent load per chunk made this the kernel's critical path)
+        {
+            constexpr int XK = (TC_NP + 19 + 3) / 4;        // 9
+            float4 x[XK];
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (c0 + q < nch) x[q] = __ldg(xt + (c0 + q) * TC_ROWS + tid);
+            for (int k = 0; k < XK; ++k)
+                if (grp + 4 * k < nch) x[k] = __ldg(xt + (grp + 4 * k) * TC_ROWS + r);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int c = c0 + q;
+            for (int k = 0; k < XK; ++k) {
+                const int c = grp + 4 * k;
                 if (c < nch) {
                     const int sc = c < npc ? 1 + c : (c < npc + 18 ? 18 + (c - npc) : 0);
-                    const float v4[4] = {x[q].x, x[q].y, x[q].z, x[q].w};
-                    tc_store_split(sm, sc, tid, v4);
+                    const float v4[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+                    tc_store_split(sm, sc, r, v4);
                 }
             }
         }
-        for (int pc = npc; pc < TC_NP + 1; ++pc) {          // zero the P padding chunks and chunk 17
-            const uint32_t off = (uint32_t)(1 + pc) * TC_CHUNK + (uint32_t)tid * 16u;
+        for (int pc = npc + grp; pc < TC_NP + 1; pc += 4) { // zero the P padding chunks and chunk 17
+            const uint32_t off = (uint32_t)(1 + pc) * TC_CHUNK + (uint32_t)r * 16u;
             *reinterpret_cast<float4 *>(sm + off) = zero4;
             *reinterpret_cast<float4 *>(sm + TC_AREG + off) = zero4;
         }
@@ -164,8 +168,8 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
             tc::bulk_g2s(sm + TC_OFF_B, W1B, 2 * TC_W1_HALF, &barL);
         }
         // ---- epilogue A: geo -> x100 columns 36..99 (global, for the backward) and stage-B operand chunks 1..16
-#pragma unroll 1
-        for (int n0 = 0; n0 < 64; n0 += 8) {
+#pragma unroll
+        for (int n0 = grp * 16; n0 < grp * 16 + 16; n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
@@ -176,8 +180,8 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
-            tc_store_split(sm, 1 + n0 / 4, tid, v);
-            tc_store_split(sm, 2 + n0 / 4, tid, v + 4);
+            tc_store_split(sm, 1 + n0 / 4, r, v);
+            tc_store_split(sm, 2 + n0 / 4, r, v + 4);
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -196,8 +200,8 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
             tc::bulk_g2s(sm + TC_OFF_W2, W2B, 2 * TC_W2_HALF, &barL);
         }
         // ---- epilogue B: H = relu(. + b1) -> global (for the backward) and stage-C operand chunks 0..23
-#pragma unroll 1
-        for (int n0 = 0; n0 < HD; n0 += 8) {
+#pragma unroll
+        for (int n0 = grp * (HD / 4); n0 < (grp + 1) * (HD / 4); n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
@@ -208,8 +212,8 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
                 dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
-            tc_store_split(sm, n0 / 4, tid, v);
-            tc_store_split(sm, n0 / 4 + 1, tid, v + 4);
+            tc_store_split(sm, n0 / 4, r, v);
+            tc_store_split(sm, n0 / 4 + 1, r, v + 4);
         }
         tc::fence_proxy_async();
         tc::tc_fence_before();
@@ -224,8 +228,11 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
         tc::tc_fence_after();
         // ---- epilogue C: activations, mask bits, survivor counts -------------------------------------------
         uint32_t bits = 0;
+        // 14 groups of 8 columns dealt 4 / 4 / 3 / 3; the opacity columns (j < KO) all belong to column group 0
+        const int c_beg = grp < 2 ? grp * 32 : 64 + (grp - 2) * 24, c_end = c_beg + (grp < 2 ? 32 : 24);
+        static_assert(ZD == 112 && KO <= 32 && HD % 32 == 0, "column-group split of the decode epilogues");
 #pragma unroll 1
-        for (int n0 = 0; n0 < ZD; n0 += 8) {
+        for (int n0 = c_beg; n0 < c_end; n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
@@ -251,12 +258,14 @@ dec_tc_fwd_kernel(int V, int DP, const float *__restrict__ XT, const uint8_t *__
                 dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
-        if (!valid) bits = 0;
-        if (valid) maskbits[row] = bits;
-        uint32_t cnt = __popc(bits);
+        if (grp == 0) {                                     // warps 0..3 hold the mask bits of their 32 rows
+            if (!valid) bits = 0;
+            if (valid) maskbits[row] = bits;
+            uint32_t cnt = __popc(bits);
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-        if (lane == 0 && cnt) atomicAdd(&block_sums[(tile * TC_ROWS + warp * 32) / 256], cnt);
+            for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+            if (lane == 0 && cnt) atomicAdd(&block_sums[(tile * TC_ROWS + warp * 32) / 256], cnt);
+        }
         tc::tc_fence_before();
         __syncthreads();                                    // TMEM and shared memory are free for the next tile
         tc::tc_fence_after();

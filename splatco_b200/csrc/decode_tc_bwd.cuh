@@ -88,7 +88,8 @@ __device__ __forceinline__ void colsum8_add(const float (&g)[8], int lane, float
     if ((lane & 3) == 0 && idx < ncols_valid && r != 0.f) atomicAdd(dst + idx, r);
 }
 
-__global__ void __launch_bounds__(TC_ROWS, 1)
+// 512 threads as in the forward: warp w <-> rows 32 (w & 3) .. +31 (its TMEM lane quarter), column group w >> 2.
+__global__ void __launch_bounds__(TC_THREADS, 1)
 dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const float *__restrict__ Hs,
                   const uint8_t *__restrict__ W2R, const uint8_t *__restrict__ W1R, const uint8_t *__restrict__ WPCR,
                   float *__restrict__ DH, float *__restrict__ DX, float *__restrict__ DXH, float *__restrict__ gb2,
@@ -97,21 +98,28 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
     __shared__ uint64_t barL, barM;
     __shared__ uint32_t tmem_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = tid & (TC_ROWS - 1), grp = tid >> 7;
     if (warp == 0) tc::tmem_alloc<256>(&tmem_s);
     if (tid == 0) { tc::mbar_init(&barL, 1); tc::mbar_init(&barM, 1); tc::fence_barrier_init(); }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t a_hi = tc::smem_u32(sm), a_lo = a_hi + TCB_AREG, b_hi = a_hi + TCB_OFF_B;
+    // 8-column groups of each stage dealt to the four column groups: 14 -> 4,4,3,3 | 12 -> 3,3,3,3 | 13 -> 4,3,3,3 | 18 -> 5,5,4,4
+    const int z_beg = (grp < 2 ? grp * 4 : 8 + (grp - 2) * 3) * 8, z_end = z_beg + (grp < 2 ? 32 : 24);
+    const int h_beg = grp * 24, h_end = h_beg + 24;
+    const int x_beg = (grp == 0 ? 0 : 4 + (grp - 1) * 3) * 8, x_end = x_beg + (grp == 0 ? 32 : 24);
+    const int o_beg = (grp < 2 ? grp * 5 : 10 + (grp - 2) * 4) * 8, o_end = o_beg + (grp < 2 ? 40 : 32);
+    static_assert(ZD == 112 && HD == 96 && TCB_NP + TCB_NC == 144, "column-group split of the decode backward epilogues");
     constexpr uint32_t idesc96 = tc::make_idesc_tf32(128, HD), idesc112 = tc::make_idesc_tf32(128, ZD),
                        idesc64 = tc::make_idesc_tf32(128, TCB_NP), idesc80 = tc::make_idesc_tf32(128, TCB_NC);
     uint32_t phL = 0, phM = 0;
     const int ntiles = (V + TC_ROWS - 1) / TC_ROWS;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row = tile * TC_ROWS + tid;
+        const int row = tile * TC_ROWS + r;
         const bool valid = row < V;
         // ---- stage 1 operands: W2R by bulk copy, dZ rows split by the threads -----------------------------------
         if (tid == 0) {
@@ -121,32 +129,31 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
         const float4 *zrow = reinterpret_cast<const float4 *>(DZ + (size_t)row * ZD);
         // the ReLU gate of epilogue 1 as 96 bits, so that its H row loads are issued here, all independent,
         // instead of one dependent round trip per 8 columns inside the TMEM read-out loop
-        uint32_t hbits[3] = {0u, 0u, 0u};
+        uint32_t hbits = 0u;                                     // bit q <-> hidden column h_beg + q (this thread's 24 columns)
         if (valid) {
-            const float4 *hrow = reinterpret_cast<const float4 *>(Hs + (size_t)row * HD);
+            const float4 *hrow = reinterpret_cast<const float4 *>(Hs + (size_t)row * HD + h_beg);
+            float4 h[6];
 #pragma unroll
-            for (int w = 0; w < 3; ++w) {
-                float4 h[8];
+            for (int q = 0; q < 6; ++q) h[q] = __ldg(hrow + q);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = __ldg(hrow + 8 * w + q);
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    hbits[w] |= (h[q].x > 0.f ? 1u : 0u) << (4 * q) | (h[q].y > 0.f ? 2u : 0u) << (4 * q) |
-                                (h[q].z > 0.f ? 4u : 0u) << (4 * q) | (h[q].w > 0.f ? 8u : 0u) << (4 * q);
-            }
+            for (int q = 0; q < 6; ++q)
+                hbits |= (h[q].x > 0.f ? 1u : 0u) << (4 * q) | (h[q].y > 0.f ? 2u : 0u) << (4 * q) |
+                         (h[q].z > 0.f ? 4u : 0u) << (4 * q) | (h[q].w > 0.f ? 8u : 0u) << (4 * q);
         }
-#pragma unroll 1
-        for (int c0 = 0; c0 < TCB_ACH; c0 += 14) {               // two halves of the dZ row, 14 loads in flight each
-            float4 x[14];
+        {                                                        // this thread's 6 or 8 chunks of the dZ row, all loads in flight
+            float4 x[8];
+            const int cb = z_beg >> 2, nc = (z_end - z_beg) >> 2;
 #pragma unroll
-            for (int q = 0; q < 14; ++q) x[q] = valid ? __ldg(zrow + c0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 8; ++q) x[q] = (valid && q < nc) ? __ldg(zrow + cb + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 14; q += 2) {
-                const int c = c0 + q;
-                const float v[8] = {x[q].x, x[q].y, x[q].z, x[q].w, x[q + 1].x, x[q + 1].y, x[q + 1].z, x[q + 1].w};
-                tcb_store_split(sm, c, tid, v);
-                tcb_store_split(sm, c + 1, tid, v + 4);
-                colsum8_add(v, lane, gb2 + 4 * c, ZD - 4 * c);
+            for (int q = 0; q < 8; q += 2) {
+                if (q < nc) {                                    // warp-uniform
+                    const int c = cb + q;
+                    const float v[8] = {x[q].x, x[q].y, x[q].z, x[q].w, x[q + 1].x, x[q + 1].y, x[q + 1].z, x[q + 1].w};
+                    tcb_store_split(sm, c, r, v);
+                    tcb_store_split(sm, c + 1, r, v + 4);
+                    colsum8_add(v, lane, gb2 + 4 * c, ZD - 4 * c);
+                }
             }
         }
         tc::fence_proxy_async();
@@ -165,13 +172,13 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
             tc::bulk_g2s(sm + TCB_OFF_B, W1R, 2 * TCB_W1R_HALF, &barL);
         }
         // ---- epilogue 1: ReLU gate, dH -> global + stage-2 operand chunks 0..23, gb1 ------------------------------
-#pragma unroll 1
-        for (int n0 = 0; n0 < HD; n0 += 8) {
+#pragma unroll
+        for (int n0 = h_beg; n0 < h_end; n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
             if (valid) {
-                const uint32_t gate = (n0 < 32 ? hbits[0] : (n0 < 64 ? hbits[1] : hbits[2])) >> (n0 & 31);
+                const uint32_t gate = hbits >> (n0 - h_beg);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = (gate >> q) & 1u ? v[q] : 0.f;
                 float4 *dst = reinterpret_cast<float4 *>(DH + (size_t)row * HD + n0);
@@ -181,8 +188,8 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
 #pragma unroll
                 for (int q = 0; q < 8; ++q) v[q] = 0.f;
             }
-            tcb_store_split(sm, n0 / 4, tid, v);
-            tcb_store_split(sm, n0 / 4 + 1, tid, v + 4);
+            tcb_store_split(sm, n0 / 4, r, v);
+            tcb_store_split(sm, n0 / 4 + 1, r, v + 4);
             colsum8_add(v, lane, gb1 + n0, 8);
         }
         tc::fence_proxy_async();
@@ -202,7 +209,7 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
         }
         // ---- epilogue 2: dX -> global (100 columns); dgeo = columns 36..99 -> stage-3 operand chunks 0..15, S0 ------
 #pragma unroll 1
-        for (int n0 = 0; n0 < 104; n0 += 8) {
+        for (int n0 = x_beg; n0 < x_end; n0 += 8) {
             float v[8];
             tc::tmem_ld8(tlane + n0, v);
             tc::tmem_ld_wait();
@@ -216,8 +223,8 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
                 if (n0 + 4 < XI) dst[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
             // dgeo chunk index of column n: (n - 36) / 4
-            if (n0 + 4 >= 36 && n0 + 4 < XI) tcb_store_split(sm, (n0 + 4 - 36) / 4, tid, v + 4);
-            if (n0 >= 36) tcb_store_split(sm, (n0 - 36) / 4, tid, v);
+            if (n0 + 4 >= 36 && n0 + 4 < XI) tcb_store_split(sm, (n0 + 4 - 36) / 4, r, v + 4);
+            if (n0 >= 36) tcb_store_split(sm, (n0 - 36) / 4, r, v);
             // S0[o] = colsum(dgeo[:, o]), o = n - 36
             if (n0 >= 36) {
                 colsum8_add(v, lane, S0 + (n0 - 36), min(8, XI - n0));
@@ -243,7 +250,7 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
         {
             float *drow = DXH + (size_t)row * LDX;
 #pragma unroll 1
-            for (int n0 = 0; n0 < TCB_NP + TCB_NC; n0 += 8) {
+            for (int n0 = o_beg; n0 < o_end; n0 += 8) {
                 float v[8];
                 tc::tmem_ld8(tlane + n0, v);          // warp-collective: every lane executes it, stores are predicated
                 tc::tmem_ld_wait();
