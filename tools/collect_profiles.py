@@ -29,7 +29,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 traffic = {}
 if os.path.exists(os.path.join(src, f"launches_{tag}.csv")):
     shutil.copy(os.path.join(src, f"launches_{tag}.csv"), os.path.join(dst, f"{tag}_launches.csv"))
-for name in ("blend_bwd", "blend_fwd", "rest"):
+for name in ("blend_bwd", "blend_fwd", "rest", "optim"):
     rep = os.path.join(src, f"prof_{name}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue

@@ -16,3 +16,5 @@ ncu --set full --clock-control none --import-source on \
     -k regex:"dec_(wgrad|tc_fwd|tc_bwd|gather|bwd_inputs|bwd_uncompact)_kernel|tile_sort_radix|tile_scatter|tile_hist|preprocess_(fwd|bwd)_kernel|visible_filter" \
     -s 40 -c 22 -o $OUT/prof_rest_$TAG -f python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_rest_$TAG.log 2>&1
 ls -la $OUT | grep $TAG
+ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|tv_add_grad_kernel|mvc_(fwd|bwd)_kernel" -s 2 -c 2 -o $OUT/prof_optim_$TAG -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_optim_$TAG.log 2>&1
