@@ -27,6 +27,7 @@ threads), one view of the workload per step.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import math
 import os
@@ -208,16 +209,32 @@ def run_ours(args):
     def timed(n, host_inputs):
         return _timed_fn(step, n, host_inputs)
 
+    host_ms = {}
+
     def _timed_fn(fn, n, host_inputs):
+        # the cyclic collector is paused inside the timed region (a generation-2 pass over the autograd graphs of a
+        # step costs tens of ms and lands on a random step); per-step host times are kept as a diagnostic
+        gc.collect()
+        gc.disable()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = [time.perf_counter()]
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
         e0.record()
-        for _ in range(n):
+        for i in range(n):
             fn(host_inputs)
+            marks[i].record()
+            ts.append(time.perf_counter())
         e1.record()
         torch.cuda.synchronize()
+        gc.enable()
+        d = sorted((b - a) * 1e3 for a, b in zip(ts[:-1], ts[1:]))
+        gd = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+        host_ms[getattr(fn, "__name__", "fn") + ("_host_inputs" if host_inputs else "")] = {
+            "host_median": round(d[len(d) // 2], 3), "host_max": round(d[-1], 3),
+            "gpu_median": round(gd[len(gd) // 2], 3), "gpu_max": round(gd[-1], 3)}
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
@@ -228,11 +245,14 @@ def run_ours(args):
         return ms
 
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step(False)
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation) stalls the GPU for tens
+    # of ms on some boxes, which otherwise lands inside the first timed loop; it keeps sampling through the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for _ in range(warm):
+        step(False)
     launches0 = L.splatco_launch_count()
     ms_dev = timed(args.steps, host_inputs=False)
     launches = L.splatco_launch_count() - launches0
@@ -341,6 +361,7 @@ def run_ours(args):
                   "includes": "the e2e step (H2D ground truth, mv views fwd+bwd, loss read-back" + (", NCCL grad all-reduce" if world > 1 else "") +
                               ") + FusedAdam update of every parameter (train.py:310-312), lr 1e-6"},
         "roofline": roof, "decode_mlp": mlp, "stages": stages, "clocks": clocks,
+        "per_step_ms": host_ms,
     }
     if bucket is not None:
         out["config"]["allreduce_bytes_per_step"] = bucket.nbytes()

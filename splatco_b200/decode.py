@@ -182,9 +182,9 @@ class _FusedDecode(torch.autograd.Function):
         desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c, pc)
         stream = _lib.raw_stream(dev)
         with _lib.on_device(dev):
-            ws = torch.empty(max(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
-            nopac = torch.empty((V * K, 1), dtype=torch.float32, device=dev)
-            mask = torch.empty(V * K, dtype=torch.bool, device=dev)
+            ws = _lib.empty_u8(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), dev)
+            nopac = _lib.empty_rows(V * K, 1, torch.float32, dev)
+            mask = _lib.empty_rows(V * K, None, torch.bool, dev)
             counter = _pinned_counter(dev)
             with stage("decode_fwd"):
                 check(L.splatco_decode_fwd(C.byref(desc), _p(ws), _p(nopac), _p(mask), counter.data_ptr(), stream),
@@ -196,7 +196,7 @@ class _FusedDecode(torch.autograd.Function):
                 # (the reference syncs twice here: boolean indexing, then num_rendered)
                 from . import diff_gaussian_rasterization as _dgr
                 VK = V * K
-                bufs = [torch.empty((VK, c), **f32) for c in (3, 3, 1, 3, 4)]
+                bufs = [_lib.empty_rows(VK, c, torch.float32, dev) for c in (3, 3, 1, 3, 4)]
                 with stage("decode_emit"):
                     check(L.splatco_decode_emit(C.byref(desc), _p(ws), VK, *[_p(b) for b in bufs], stream),
                           "splatco_decode_emit")
@@ -256,7 +256,7 @@ class _FusedDecode(torch.autograd.Function):
                 ups = [u if u is not None else z(*s) for u, s in zip(ups[:5], ((M, 3), (M, 3), (M, 1), (M, 3), (M, 4)))] + [ups[5]]
             stream = _lib.raw_stream(dev)
             with _lib.on_device(dev):
-                bws = torch.empty(max(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), 256), dtype=torch.uint8, device=dev)
+                bws = _lib.empty_u8(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), dev)
                 with stage("decode_bwd"):
                     check(L.splatco_decode_bwd(C.byref(desc), _p(ctx.ws), _p(bws), M, *[_p(u) for u in ups],
                                                gd, stream), "splatco_decode_bwd")

@@ -113,8 +113,8 @@ def preprocess_speculative(xyz_b, color_b, opacity_b, scaling_b, rot_b, count_pt
     PL = int(xyz_b.shape[0])
     sp = _Speculated()
     sp.settings, sp.PL = settings, PL
-    sp.radii_full = torch.empty(PL, dtype=torch.int32, device=dev)
-    sp.geom = torch.empty(L.splatco_geom_bytes(PL), dtype=torch.uint8, device=dev)
+    sp.radii_full = _lib.empty_rows(PL, None, torch.int32, dev)
+    sp.geom = _lib.empty_u8(L.splatco_geom_bytes(PL), dev)
     sp.counter = _pinned_counter(dev, 1)
     view, proj = _f32c(settings.viewmatrix), _f32c(settings.projmatrix)
     with stage("preprocess_fwd"):
@@ -146,7 +146,7 @@ def _queue_binning_blend(sp, dev, H, W):
     L = _lib.lib()
     settings = sp.settings
     stream = _stream_ptr(dev)
-    sp.binning = torch.empty(max(L.splatco_binning_bytes(sp.RL), 256), dtype=torch.uint8, device=dev)
+    sp.binning = _lib.empty_u8(L.splatco_binning_bytes(sp.RL), dev)
     sp.image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
     sp.color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
     with stage("binning"):
@@ -227,8 +227,8 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
             scales, sstride = _rows_f32(scales, 3)
             view = _f32c(settings.viewmatrix)
             proj = _f32c(settings.projmatrix)
-            radii = radii_full = torch.empty(P, dtype=torch.int32, device=dev)
-            geom = torch.empty(L.splatco_geom_bytes(P), dtype=torch.uint8, device=dev)
+            radii = radii_full = _lib.empty_rows(P, None, torch.int32, dev)
+            geom = _lib.empty_u8(L.splatco_geom_bytes(P), dev)
             counter = _pinned_counter(dev)
             with stage("preprocess_fwd"):
                 check(L.splatco_preprocess_fwd(P, ptr(means3D), ptr(scales), sstride, ptr(rotations), ptr(opacities),
@@ -239,7 +239,7 @@ def rasterize_forward_state(means3D, colors, opacities, scales, rotations, setti
             torch.cuda.current_stream(dev).synchronize()
             R = int(counter[0])
         _debug_sync(settings, "preprocess")
-        binning = torch.empty(max(L.splatco_binning_bytes(R), 256), dtype=torch.uint8, device=dev)
+        binning = _lib.empty_u8(L.splatco_binning_bytes(R), dev)
         image = torch.empty(L.splatco_image_bytes(H, W), dtype=torch.uint8, device=dev)
         with stage("binning"):
             check(L.splatco_binning(st.PL, R, H, W, ptr(radii_full), ptr(geom), ptr(binning), ptr(image), stream),
@@ -261,9 +261,9 @@ def rasterize_backward_state(st: RasterState, grad_color, means3D, scales, rotat
     P, R, H, W = st.P, st.RL, st.H, st.W          # RL: the binning workspace's layout size
     # two allocations, two split calls: [mean2D 3 | conic 3 | opacity 1 | colour 3] is zero-filled for the blend's
     # REDs, [means3D 3 | scales 3 | rotations 4] is overwritten by preprocess_bwd (rotations stay 16-byte aligned)
-    a, b_, c, d = torch.zeros(10 * P, dtype=torch.float32, device=dev).split_with_sizes([3 * P, 3 * P, P, 3 * P])
+    a, b_, c, d = torch.zeros(_lib.bucket(10 * P), dtype=torch.float32, device=dev)[:10 * P].split_with_sizes([3 * P, 3 * P, P, 3 * P])
     g_mean2D, g_conic, g_opac, g_color = a.view(P, 3), b_.view(P, 3), c.view(P, 1), d.view(P, 3)
-    e, f, g_ = torch.empty(12 * P, dtype=torch.float32, device=dev).split_with_sizes([4 * P, 4 * P, 4 * P])
+    e, f, g_ = _lib.empty_rows(12 * P, None, torch.float32, dev).split_with_sizes([4 * P, 4 * P, 4 * P])
     g_rots, g_means3D, g_scales = e.view(P, 4), f[:3 * P].view(P, 3), g_[:3 * P].view(P, 3)
     if P == 0:
         return dict(means3D=g_means3D, means2D=g_mean2D, colors=g_color, opacities=g_opac,
