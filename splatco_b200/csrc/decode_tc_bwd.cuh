@@ -257,9 +257,19 @@ dec_tc_bwd_kernel(int V, int DP, int LDX, const float *__restrict__ DZ, const fl
                 const int base = n0 < TCB_NP ? n0 : DP + (n0 - TCB_NP);
                 const int lim = n0 < TCB_NP ? DP : DP + GD;
                 if (valid) {
+                    // rows are 16-byte aligned (LDX % 4 == 0); whole groups that start on a 16-byte boundary (always in the
+                    // plane block; in the context block when DP = 6/9/12 rc is a multiple of 4) go out as two 16-byte
+                    // stores (scalar stores of this epilogue were 144 of the ~200 store instructions per row and showed
+                    // up as lg_throttle stalls, ncu r1z)
+                    if (base + 8 <= lim && (base & 3) == 0) {
+                        float4 *dst = reinterpret_cast<float4 *>(drow + base);
+                        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        if (base + q < lim) drow[base + q] = v[q];
+                        for (int q = 0; q < 8; ++q)
+                            if (base + q < lim) drow[base + q] = v[q];
+                    }
                 }
             }
         }

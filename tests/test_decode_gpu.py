@@ -222,7 +222,8 @@ def test_plane_feature_noise_generated_in_kernel():
     assert float(n1.abs().max()) <= 0.5 * Q * (1 + 1e-4) + 1e-7
     assert abs(float(n1.mean())) < 5e-3 * Q
     assert abs(float(n1.var()) / (Q * Q / 12.0) - 1.0) < 0.02
-    assert abs(float((n1[:, 0] * n1[:, 1]).mean())) < 0.02 * Q * Q / 12.0        # neighbouring columns uncorrelated
+    # neighbouring columns uncorrelated: the mean of 6000 products has sigma = (Q^2/12) / sqrt(6000) = 0.013 Q^2/12; 5 sigma
+    assert abs(float((n1[:, 0] * n1[:, 1]).mean())) < 0.065 * Q * Q / 12.0
     assert float((d1 - d2).abs().max()) > 0.1 * Q, "every call must draw fresh noise"
 
 
