@@ -694,8 +694,9 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
         return splatco_binning_radix(P, R, H, W, radii, geom, binning, image, stream);
     GeomWs g = geom_view(const_cast<void *>(geom), P);
     uint32_t *chunk_hist = b.vals[s ^ 1];
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned char attr_dev[64];       // cudaFuncSetAttribute is per device
+    const int attr_i = current_device() & 63;
+    if (!attr_dev[attr_i]) {
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_NT_S, TSORT_ITEMS_S>,
@@ -704,7 +705,7 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_radix_kernel<TSORT_NT_L, TSORT_ITEMS_L>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)tsort_smem(TSORT_NT_L, TSORT_ITEMS_L)));
-        attr_set = true;
+        attr_dev[attr_i] = 1;
     }
     tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist);
     SPLATCO_CHECK_LAUNCH();

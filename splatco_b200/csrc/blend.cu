@@ -422,10 +422,11 @@ extern "C" int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg
     ImgWs im = img_view(const_cast<void *>(image), H, W);
     BinWs b = bin_view(const_cast<void *>(binning), R);
     const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned char attr_dev[64];       // cudaFuncSetAttribute is per device
+    const int attr_i = current_device() & 63;
+    if (!attr_dev[attr_i]) {
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-        attr_set = true;
+        attr_dev[attr_i] = 1;
     }
     blend_bwd_kernel<<<gx * gy, BLEND_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
         im.ranges, b.vals[splatco_sorted_buffer_index(H, W)], reinterpret_cast<const float4 *>(geom), W, H, gx, bg,

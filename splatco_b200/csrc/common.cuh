@@ -18,6 +18,7 @@ constexpr size_t ALIGN = 256;
 
 inline size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 void set_error(const char *fmt, ...);

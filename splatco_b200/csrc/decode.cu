@@ -1048,10 +1048,11 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
         SPLATCO_CHECK_LAUNCH();
         dec_tc_pack_bwd_kernel<<<12, 256, 0, st>>>(dd.DP, f.W2T, f.W1T, f.WpG, f.WcG, f.W2R, f.W1R, f.WPCR);   // for the backward
         SPLATCO_CHECK_LAUNCH();
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned char attr_dev[64];       // cudaFuncSetAttribute is per device
+    const int attr_i = current_device() & 63;
+        if (!attr_dev[attr_i]) {
             SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-            attr_set = true;
+            attr_dev[attr_i] = 1;
         }
         const int ntiles = ceil_div(V, TC_ROWS);
         dec_tc_fwd_kernel<<<min(ntiles, 148), TC_THREADS, TC_SMEM, st>>>(V, dd.DP, f.XT, f.BA, f.W1B, f.W2B, f.bgeo, f.b1e, f.b2,
@@ -1124,10 +1125,11 @@ extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_
     const bool use_tc = dd.rc <= TC_MAX_RC;
     if (use_tc) {
         // row chain on tensor cores: dH = (dZ W2).[H>0], dX = dH W1, dxhat = dgeo (gamma W); gb2, gb1, S0 in its epilogues
-        static bool attr_set = false;
-        if (!attr_set) {
+        static unsigned char attr_dev[64];       // cudaFuncSetAttribute is per device
+    const int attr_i = current_device() & 63;
+        if (!attr_dev[attr_i]) {
             SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCB_SMEM));
-            attr_set = true;
+            attr_dev[attr_i] = 1;
         }
         dec_tc_bwd_kernel<<<min(ceil_div(V, TC_ROWS), 148), TC_THREADS, TCB_SMEM, st>>>(V, DP, LDX, b.DZ, f.H, f.W2R, f.W1R, f.WPCR,
                                                                                     b.DH, b.DX, b.DXH, b.gb2, b.gb1, b.S0);
