@@ -127,6 +127,52 @@ def allreduce_count(value: int, device, group=None) -> int:
     return int(t.item())
 
 
+def gather_view_images(local_images, num_views: int, rank: int, world: int, group=None) -> List[torch.Tensor]:
+    """All views' rendered images on every rank (SURVEY §8e collective (2)): `local_images[k]` is the image of this
+    rank's k-th view (global index shard_views(num_views, rank, world)[k]).  One all_gather of the padded local stack;
+    the result is in global view order, remote images are plain (detached) tensors, the local ones are returned as
+    given (so autograd still reaches them).  All views must share one [C,H,W] shape."""
+    mine = shard_views(num_views, rank, world)
+    if len(local_images) != len(mine):
+        raise ValueError(f"rank {rank} owns {len(mine)} of {num_views} views but passed {len(local_images)} images")
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return list(local_images)
+    slots = (num_views + world - 1) // world
+    if not local_images:
+        raise ValueError("gather_view_images: every rank must own at least one view (num_views >= world)")
+    ref = local_images[0]
+    shape = torch.tensor(list(ref.shape), dtype=torch.int64, device=ref.device)
+    hi = shape.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    lo = shape.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    if not torch.equal(lo, hi):
+        raise NotImplementedError("gather_view_images: views of different sizes across ranks are not supported")
+    stack = torch.zeros((slots,) + tuple(ref.shape), dtype=ref.dtype, device=ref.device)
+    for k, img in enumerate(local_images):
+        stack[k].copy_(img.detach())
+    out = torch.empty((world,) + tuple(stack.shape), dtype=ref.dtype, device=ref.device)
+    dist.all_gather(list(out.unbind(0)), stack, group=group)        # list form: supported by both nccl and gloo
+    images = []
+    for i in range(num_views):
+        r, k = owner_of_view(i, world), i // world
+        images.append(local_images[k] if r == rank else out[r, k])
+    return images
+
+
+def sharded_consistency_loss(local_gen, all_real, num_views: int, rank: int, world: int, loss_fn=None, group=None):
+    """Cross-view consistency term of the mv batch (train.py:199-216) when the views are sharded: every rank gathers the
+    other ranks' rendered images (detached — exact, d/d gen_i treats gen_j as a constant), evaluates ALL pairs and
+    differentiates w.r.t. its own images only.  The returned value is the full sum over pairs on every rank (do not
+    sum it over ranks when logging); after each rank's backward the gradient all-reduce adds every pair's two halves
+    exactly once.  `all_real`: the ground-truth images of all num_views views (the camera list is replicated,
+    SURVEY §8e); `loss_fn(gens, reals)` defaults to splatco_b200.loss.multiview_consistency_loss."""
+    if loss_fn is None:
+        from .loss import multiview_consistency_loss as loss_fn
+    gens = gather_view_images(local_gen, num_views, rank, world, group)
+    return loss_fn(gens, list(all_real))
+
+
 def render_views_sharded(cams, pc, pipe, bg, loss_fn, rank: int, world: int, bucket: GradBucket = None, group=None):
     """One iteration's render work for the views owned by `rank`: prefilter -> render -> loss for each,
     ONE backward over the summed loss (as train.py:240), then the gradient all-reduce.

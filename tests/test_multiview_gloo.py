@@ -75,3 +75,58 @@ def test_grad_bucket_allreduce_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def _pair_loss(gens, reals):
+    """Stand-in for splatco_b200.loss.multiview_consistency_loss (the CUDA kernel) with the same pair structure."""
+    total = 0
+    for i in range(len(gens)):
+        for j in range(i + 1, len(gens)):
+            total = total + (0.5 + 0.1 * i + 0.01 * j) * ((reals[i] - reals[j]) - (gens[i] - gens[j])).abs().mean()
+    return total
+
+
+def _render(theta, i):
+    """A differentiable stand-in "renderer": view i's image as a function of the replicated parameter."""
+    g = torch.Generator().manual_seed(100 + i)
+    basis = torch.rand(3, 6, 7, generator=g)
+    return torch.sin(theta[0] * basis * (i + 1)) + theta[1] * basis
+
+
+def _worker_consistency(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from splatco_b200.multiview import GradBucket, gather_view_images, sharded_consistency_loss
+        mv = 5                                                     # uneven: rank 0 owns 3 views, rank 1 owns 2
+        g = torch.Generator().manual_seed(7)
+        reals = [torch.rand(3, 6, 7, generator=g) for _ in range(mv)]
+        theta = torch.nn.Parameter(torch.tensor([0.7, -0.3]))
+        # single-process answer
+        full = _pair_loss([_render(theta, i) for i in range(mv)], reals)
+        (want_grad,) = torch.autograd.grad(full, theta)
+        # sharded: own views only, all pairs through the gathered images
+        local = [_render(theta, i) for i in shard_views(mv, rank, world)]
+        gathered = gather_view_images(local, mv, rank, world)
+        ok = len(gathered) == mv
+        for i in range(mv):
+            ok &= torch.allclose(gathered[i], _render(theta, i).detach())
+            ok &= gathered[i].requires_grad == (owner_of_view(i, world) == rank)
+        loss = sharded_consistency_loss(local, reals, mv, rank, world, loss_fn=_pair_loss)
+        ok &= torch.allclose(loss.detach(), full.detach())          # the full sum on every rank
+        loss.backward()
+        GradBucket([theta]).allreduce()
+        ok &= torch.allclose(theta.grad, want_grad, rtol=1e-5, atol=1e-7)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_consistency_loss_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_consistency, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
