@@ -67,6 +67,26 @@ def _get_scaling(pc, remember):
     return value
 
 
+# pc.get_rotation = normalize(pc._rotation) is four launches per prefilter call on a tensor nothing in the render path
+# ever updates (anchor rotations receive no gradient); the normalised copy is kept for as long as the same tensor object
+# has the same version counter (any in-place update, e.g. an optimizer step, bumps it; densification replaces the object).
+_rotation_stash = {"src": None, "version": -1, "fn": None, "value": None}
+
+
+def _get_rotation(pc):
+    src = getattr(pc, "_rotation", None)
+    if src is None or not isinstance(src, torch.Tensor):
+        return pc.get_rotation              # (the prefilter is not differentiable: a detached copy serves it in any grad mode)
+    st = _rotation_stash
+    fn = getattr(pc, "rotation_activation", None)
+    held = st["src"]() if st["src"] is not None else None
+    if held is src and st["version"] == src._version and st["fn"] is fn and st["value"] is not None:
+        return st["value"]
+    value = pc.get_rotation
+    st.update(src=weakref.ref(src), version=src._version, fn=fn, value=value.detach())
+    return st["value"]
+
+
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, visible_mask=None,
            retain_grad=False):
     """Render the scene.  Background tensor (bg_color) must be on GPU!"""
@@ -121,7 +141,7 @@ def prefilter_voxel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_
         cov3D_precomp = pc.get_covariance(scaling_modifier)
     else:
         scales = _get_scaling(pc, remember=True)
-        rotations = pc.get_rotation
+        rotations = _get_rotation(pc)
     if cov3D_precomp is not None:
         radii_pure = rasterizer.visible_filter(means3D=means3D, scales=scales, rotations=rotations,
                                                cov3D_precomp=cov3D_precomp)          # raises (unsupported, see above)
