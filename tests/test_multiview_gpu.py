@@ -78,3 +78,48 @@ def test_two_ranks_sum_to_the_single_process_gradients(tmp_path):
         assert (a - b).abs().max().item() <= 2e-4 * scale + 1e-9, (tuple(b.shape), (a - b).abs().max().item(), scale)
         n += 1
     assert n >= 40
+
+
+# ---- cross-view consistency term, sharded (SURVEY §8e collective (2)) ---------------------------------------------
+def _images(theta, idx, H=40, W=56):
+    """Differentiable stand-in renders of views idx (functions of one replicated parameter) and all ground truths."""
+    g = torch.Generator().manual_seed(31)
+    base = torch.rand(3, H, W, generator=g)
+    reals, basis = [], []
+    for i in range(4):
+        reals.append(((base + 0.03 * torch.randn(3, H, W, generator=g)).clamp(0, 1) if i < 3 else torch.rand(3, H, W, generator=g)).cuda())
+        basis.append(torch.rand(3, H, W, generator=g).cuda())
+    gens = [(reals[i] + theta[0] * basis[i] + theta[1] * torch.sin(7.0 * basis[i])).clamp(0, 1) for i in idx]
+    return gens, reals
+
+
+def _worker_consistency(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from splatco_b200.multiview import GradBucket, shard_views, sharded_consistency_loss
+        theta = torch.nn.Parameter(torch.tensor([0.11, -0.04], device="cuda"))
+        gens, reals = _images(theta, shard_views(4, rank, world))
+        loss = sharded_consistency_loss(gens, reals, 4, rank, world)          # the CUDA kernel, all pairs, own views differentiated
+        loss.backward()
+        GradBucket([theta]).allreduce()
+        if rank == 0:
+            torch.save((loss.detach().cpu(), theta.grad.detach().cpu()), out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_consistency_loss_matches_single_process(tmp_path):
+    from splatco_b200.loss import multiview_consistency_loss
+    out = str(tmp_path / "c.pt")
+    mp.spawn(_worker_consistency, args=(2, _free_port(), out), nprocs=2, join=True)
+    got_loss, got_grad = torch.load(out)
+    theta = torch.nn.Parameter(torch.tensor([0.11, -0.04], device="cuda"))
+    gens, reals = _images(theta, range(4))
+    want = multiview_consistency_loss(gens, reals)
+    want.backward()
+    assert want.item() > 0
+    assert abs(got_loss.item() - want.item()) <= 1e-6 * abs(want.item())
+    assert torch.allclose(got_grad, theta.grad.cpu(), rtol=1e-4, atol=1e-9)
