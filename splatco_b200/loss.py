@@ -5,11 +5,16 @@
            with the reference's l1_loss / ssim (utils/loss_utils.py:17-18, 33-63; combined at train.py:192-196)
     l1_loss(a, b), ssim(a, b): the reference's names, evaluated by the same kernels.
 
+    scaling_reg(scaling)                                 == scaling.prod(dim=1).mean()   (train.py:195; no host sync in backward)
+    multiview_consistency_loss(gen_imgs, real_imgs, 0.6) == `muiti_con_loss` of train.py:199-216 (all view pairs, one pass)
+
 Two kernels forward, one backward in libsplatco_b200.so (csrc/loss.cu) instead of 5 cuDNN grouped convolutions and
 ~15 elementwise launches each way; the backward writes dL/dimage, which is what the blend backward consumes.
 Gradients flow to `image` only (the ground truth never requires grad in train.py); no CPU fallback.
 """
 from __future__ import annotations
+
+import ctypes as _C
 
 import torch
 
@@ -114,8 +119,6 @@ def scaling_reg(scaling):
 
 
 # ---- cross-view consistency term of the mv batch (train.py:199-216, summed in at :237-239) ----------------------
-import ctypes as _C
-
 
 def _pair_list(n):
     return [(i, j) for i in range(n) for j in range(i + 1, n)]
