@@ -14,6 +14,9 @@ Mirrors (file:line in /root/reference):
   scene/gaussian_model.py:97-147   FeaturePlanes (k0s = [TA@P/4, P/4, P/2, P], models, CTX_models)
   scene/gaussian_model.py:183-215  GaussianLearner (Q0, _feat, bbox [-2,2]^3)
   scene/gaussian_model.py:307-337  MLP heads;  :403-441 accessors
+  scene/gaussian_model.py:510-572  training_setup (statistics + Adam parameter groups), :733-758 / :784-830 the optimizer
+                                   bookkeeping of growing / pruning anchors — so the densification drop-ins
+                                   (splatco_b200.densify) can be exercised end to end without the reference tree
 """
 from __future__ import annotations
 
@@ -186,6 +189,97 @@ class AnchorModel:
     @property
     def get_appearance(self):
         return self.embedding_appearance
+
+    # ---- training-side bookkeeping (what densify.anchor_growing / adjust_anchor and statis.training_statis touch) ----
+    PER_ANCHOR = ("anchor", "offset", "anchor_feat", "opacity", "scaling", "rotation")
+    _SKIP = ("mlp", "conv", "feat_base", "embedding", "feat_planes")
+
+    def training_setup(self, voxel_size=0.01, update_depth=3, update_init_factor=16, update_hierachy_factor=4, fused=True):
+        """Statistics and Adam parameter groups as GaussianModel.training_setup creates them (scene/gaussian_model.py:510-572;
+        learning rates = arguments/__init__.py defaults), with splatco_b200.optim.FusedAdam (or torch.optim.Adam)."""
+        dev, N = self._anchor.device, int(self._anchor.shape[0])
+        self.voxel_size, self.update_depth = voxel_size, update_depth
+        self.update_init_factor, self.update_hierachy_factor = update_init_factor, update_hierachy_factor
+        if not hasattr(self, "_opacity"):
+            self._opacity = nn.Parameter(torch.full((N, 1), -2.1972246, device=dev), requires_grad=False)   # inverse_sigmoid(0.1)
+        self.opacity_accum = torch.zeros(N, 1, device=dev)
+        self.anchor_demon = torch.zeros(N, 1, device=dev)
+        self.offset_gradient_accum = torch.zeros(N * self.n_offsets, 1, device=dev)
+        self.offset_denom = torch.zeros(N * self.n_offsets, 1, device=dev)
+        self.max_radii2D = torch.zeros(N, device=dev)
+        groups = [{"params": [self._anchor], "lr": 0.0, "name": "anchor"}, {"params": [self._offset], "lr": 0.01, "name": "offset"},
+                  {"params": [self._anchor_feat], "lr": 0.0075, "name": "anchor_feat"}, {"params": [self._opacity], "lr": 0.02, "name": "opacity"},
+                  {"params": [self._scaling], "lr": 0.007, "name": "scaling"}, {"params": [self._rotation], "lr": 0.002, "name": "rotation"},
+                  {"params": list(self.mlp_opacity.parameters()), "lr": 0.002, "name": "mlp_opacity"},
+                  {"params": list(self.mlp_cov.parameters()), "lr": 0.004, "name": "mlp_cov"},
+                  {"params": list(self.mlp_color.parameters()), "lr": 0.008, "name": "mlp_color"}]
+        if self.embedding_appearance is not None:
+            groups.append({"params": list(self.embedding_appearance.parameters()), "lr": 0.05, "name": "embedding_appearance"})
+        feat = self.feat_planes._feat
+        for i in range(3):
+            active = i == feat.activate_level
+            groups.append({"params": list(feat.k0s[i].parameters()), "lr": 0.01 if active else 0.001, "name": f"feat_planes{i}"})
+            groups.append({"params": list(feat.models[i].parameters()), "lr": 1e-4 if active else 1e-5, "name": f"fp_mlp_f{i}"})
+        if fused:
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
+        else:
+            self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        return self.optimizer
+
+    def _swap_rows(self, new_rows):
+        """Replace the per-anchor Parameters (and their Adam moments) by `new_rows[name](old tensor)`."""
+        out = {}
+        for group in self.optimizer.param_groups:
+            if any(k in group["name"] for k in self._SKIP):
+                continue
+            old = group["params"][0]
+            state = self.optimizer.state.pop(old, None)
+            fn = new_rows[group["name"]]
+            new = nn.Parameter(fn(old.detach(), False), requires_grad=old.requires_grad)
+            if state is not None and len(state) > 0:
+                state["exp_avg"] = fn(state["exp_avg"], True)
+                state["exp_avg_sq"] = fn(state["exp_avg_sq"], True)
+                self.optimizer.state[new] = state
+            group["params"][0] = new
+            out[group["name"]] = new
+        self._anchor, self._offset, self._anchor_feat = out["anchor"], out["offset"], out["anchor_feat"]
+        self._opacity, self._scaling, self._rotation = out["opacity"], out["scaling"], out["rotation"]
+        return out
+
+    def cat_tensors_to_optimizer(self, tensors_dict):
+        """scene/gaussian_model.py:733-758: append rows to every per-anchor Parameter; their Adam moments get zero rows."""
+        def rows(name):
+            ext = tensors_dict[name]
+            return lambda t, is_moment: torch.cat([t, torch.zeros_like(ext) if is_moment else ext.to(t.dtype)], dim=0)
+        return self._swap_rows({n: rows(n) for n in self.PER_ANCHOR})
+
+    def prune_anchor(self, mask):
+        """scene/gaussian_model.py:784-830: drop the masked anchors (and their moments); the reference also clamps the
+        kept rows' scaling[:, 3:] at 0.05 here (:796-800), reproduced because the decode reads those columns."""
+        keep = ~mask
+
+        def rows(name):
+            def fn(t, is_moment):
+                t = t[keep]
+                if name == "scaling" and not is_moment:
+                    t = t.clone()
+                    t[:, 3:] = t[:, 3:].clamp(max=0.05)
+                return t
+            return fn
+        return self._swap_rows({n: rows(n) for n in self.PER_ANCHOR})
+
+    def training_statis(self, viewspace_point_tensor, opacity, update_filter, offset_selection_mask, anchor_visible_mask):
+        from .statis import training_statis
+        return training_statis(self, viewspace_point_tensor, opacity, update_filter, offset_selection_mask, anchor_visible_mask)
+
+    def anchor_growing(self, grads, threshold, offset_mask):
+        from .densify import anchor_growing
+        return anchor_growing(self, grads, threshold, offset_mask)
+
+    def adjust_anchor(self, iteration, check_interval=100, success_threshold=0.8, grad_threshold=0.0002, min_opacity=0.005):
+        from .densify import adjust_anchor
+        return adjust_anchor(self, iteration, check_interval, success_threshold, grad_threshold, min_opacity)
 
     def eval(self):           # scene/gaussian_model.py:350-357: MLP heads only; feat_planes stays in train mode
         self.mlp_opacity.eval(); self.mlp_cov.eval(); self.mlp_color.eval()
