@@ -76,3 +76,21 @@ def test_rasterizer_refuses_cpu_tensors():
     with pytest.raises(Exception, match="excatly one"):
         r(means3D=torch.zeros(4, 3), means2D=torch.zeros(4, 3), shs=None, colors_precomp=None,
           opacities=torch.zeros(4, 1), scales=torch.ones(4, 3), rotations=torch.ones(4, 4), cov3D_precomp=None)
+
+
+def test_argument_validation_of_the_training_loop_entry_points():
+    """Bad sizes / null pointers are refused with a message before any device work (so this runs without a GPU)."""
+    L = _lib.lib()
+    err = lambda: L.splatco_last_error().decode()
+    assert L.splatco_tv_add_grad(0, 4, 4, None, None, 1.0, None) < 0 and "tv_add_grad" in err()
+    assert L.splatco_tv_add_grad(5, 4, 4, None, None, 1.0, None) < 0 and "null pointer" in err()
+    assert L.splatco_scaling_reg_fwd(0, None, None, None, None) < 0 and "at least one row" in err()
+    assert L.splatco_mv_consistency_fwd(1, 3, None, None, None, None, None, 0.6, None, None, None) < 0 and "views supported" in err()
+    assert L.splatco_mv_consistency_fwd(9, 3, None, None, None, None, None, 0.6, None, None, None) < 0 and "views supported" in err()
+    assert L.splatco_grow_count(-1, None, None, 0.0, None, None, 0.0, None, None) < 0 and "bad slot count" in err()
+    assert L.splatco_grow_count(10, None, None, 0.0, None, None, 0.0, None, None) < 0 and "cand_mask" in err()
+    assert L.splatco_grow_emit(10, 32, 0.1, 5, 6, None, None, None, None, None) < 0 and "bad sizes" in err()
+    assert L.splatco_cvpm_mask(-1, None, None, None, None, 0.6, 0.01, 3.0, 0.5, None, None, None, None) < 0 and "bad N" in err()
+    assert L.splatco_adam_step(-1, None, 0.9, 0.999, 1e-15, None) < 0 and "bad tensor list" in err()
+    assert L.splatco_adam_step(0, None, 0.9, 0.999, 1e-15, None) == 0            # nothing to update is not an error
+    assert L.splatco_mv_consistency_ws_bytes(4) >= 6 * 8 + 6 * 4 and L.splatco_grow_ws_bytes(1000) >= 1000 * (4 + 12 + 4 + 4 + 1 + 24)
