@@ -465,9 +465,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--level", type=int, default=2, choices=[0, 1, 2],
+                    help="activate_level of the feature planes: 2 = steady state after iteration 21 000 (default, the headline), "
+                         "0 = the first 12 000 iterations (train.py:305-307, SURVEY §8d times both)")
     ap.add_argument("--torch-scaling-reg", action="store_true",
                     help="scaling regulariser with torch ops as train.py:195 writes it (its prod backward syncs with the host every view)")
     args = ap.parse_args()
+    global LEVEL
+    LEVEL = args.level
     if args.impl == "reference":
         run_reference(args)
     else:
