@@ -95,6 +95,10 @@ int splatco_preprocess_fwd_counted(int P_max, const int32_t *P_dev, const float 
                                    int H, int W, int32_t *radii_out, void *geom,
                                    int32_t *num_rendered_host, void *stream);
 
+/* 1 when splatco_binning(P, R, H, W) will take the tile-segmented path, for which R may be an upper bound on the
+ * instance count (a capacity: all writes are clamped to it).  0: the call falls back to the radix composition
+ * (splatco_binning_radix), which needs the exact R -- do not pass a guessed capacity then. */
+int splatco_binning_accepts_capacity(int P, int64_t R, int H, int W);
 /* ---- forward, stage 2: the sorted per-tile instance lists ------------------------------------
  * Produces what upstream's duplicateWithKeys + stable 64-bit SortPairs + identifyTileRanges produce:
  * sorted keys (tile << 32 | depth bits), the sorted Gaussian-id list and the per-tile ranges, bit for
@@ -198,6 +202,12 @@ size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level);
  * M_host (pinned) asynchronously if not NULL). */
 int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
                        int32_t *M_host, void *stream);
+/* Two implementations sit behind the decode entry points: 1 = the three-stage chain (geo -> hidden -> heads), 2 = the
+ * collapsed two-stage pipeline (default for plane grids with <= 5 channels per plane; csrc/decode2.cuh).  The choice
+ * is process-wide, must not change between a forward and its backward, and is meant for A/B timing and debugging
+ * (environment: SPLATCO_DECODE_IMPL=1|2). */
+int splatco_decode_set_impl(int impl);
+int splatco_decode_get_impl(void);
 /* Device address (inside ws) of the survivor count M that splatco_decode_fwd leaves behind. */
 const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level);
 /* Stage 2: stable compaction + post-processing into the M surviving Gaussians.  M is only tested for
@@ -339,6 +349,13 @@ int splatco_adam_step(int n_tensors, const splatco_adam_tensor *tensors, double 
  * descriptor convention (expected to be wrong), bit1: single-pass TF32.  Used by tests/test_tc_gpu.py. */
 int splatco_tc_gemm_selftest(int M, int N, int K, const float *A, const float *B, float *C, int variant,
                              void *stream);
+
+
+/* Self-test of the MN-major (transposed-operand) tcgen05 path used by the decode backward's weight-gradient
+ * products: C[m][n] = sum_k At[k][m] * Bt[k][n], At [128][128], Bt [128][N], C [128][N], N <= 96.
+ * variant bits: 0 A read as an MN-major tile, 1 B read as an MN-major tile (otherwise transposed into K-major tiles by
+ * the threads), 2 LBO/SBO roles swapped, 3 single-pass TF32, [4,7) descriptor layout type, 7 unused stride = 0. */
+int splatco_tc_wgrad_selftest(int N, const float *At, const float *Bt, float *C, int variant, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,11 +27,16 @@ _ALIGN = 64           # floats (256 bytes): every carved buffer keeps the alignm
 
 
 _last = {}            # device index -> flat buffers of the most recent finished backward pass
+_arena = {}           # device index -> {cur: flat being carved, used: floats taken from it, total: floats carved this pass}
+_arena_size = {}      # device index -> floats the previous pass carved (sizes the next pass's single allocation)
 
 
 def _end_of_pass(index):
     with _lock:
         table = _passes.pop(index, None)
+        arena = _arena.pop(index, None)
+        if arena is not None:
+            _arena_size[index] = arena["total"]
         if table is not None:
             seen, flats = set(), []
             for flat, _, _ in table.values():
@@ -86,14 +91,31 @@ def acquire(device, requests, want_views=False):
             todo.append((n, key, shape, total, numel))
             total += (numel + _ALIGN - 1) // _ALIGN * _ALIGN
     if todo:
-        flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)      # ONE fill kernel
-        base = flat.data_ptr()
+        # ONE zero-filled allocation per backward pass (sized from what the previous pass carved): the decode nodes, the
+        # TriPlaneAttention backward and the plane unpacking all carve from it, so a multi-GPU caller all-reduces one
+        # buffer with one collective (multiview.GradBucket) and the pass pays one fill kernel
+        total = max(total, 1)
+        in_pass = index in _passes
+        arena = _arena.get(index) if in_pass else None
+        if arena is not None and arena["used"] + total <= arena["cur"].numel():
+            flat, start = arena["cur"], arena["used"]
+        else:
+            want = max(total, _arena_size.get(index, 0)) if (in_pass and arena is None) else total
+            flat, start = torch.zeros(want, dtype=torch.float32, device=device), 0
+            if in_pass:
+                if arena is None:
+                    arena = _arena[index] = {"cur": flat, "used": 0, "total": 0}
+                arena["cur"], arena["used"] = flat, 0
+        if arena is not None:
+            arena["used"] = start + total
+            arena["total"] += total
+        base = flat.data_ptr() + 4 * start
         # all views with one split call (a slice + view pair per tensor costs ~5 us, there are ~50 of them)
-        bounds = [off for _, _, _, off, _ in todo] + [max(total, 1)]
-        pieces = flat.split_with_sizes([b - a for a, b in zip(bounds[:-1], bounds[1:])])
+        bounds = [off for _, _, _, off, _ in todo] + [total]
+        pieces = flat[start:start + total].split_with_sizes([b - a for a, b in zip(bounds[:-1], bounds[1:])])
         for (n, key, shape, off, numel), piece in zip(todo, pieces):
             buf = (piece if piece.numel() == numel else piece[:numel]).view(shape)
             out[n] = (base + 4 * off, buf, buf) if want_views else (base + 4 * off, buf)
             if key is not None:
-                table[key] = (flat, off, numel)
+                table[key] = (flat, start + off, numel)
     return out

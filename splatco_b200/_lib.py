@@ -34,6 +34,7 @@ SIGNATURES = {
     "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd_counted": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_binning": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_binning_accepts_capacity": (_i, [_i, _i64, _i, _i]),
     "splatco_binning_radix": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "splatco_duplicate_with_keys": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_sort_pairs": (_i, [_i64, _i, _i, _vp, _vp]),
@@ -47,6 +48,8 @@ SIGNATURES = {
     "splatco_decode_fwd_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_decode_bwd_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_decode_count_ptr": (_vp, [_vp, _i, _i, _i]),
+    "splatco_decode_set_impl": (_i, [_i]),
+    "splatco_decode_get_impl": (_i, []),
     "splatco_decode_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -72,6 +75,7 @@ SIGNATURES = {
     "splatco_adam_step": (_i, [_i, _vp, C.c_double, C.c_double, C.c_double, _vp]),
     "splatco_training_statis": (_i, [_i, _i] + [_vp] * 11),
     "splatco_tc_gemm_selftest": (_i, [_i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "splatco_tc_wgrad_selftest": (_i, [_i, _vp, _vp, _vp, _i, _vp]),
 }
 
 

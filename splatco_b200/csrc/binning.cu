@@ -671,6 +671,17 @@ extern "C" int splatco_binning_radix(int P, int64_t R, int H, int W, const int32
     return 0;
 }
 
+// 1 when splatco_binning(P, R, H, W) takes the tile-segmented path, whose R may be a CAPACITY (every write is clamped
+// to it); 0 when it falls back to the radix composition, which needs the exact instance count.
+static bool tile_path(int P, int64_t R, int H, int W) {
+    const int T = ceil_div(W, TILE) * ceil_div(H, TILE);
+    const size_t hist_bytes = (size_t)T * sizeof(uint32_t);
+    return !((size_t)ceil_div(P, TCHUNK) * hist_bytes > (size_t)R * sizeof(uint32_t) || hist_bytes > 200 * 1024);
+}
+extern "C" int splatco_binning_accepts_capacity(int P, int64_t R, int H, int W) {
+    return (P > 0 && R > 0 && H > 0 && W > 0 && tile_path(P, R, H, W)) ? 1 : 0;
+}
+
 extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *radii, const void *geom,
                                void *binning, void *image, void *stream) {
     if (check_R(R)) return -1;
@@ -690,7 +701,9 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     const int s = splatco_sorted_buffer_index(H, W);
     // the per-chunk histogram rows live in the value buffer that is not the sorted output (4 B*R): fall back to the
     // radix composition when they do not fit there or the tile histogram does not fit in shared memory
-    if ((size_t)nchunks * hist_bytes > (size_t)R * sizeof(uint32_t) || hist_bytes > 200 * 1024)
+    // (that path treats R as the EXACT instance count: callers that pass a capacity must ask
+    // splatco_binning_accepts_capacity first -- diff_gaussian_rasterization does)
+    if (!tile_path(P, R, H, W))
         return splatco_binning_radix(P, R, H, W, radii, geom, binning, image, stream);
     GeomWs g = geom_view(const_cast<void *>(geom), P);
     uint32_t *chunk_hist = b.vals[s ^ 1];

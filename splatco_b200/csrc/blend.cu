@@ -5,7 +5,7 @@
 // One CTA per 16x16 tile, one thread per pixel; warps cover 8x4-pixel patches.  ncu showed the first
 // version of these kernels to be instruction-issue bound (81 % issue-active, DRAM < 1 % of peak), so
 // the design goal is the fewest instructions per (pixel, splat) pair:
-//  * splats are staged through shared memory in batches of 256; the staging thread precomputes, once
+//  * splats are staged through shared memory in batches of 512 (two per thread); the staging thread precomputes, once
 //    per (tile, splat), the conic pre-scaled into the log2 domain (P2 = log2(e) * power, evaluated from
 //    (dx, dy) exactly like the reference so threshold decisions keep full fp32 precision) and
 //    log2(opacity), which is folded into the exponent so the alpha >= 1/255 cut is a compare BEFORE the
@@ -15,10 +15,10 @@
 //    set bits, in list order — semantics per pixel are unchanged (a culled splat has alpha < 1/255 on
 //    every pixel of the patch and would have been skipped);
 //  * a warp leaves as soon as all its pixels are saturated, the CTA when every warp has.
-// Backward: same staging / culling / skip decisions (bit-identical exponent), gradients of the 9
-// per-splat scalars are reduced across the warp with a transposed butterfly (14 shuffles instead of
-// 45), accumulated per CTA in shared memory and flushed with ONE global RED per scalar per
-// (tile, splat) — 256x fewer global atomics than per-pixel atomics.
+// Backward: same staging / culling / skip decisions (bit-identical exponent).  Per (pixel, splat) the lanes form the
+// six moments of D = dL/dG * G about the splat centre and three colour terms; each warp parks the 9 partials of a visit
+// column-wise in its own shared-memory transposition buffer and, every third visit, sums the 27 rows with 16-byte
+// loads and issues ONE global RED per sum -- 32x fewer global atomics than per-pixel atomics, no shuffle butterfly.
 #include "common.cuh"
 
 namespace splatco {
@@ -182,35 +182,6 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
 }
 
 // ---- backward ---------------------------------------------------------------------------------------
-// Transposed butterfly: every lane enters with 8 values g[0..7]; on return lanes with (lane & 3) == 0
-// hold in `r` the warp-wide sum of value index ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
-__device__ __forceinline__ float warp_reduce8(const float (&g)[8], int lane) {
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    float w4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b4 ? g[i] : g[i + 4];
-        const float keep = b4 ? g[i + 4] : g[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    float w2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b3 ? w4[i] : w4[i + 2];
-        const float keep = b3 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    float r = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    return v;
-}
-
 __device__ __forceinline__ float4 lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));

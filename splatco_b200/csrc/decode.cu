@@ -896,6 +896,7 @@ dec_bwd_inputs_kernel(DecPtrs p, DecInputGrads gi, int V, int rc, int DP, int LD
 }
 
 }  // namespace splatco
+#include "decode2.cuh"
 
 using namespace splatco;
 
@@ -1006,21 +1007,21 @@ int gather_grid(int V) { return min(ceil_div(V, GATHER_WARPS), 148 * 8); }
 
 }  // namespace
 
-extern "C" size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level) {
+static size_t v1_decode_fwd_ws_bytes(int V, int rc, int level) {
     size_t off[F_NCHUNK + 1];
     return dec_fwd_offsets(dec_dims(V, rc, level), off);
 }
-extern "C" size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level) {
+static size_t v1_decode_bwd_ws_bytes(int V, int rc, int level) {
     size_t off[B_NCHUNK + 1];
     return dec_bwd_offsets(dec_dims(V, rc, level), off);
 }
 
-extern "C" const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level) {
+static const int32_t *v1_decode_count_ptr(const void *ws, int V, int rc, int level) {
     if (!ws) return nullptr;
     return reinterpret_cast<const int32_t *>(fwd_view(const_cast<void *>(ws), dec_dims(V, rc, level)).total);
 }
 
-extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
+static int v1_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
                                   int32_t *M_host, void *stream) {
     if (check_desc(d)) return -1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1076,7 +1077,7 @@ extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float 
     return 0;
 }
 
-extern "C" int splatco_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
+static int v1_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
                                    float *opacity, float *scaling, float *rot, void *stream) {
     if (check_desc(d)) return -1;
     if (d->V == 0 || M == 0) return 0;
@@ -1089,7 +1090,7 @@ extern "C" int splatco_decode_emit(const splatco_decode_desc *d, const void *ws,
     return 0;
 }
 
-extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M,
+static int v1_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M,
                                   const float *d_xyz, const float *d_color, const float *d_opacity,
                                   const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
                                   const splatco_decode_grads *g, void *stream) {
@@ -1246,4 +1247,229 @@ extern "C" int splatco_unpack_planes_add(int rc, int E, const float *gpxy, const
                                                                                                           gxy, gxz, gyz);
     SPLATCO_CHECK_LAUNCH();
     return 0;
+}
+
+// =====================================================================================================================
+// v2 host side (decode2.cuh) and the dispatch between the two implementations.
+//   v2: plane grids with at most 5 channels per plane (num_channels <= 15, the reference's configurations)
+//   v1: everything else, or when forced with splatco_decode_set_impl(1) / SPLATCO_DECODE_IMPL=1 (A/B timing, debugging)
+// =====================================================================================================================
+namespace {
+
+int g_decode_impl = 0;      // 0: not read yet, 1: v1, 2: v2
+int decode_impl() {
+    if (!g_decode_impl) {
+        const char *e = getenv("SPLATCO_DECODE_IMPL");
+        g_decode_impl = (e && e[0] == '1') ? 1 : 2;
+    }
+    return g_decode_impl;
+}
+bool use_v2(int rc) { return decode_impl() == 2 && rc >= 1 && rc <= 5; }
+
+enum F2Chunk { G_STATS, G_MU, G_RSTD, G_WPT, G_WCT, G_BGEO, G_W1T, G_B1E, G_W2T, G_B2, G_WPG, G_WCG, G_XT, G_HT, G_ZT,
+               G_MASKBITS, G_OFFS, G_BSUM, G_BOFF, G_TOTAL, G_W1S, G_W1R, G_W2B, G_B2BLK, G_W2R, G_NCHUNK };
+
+size_t d2_fwd_offsets(const D2Dims &d, size_t off[G_NCHUNK + 1]) {
+    const size_t V = (size_t)(d.V > 0 ? d.V : 0);
+    const size_t nb = (V + 255) / 256, nt = (size_t)d.ntiles;
+    size_t o = 0;
+    auto put = [&](int c, size_t bytes) { off[c] = o; o += align_up(bytes); };
+    put(G_STATS, 2 * (size_t)d.LDX * 8);
+    put(G_MU, d.LDX * 4); put(G_RSTD, d.LDX * 4);
+    put(G_WPT, DEC_MAX_DP * 32 * 4); put(G_WCT, GD * 32 * 4); put(G_BGEO, 64 * 4);
+    put(G_W1T, XI * HD * 4); put(G_B1E, HD * 4);
+    put(G_W2T, HD * ZD * 4); put(G_B2, ZD * 4);
+    put(G_WPG, 32 * DEC_MAX_DP * 4); put(G_WCG, 32 * GD * 4);
+    put(G_XT, nt * d.nch * D2_CHUNK); put(G_HT, nt * 24 * D2_CHUNK); put(G_ZT, nt * D2_ZCH * D2_CHUNK);
+    put(G_MASKBITS, V * 4); put(G_OFFS, V * 4); put(G_BSUM, nb * 4); put(G_BOFF, nb * 4); put(G_TOTAL, 4);
+    put(G_W1S, 3 * (size_t)d.nk * 32 * 16 * 2); put(G_W1R, 2 * 24 * (size_t)d.NB * 16);
+    put(G_W2B, 2 * D2_W2B_HALF); put(G_B2BLK, 128 * 4); put(G_W2R, 2 * D2_W2R_HALF);
+    off[G_NCHUNK] = o;
+    return o;
+}
+
+struct F2View {
+    double *stats;
+    float *mu, *rstd, *WpT, *WcT, *bgeo, *W1T, *b1e, *W2T, *b2, *WpG, *WcG, *b2blk;
+    float4 *XT, *HT, *ZT;
+    uint32_t *maskbits, *offs, *bsum, *boff, *total;
+    uint8_t *W1S, *W1R, *W2B, *W2R;
+};
+F2View f2_view(void *ws, const D2Dims &d) {
+    size_t off[G_NCHUNK + 1];
+    d2_fwd_offsets(d, off);
+    char *b = (char *)ws;
+    F2View v;
+    v.stats = (double *)(b + off[G_STATS]);
+    v.mu = (float *)(b + off[G_MU]); v.rstd = (float *)(b + off[G_RSTD]);
+    v.WpT = (float *)(b + off[G_WPT]); v.WcT = (float *)(b + off[G_WCT]); v.bgeo = (float *)(b + off[G_BGEO]);
+    v.W1T = (float *)(b + off[G_W1T]); v.b1e = (float *)(b + off[G_B1E]);
+    v.W2T = (float *)(b + off[G_W2T]); v.b2 = (float *)(b + off[G_B2]);
+    v.WpG = (float *)(b + off[G_WPG]); v.WcG = (float *)(b + off[G_WCG]);
+    v.XT = (float4 *)(b + off[G_XT]); v.HT = (float4 *)(b + off[G_HT]); v.ZT = (float4 *)(b + off[G_ZT]);
+    v.maskbits = (uint32_t *)(b + off[G_MASKBITS]); v.offs = (uint32_t *)(b + off[G_OFFS]);
+    v.bsum = (uint32_t *)(b + off[G_BSUM]); v.boff = (uint32_t *)(b + off[G_BOFF]); v.total = (uint32_t *)(b + off[G_TOTAL]);
+    v.W1S = (uint8_t *)(b + off[G_W1S]); v.W1R = (uint8_t *)(b + off[G_W1R]);
+    v.W2B = (uint8_t *)(b + off[G_W2B]); v.b2blk = (float *)(b + off[G_B2BLK]); v.W2R = (uint8_t *)(b + off[G_W2R]);
+    return v;
+}
+
+enum B2Chunk { H_DUT, H_PART, H_RED, H_GB2BLK, H_GW2T, H_GB2, H_GW1T, H_GB1, H_S1, H_S0, H_M1, H_M2, H_NCHUNK };
+constexpr int D2_MAX_CTAS = 148;
+
+size_t d2_bwd_offsets(const D2Dims &d, size_t off[H_NCHUNK + 1]) {
+    size_t o = 0;
+    auto put = [&](int c, size_t bytes) { off[c] = o; o += align_up(bytes); };
+    put(H_DUT, (size_t)d.ntiles * d.nch * D2_CHUNK);
+    put(H_PART, (size_t)D2_MAX_CTAS * D2_PART * 4); put(H_RED, (size_t)D2_PART * 4); put(H_GB2BLK, 128 * 4);
+    put(H_GW2T, HD * ZD * 4); put(H_GB2, ZD * 4); put(H_GW1T, XI * HD * 4); put(H_GB1, HD * 4);
+    put(H_S1, 32 * (size_t)d.LDX * 4); put(H_S0, 64 * 4); put(H_M1, d.LDX * 4); put(H_M2, d.LDX * 4);
+    off[H_NCHUNK] = o;
+    return o;
+}
+struct B2View { float4 *DUT; float *part, *red, *gb2blk, *gW2T, *gb2, *gW1T, *gb1, *S1, *S0, *m1, *m2; };
+B2View b2_view(void *ws, const D2Dims &d) {
+    size_t off[H_NCHUNK + 1];
+    d2_bwd_offsets(d, off);
+    char *b = (char *)ws;
+    B2View v;
+    v.DUT = (float4 *)(b + off[H_DUT]); v.part = (float *)(b + off[H_PART]); v.red = (float *)(b + off[H_RED]);
+    v.gb2blk = (float *)(b + off[H_GB2BLK]);
+    v.gW2T = (float *)(b + off[H_GW2T]); v.gb2 = (float *)(b + off[H_GB2]); v.gW1T = (float *)(b + off[H_GW1T]);
+    v.gb1 = (float *)(b + off[H_GB1]); v.S1 = (float *)(b + off[H_S1]); v.S0 = (float *)(b + off[H_S0]);
+    v.m1 = (float *)(b + off[H_M1]); v.m2 = (float *)(b + off[H_M2]);
+    return v;
+}
+
+template <int LEVEL, int RC>
+int launch_gather2(bool packed, cudaStream_t st, const DecPtrs &p, const D2Dims &d, float4 *XT, double *stats) {
+    if (packed) dec2_gather_kernel<LEVEL, RC, true><<<d.ntiles, D2_ROWS, 0, st>>>(p, d.V, d.LDX, XT, stats);
+    else dec2_gather_kernel<LEVEL, RC, false><<<d.ntiles, D2_ROWS, 0, st>>>(p, d.V, d.LDX, XT, stats);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+template <int LEVEL, int RC>
+int launch_inputs2(bool packed, cudaStream_t st, const DecPtrs &p, const DecInputGrads &gi, const D2Dims &d, const float4 *XT,
+                   const float4 *DUT, const float *mu, const float *rstd, const float *m1, const float *m2) {
+    if (packed) dec2_bwd_inputs_kernel<LEVEL, RC, true><<<d.ntiles, D2_ROWS, 0, st>>>(p, gi, d.V, XT, DUT, mu, rstd, m1, m2);
+    else dec2_bwd_inputs_kernel<LEVEL, RC, false><<<d.ntiles, D2_ROWS, 0, st>>>(p, gi, d.V, XT, DUT, mu, rstd, m1, m2);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+#define D2_DISPATCH(FN, level, rc, ...)                                                                      \
+    [&]() -> int {                                                                                           \
+        switch ((level) * 8 + (rc)) {                                                                        \
+            case 1: return FN<0, 1>(__VA_ARGS__); case 2: return FN<0, 2>(__VA_ARGS__);                      \
+            case 3: return FN<0, 3>(__VA_ARGS__); case 4: return FN<0, 4>(__VA_ARGS__);                      \
+            case 5: return FN<0, 5>(__VA_ARGS__);                                                            \
+            case 9: return FN<1, 1>(__VA_ARGS__); case 10: return FN<1, 2>(__VA_ARGS__);                     \
+            case 11: return FN<1, 3>(__VA_ARGS__); case 12: return FN<1, 4>(__VA_ARGS__);                    \
+            case 13: return FN<1, 5>(__VA_ARGS__);                                                           \
+            case 17: return FN<2, 1>(__VA_ARGS__); case 18: return FN<2, 2>(__VA_ARGS__);                    \
+            case 19: return FN<2, 3>(__VA_ARGS__); case 20: return FN<2, 4>(__VA_ARGS__);                    \
+            case 21: return FN<2, 5>(__VA_ARGS__);                                                           \
+        }                                                                                                    \
+        splatco::set_error("decode v2: unsupported level %d / channels per plane %d", (level), (rc));        \
+        return -1;                                                                                           \
+    }()
+
+int v2_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask, int32_t *M_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->V == 0) { if (M_host) *M_host = 0; return 0; }
+    SPLATCO_REQUIRE(d->V >= 2, "decode: BatchNorm in train mode needs more than 1 visible anchor (got %d)", d->V);
+    SPLATCO_REQUIRE(ws && neural_opacity && mask, "decode_fwd: null pointer");
+    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    F2View f = f2_view(ws, dd);
+    const DecPtrs p = make_ptrs(d);
+    const DecWeights w = make_weights(d);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.stats, 0, 2 * (size_t)dd.LDX * sizeof(double), st));
+    if (D2_DISPATCH(launch_gather2, dd.level, dd.rc, d->plane_layout != 0, st, p, dd, f.XT, f.stats)) return -2;
+    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
+                                              f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
+    SPLATCO_CHECK_LAUNCH();
+    dec2_combine_kernel<<<24, 256, 0, st>>>(dd.DP, dd.nk, dd.NB, f.WpT, f.WcT, f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.W1S, f.W1R,
+                                            f.W2B, f.b2blk, f.W2R);
+    SPLATCO_CHECK_LAUNCH();
+    const int nb = ceil_div(dd.V, 256);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.bsum, 0, (size_t)nb * sizeof(uint32_t), st));
+    static unsigned char attr_dev[64];
+    const int attr_i = current_device() & 63;
+    if (!attr_dev[attr_i]) {
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec2_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2F_SMEM));
+        attr_dev[attr_i] = 1;
+    }
+    D2Fwd a;
+    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.ntiles = dd.ntiles;
+    a.XT = f.XT; a.W1S = f.W1S; a.W2B = f.W2B; a.b2blk = f.b2blk; a.HT = f.HT; a.ZT = f.ZT;
+    a.nopac = neural_opacity; a.mask_out = mask; a.maskbits = f.maskbits; a.block_sums = f.bsum;
+    dec2_mlp_fwd_kernel<<<min(dd.ntiles, D2_MAX_CTAS), D2_THREADS, D2F_SMEM, st>>>(a);
+    SPLATCO_CHECK_LAUNCH();
+    scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
+    SPLATCO_CHECK_LAUNCH();
+    dec_offsets_kernel<<<nb, 256, 0, st>>>(dd.V, f.maskbits, f.boff, f.offs);
+    SPLATCO_CHECK_LAUNCH();
+    if (M_host) SPLATCO_CHECK_CUDA(cudaMemcpyAsync(M_host, f.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int v2_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color, float *opacity,
+                   float *scaling, float *rot, void *stream) {
+    if (d->V == 0 || M == 0) return 0;
+    SPLATCO_REQUIRE(ws && xyz && color && opacity && scaling && rot, "decode_emit: null pointer");
+    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    F2View f = f2_view(const_cast<void *>(ws), dd);
+    dec2_compact_kernel<<<ceil_div(d->V * KO, 256), 256, 0, (cudaStream_t)stream>>>(d->V, dd.nch, f.XT, f.ZT, f.maskbits, f.offs,
+                                                                                 xyz, color, opacity, scaling, rot);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+#include "decode2_bwd.cuh"
+
+extern "C" int splatco_decode_set_impl(int impl) {
+    SPLATCO_REQUIRE(impl == 1 || impl == 2, "decode_set_impl: 1 (three-stage chain) or 2 (collapsed two-stage pipeline)");
+    g_decode_impl = impl;
+    return 0;
+}
+extern "C" int splatco_decode_get_impl(void) { return decode_impl(); }
+
+// workspaces are sized for whichever implementation is larger, so the choice may change between calls
+extern "C" size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level) {
+    size_t off[G_NCHUNK + 1];
+    const size_t a = v1_decode_fwd_ws_bytes(V, rc, level);
+    const size_t b = (rc >= 1 && rc <= 5 && level >= 0 && level <= 2) ? d2_fwd_offsets(d2_dims(V, rc, level), off) : 0;
+    return a > b ? a : b;
+}
+extern "C" size_t splatco_decode_bwd_ws_bytes(int V, int rc, int level) {
+    size_t off[H_NCHUNK + 1];
+    const size_t a = v1_decode_bwd_ws_bytes(V, rc, level);
+    const size_t b = (rc >= 1 && rc <= 5 && level >= 0 && level <= 2) ? d2_bwd_offsets(d2_dims(V, rc, level), off) : 0;
+    return a > b ? a : b;
+}
+extern "C" const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level) {
+    if (!ws) return nullptr;
+    if (use_v2(rc)) return reinterpret_cast<const int32_t *>(f2_view(const_cast<void *>(ws), d2_dims(V, rc, level)).total);
+    return v1_decode_count_ptr(ws, V, rc, level);
+}
+extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
+                                  int32_t *M_host, void *stream) {
+    if (check_desc(d)) return -1;
+    return use_v2(d->rc) ? v2_decode_fwd(d, ws, neural_opacity, mask, M_host, stream)
+                         : v1_decode_fwd(d, ws, neural_opacity, mask, M_host, stream);
+}
+extern "C" int splatco_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *xyz, float *color,
+                                   float *opacity, float *scaling, float *rot, void *stream) {
+    if (check_desc(d)) return -1;
+    return use_v2(d->rc) ? v2_decode_emit(d, ws, M, xyz, color, opacity, scaling, rot, stream)
+                         : v1_decode_emit(d, ws, M, xyz, color, opacity, scaling, rot, stream);
+}
+extern "C" int splatco_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M,
+                                  const float *d_xyz, const float *d_color, const float *d_opacity,
+                                  const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
+                                  const splatco_decode_grads *g, void *stream) {
+    if (check_desc(d)) return -1;
+    return use_v2(d->rc) ? v2_decode_bwd(d, fwd_ws, bwd_ws, M, d_xyz, d_color, d_opacity, d_scaling, d_rot, d_neural_opacity, g, stream)
+                         : v1_decode_bwd(d, fwd_ws, bwd_ws, M, d_xyz, d_color, d_opacity, d_scaling, d_rot, d_neural_opacity, g, stream);
 }

@@ -1,0 +1,470 @@
+// Decode v2 backward MLP kernel (included at the end of decode.cu; see decode2.cuh for the algebra and the tile layouts).
+//
+// Persistent, one CTA per SM, 128 anchors per tile, 16 worker warps + 1 control warp (bulk copies, tcgen05.mma).
+// Per tile:
+//   P0   un-compaction: upstream gradients of the compacted Gaussians -> dZ rows (pre-activation), written straight
+//        into the K-major operand tile; the direct anchor / offset / scaling gradients stay in registers
+//   b1   dH = (dZ W2^T) .* [H > 0]        three block products (K = 16 | 72 | 32), accumulator in TMEM
+//   w2   gW2[j][i] += sum_v dZ[v][j] H[v][i]       reduction over the tile's anchors
+//   b2   dU = dH Wc1^T                              (N = NB <= 144)  -> DUT (+ the direct gradients)
+//   g    GT[n][uc]  += sum_v dH[v][n] u[v][uc]
+// The two weight-gradient products reduce over anchors, i.e. over the ROWS of the activation tiles.  kind::tf32 reads
+// no-swizzle tiles only K-major (tools/tc_mn_probe.py: with a majorness bit set the instruction produces nothing), so
+// their operands are transposed copies written by the threads, 32 anchors (4 K steps) at a time: chunk = 4 anchors,
+// chunk stride = (rows + 1) * 16 B, which makes the 4-byte transposed stores of a warp hit 32 different banks.
+// Both products accumulate in TMEM over all tiles of the CTA and leave it once, as a per-CTA partial (dec2_reduce_kernel).
+//
+// Shared memory (bytes), regions alias across the phases of a tile:
+//   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600), then the w2 quarter tiles from 122880
+//   b2/g    : dH rows hi [0,49152) lo [49152,98304) | W1R [98304,208896), then the g quarter tiles from 98304 |
+//             direct gradients [208896, 229888)
+// TMEM: dH acc [0,96) | dU acc [96,240) | gW2 acc [240,336) | GT acc [336,480).
+#pragma once
+
+namespace splatco {
+
+constexpr uint32_t D2B_DZLO = D2_RCH * D2_CHUNK;                     // 61440
+constexpr uint32_t D2B_W2R = 2 * D2B_DZLO;                           // 122880
+constexpr uint32_t D2B_DHLO = 24 * D2_CHUNK;                         // 49152
+constexpr uint32_t D2B_W1R = 2 * D2B_DHLO;                           // 98304
+constexpr uint32_t D2B_DGA = D2B_W1R + 2 * 24 * 144 * 16;            // 208896
+constexpr int D2B_DGA_LD = 41;
+constexpr uint32_t D2B_SMEM = D2B_DGA + D2_ROWS * D2B_DGA_LD * 4;    // 229888
+constexpr uint32_t D2B_LA = 129 * 16, D2B_LH = 97 * 16, D2B_LU = 145 * 16;   // chunk strides of the transposed quarter tiles
+// w2 quarter: dZ^T hi | lo | H^T hi | lo       g quarter: dH^T hi | lo | u^T hi | lo
+constexpr uint32_t D2B_QW_A = D2B_W2R, D2B_QW_B = D2B_QW_A + 2 * 8 * D2B_LA;
+constexpr uint32_t D2B_QG_A = D2B_W1R, D2B_QG_B = D2B_QG_A + 2 * 8 * D2B_LA;
+static_assert(D2B_QW_B + 2 * 8 * D2B_LH <= D2B_DGA && D2B_QG_B + 2 * 8 * D2B_LU <= D2B_DGA, "quarter tiles overlap the direct gradients");
+
+struct D2Bwd {
+    int V, nch, nk, NB, ntiles;
+    const float4 *XT, *HT, *ZT;
+    const uint32_t *maskbits, *offs;
+    const float *d_xyz, *d_color, *d_opacity, *d_scaling, *d_rot, *d_nopac;
+    const uint8_t *W2R, *W1R;
+    float4 *DUT;
+    float *part, *gb2blk;
+};
+
+__device__ __forceinline__ void d2_issue_lbo(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lboA, uint32_t b_hi,
+                                             uint32_t b_lo, uint32_t lboB, int ksteps, uint32_t idesc, bool accumulate_first) {
+    for (int s = 0; s < ksteps; ++s) {
+        const uint32_t ao = (uint32_t)(2 * s) * lboA, bo = (uint32_t)(2 * s) * lboB;
+        const uint64_t dah = tc::make_desc(a_hi + ao, lboA, 128), dal = tc::make_desc(a_lo + ao, lboA, 128);
+        const uint64_t dbh = tc::make_desc(b_hi + bo, lboB, 128), dbl = tc::make_desc(b_lo + bo, lboB, 128);
+        tc::mma_tf32(d_tmem, dal, dbh, idesc, accumulate_first || s > 0);
+        tc::mma_tf32(d_tmem, dah, dbl, idesc, true);
+        tc::mma_tf32(d_tmem, dah, dbh, idesc, true);
+    }
+}
+
+// transposed hi/lo store of one 16-byte cell (4 consecutive columns m0.. of anchor row rr) into a quarter tile
+__device__ __forceinline__ void d2_put_t(uint8_t *sm, uint32_t base_hi, uint32_t base_lo, uint32_t lbo, int m0, int rr, const float4 &h,
+                                         const float4 &l) {
+    const uint32_t o = (uint32_t)((rr & 31) >> 2) * lbo + (uint32_t)m0 * 16u + (uint32_t)(rr & 3) * 4u;
+    *reinterpret_cast<float *>(sm + base_hi + o) = h.x; *reinterpret_cast<float *>(sm + base_hi + o + 16) = h.y;
+    *reinterpret_cast<float *>(sm + base_hi + o + 32) = h.z; *reinterpret_cast<float *>(sm + base_hi + o + 48) = h.w;
+    *reinterpret_cast<float *>(sm + base_lo + o) = l.x; *reinterpret_cast<float *>(sm + base_lo + o + 16) = l.y;
+    *reinterpret_cast<float *>(sm + base_lo + o + 32) = l.z; *reinterpret_cast<float *>(sm + base_lo + o + 48) = l.w;
+}
+__device__ __forceinline__ void d2_split4(const float4 &x, float4 &h, float4 &l) {
+    h = make_float4(tc::tf32_hi(x.x), tc::tf32_hi(x.y), tc::tf32_hi(x.z), tc::tf32_hi(x.w));
+    l = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 1)
+dec2_mlp_bwd_kernel(D2Bwd a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ;
+    __shared__ uint32_t tmem_s;
+    __shared__ float s_gb2[128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
+    if (tid == 0) {
+        tc::mbar_init(&barWa, 1); tc::mbar_init(&barWb, 1); tc::mbar_init(&barB1, 1); tc::mbar_init(&barB2, 1); tc::mbar_init(&barQ, 1);
+        tc::fence_barrier_init();
+    }
+    if (tid < 128) s_gb2[tid] = 0.f;
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = tmem_s;
+    const uint32_t sb = tc::smem_u32(sm);
+    const int ntl = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t w1r_half = 24u * (uint32_t)a.NB * 16u;
+    constexpr uint32_t T_DH = 0, T_DU = 96, T_GW2 = 240, T_GT = 336;
+    uint32_t qph = 0;                                        // phases of barQ this thread has waited for
+
+    if (warp == D2_WORKERS / 32) {
+        // =========================== control warp ===========================
+        constexpr uint32_t id32 = tc::make_idesc_tf32(128, 32), id96 = tc::make_idesc_tf32(128, HD), id144 = tc::make_idesc_tf32(128, 144);
+        const uint32_t idNB = tc::make_idesc_tf32(128, a.NB);
+        for (int it = 0; it < ntl; ++it) {
+            const uint32_t par = it & 1;
+            if (lane == 0) {                                 // (all quarter products of the previous tile have completed)
+                tc::mbar_arrive_expect_tx(&barWa, 2 * D2_W2R_HALF);
+                tc::bulk_g2s(sm + D2B_W2R, a.W2R, 2 * D2_W2R_HALF, &barWa);
+            }
+            d2_bar_sync_all();                               // 1: dZ rows written
+            tc::tc_fence_after();
+            tc::mbar_wait(&barWa, par);
+            if (lane == 0) {
+                const uint32_t b = sb + D2B_W2R, bl = b + D2_W2R_HALF;
+                tc::issue_3xtf32(tmem + T_DH, sb, sb + D2B_DZLO, D2_ROWS, 0, b, bl, 32, 0, 2, id32, false);
+                tc::issue_3xtf32(tmem + T_DH + 32, sb, sb + D2B_DZLO, D2_ROWS, 4, b + 4 * 32 * 16, bl + 4 * 32 * 16, 32, 0, 9, id32, false);
+                tc::issue_3xtf32(tmem + T_DH + 64, sb, sb + D2B_DZLO, D2_ROWS, 22, b + 22 * 32 * 16, bl + 22 * 32 * 16, 32, 0, 4, id32, false);
+                tc::mma_commit(&barB1);
+            }
+            __syncwarp();
+            tc::mbar_wait(&barB1, par);                      // W2R is dead: the w2 quarter tiles may land on it
+            for (int q = 0; q < 4; ++q) {
+                d2_bar_sync_all();                           // 2..5: w2 quarter operands written
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    d2_issue_lbo(tmem + T_GW2, sb + D2B_QW_A, sb + D2B_QW_A + 8 * D2B_LA, D2B_LA, sb + D2B_QW_B, sb + D2B_QW_B + 8 * D2B_LH,
+                                 D2B_LH, 4, id96, it > 0 || q > 0);
+                    tc::mma_commit(&barQ);
+                }
+                __syncwarp();
+                tc::mbar_wait(&barQ, qph & 1); ++qph;
+            }
+            if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&barWb, 2 * w1r_half);
+                tc::bulk_g2s(sm + D2B_W1R, a.W1R, 2 * w1r_half, &barWb);
+            }
+            d2_bar_sync_all();                               // 6: dH rows written
+            tc::tc_fence_after();
+            tc::mbar_wait(&barWb, par);
+            if (lane == 0) {
+                tc::issue_3xtf32(tmem + T_DU, sb, sb + D2B_DHLO, D2_ROWS, 0, sb + D2B_W1R, sb + D2B_W1R + w1r_half, a.NB, 0, HD / 8, idNB, false);
+                tc::mma_commit(&barB2);
+            }
+            __syncwarp();
+            tc::mbar_wait(&barB2, par);
+            for (int q = 0; q < 4; ++q) {
+                d2_bar_sync_all();                           // 7..10: g quarter operands written
+                tc::tc_fence_after();
+                if (lane == 0) {
+                    d2_issue_lbo(tmem + T_GT, sb + D2B_QG_A, sb + D2B_QG_A + 8 * D2B_LA, D2B_LA, sb + D2B_QG_B, sb + D2B_QG_B + 8 * D2B_LU,
+                                 D2B_LU, 4, id144, it > 0 || q > 0);
+                    tc::mma_commit(&barQ);
+                }
+                __syncwarp();
+                tc::mbar_wait(&barQ, qph & 1); ++qph;
+            }
+        }
+    } else {
+        // =========================== workers ===========================
+        const int r = tid & (D2_ROWS - 1), grp = tid >> 7;
+        const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const int rp = tid >> 2, kq = tid & 3;               // un-compaction: row, offsets kq, kq + 4, kq + 8
+        const int ng = a.NB / 8, g_beg = (ng * grp) / 4, g_end = (ng * (grp + 1)) / 4;      // dU column groups of this thread
+        float *s_dga = reinterpret_cast<float *>(sm + D2B_DGA);
+        for (int it = 0; it < ntl; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const uint32_t par = it & 1;
+            // ---- P0: un-compaction (gaussian_renderer/__init__.py:96-111 backwards) --------------------------------------
+            float dofr[9], acc9[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { dofr[q] = 0.f; acc9[q] = 0.f; }
+            {
+                const int v = tile * D2_ROWS + rp;
+                const bool valid = v < a.V;
+                const uint32_t bits = valid ? a.maskbits[v] : 0u;
+                const uint32_t off0 = valid ? a.offs[v] : 0u;
+                const float *g = reinterpret_cast<const float *>(a.XT + (size_t)tile * a.nch * D2_ROWS + rp);
+                const float *z = reinterpret_cast<const float *>(a.ZT + (size_t)tile * D2_ZCH * D2_ROWS + rp);
+                float s6[6];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s6[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + q));
+                float dz[3][11];
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = kq + 4 * kk;
+#pragma unroll
+                    for (int q = 0; q < 11; ++q) dz[kk][q] = 0.f;
+                    if (k < KO && valid) {
+                        const bool m = (bits >> k) & 1u;
+                        const float no = __ldg(z + d2_tile_idx(d2_zcol_op(k)));
+                        float dno = a.d_nopac ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
+                        if (m) {
+                            const size_t j = off0 + __popc(bits & ((1u << k) - 1u));
+                            dno += __ldg(a.d_opacity + j);
+                            const float gx = __ldg(a.d_xyz + 3 * j), gy = __ldg(a.d_xyz + 3 * j + 1), gz = __ldg(a.d_xyz + 3 * j + 2);
+                            const float ox = __ldg(g + d2_tile_idx(FD + 3 + 3 * k)), oy = __ldg(g + d2_tile_idx(FD + 3 + 3 * k + 1)),
+                                        oz = __ldg(g + d2_tile_idx(FD + 3 + 3 * k + 2));
+                            dofr[3 * kk] = gx * s6[0]; dofr[3 * kk + 1] = gy * s6[1]; dofr[3 * kk + 2] = gz * s6[2];
+                            acc9[0] += gx; acc9[1] += gy; acc9[2] += gz;
+                            acc9[3] += gx * ox; acc9[4] += gy * oy; acc9[5] += gz * oz;
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float c = __ldg(z + d2_tile_idx(d2_zcol_col(k, q)));
+                                dz[kk][8 + q] = __ldg(a.d_color + 3 * j + q) * c * (1.f - c);
+                            }
+                            float sr[7];
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) sr[q] = __ldg(z + d2_tile_idx(d2_zcol_cov(k, q)));
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float sg = 1.f / (1.f + expf(-sr[q]));
+                                const float gsc = __ldg(a.d_scaling + 3 * j + q);
+                                dz[kk][1 + q] = gsc * s6[3 + q] * sg * (1.f - sg);
+                                acc9[6 + q] += gsc * sg;
+                            }
+                            const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
+                            const float n = fmaxf(nrm, 1e-12f);
+                            const float r0 = sr[3] / n, r1 = sr[4] / n, r2 = sr[5] / n, r3 = sr[6] / n;
+                            const float g0 = __ldg(a.d_rot + 4 * j), g1 = __ldg(a.d_rot + 4 * j + 1), g2 = __ldg(a.d_rot + 4 * j + 2),
+                                        g3 = __ldg(a.d_rot + 4 * j + 3);
+                            if (nrm > 1e-12f) {
+                                const float dot = r0 * g0 + r1 * g1 + r2 * g2 + r3 * g3;
+                                dz[kk][4] = (g0 - r0 * dot) / n; dz[kk][5] = (g1 - r1 * dot) / n;
+                                dz[kk][6] = (g2 - r2 * dot) / n; dz[kk][7] = (g3 - r3 * dot) / n;
+                            } else {
+                                dz[kk][4] = g0 / n; dz[kk][5] = g1 / n; dz[kk][6] = g2 / n; dz[kk][7] = g3 / n;
+                            }
+                        }
+                        dz[kk][0] = dno * (1.f - no * no);
+                    }
+                }
+                // the 4 lanes of a row hold partial sums over their offsets
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 1);
+                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 2);
+                }
+                // column sums of dZ (= the output-bias gradients): over the 8 rows of the warp, then one shared-memory add
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = kq + 4 * kk;
+#pragma unroll
+                    for (int q = 0; q < 11; ++q) {
+                        float s = dz[kk][q];
+                        s += __shfl_xor_sync(0xffffffffu, s, 4);
+                        s += __shfl_xor_sync(0xffffffffu, s, 8);
+                        s += __shfl_xor_sync(0xffffffffu, s, 16);
+                        if (lane < 4 && k < KO && s != 0.f)
+                            atomicAdd(&s_gb2[q == 0 ? k : (q < 8 ? D2_RCOV + 7 * k + (q - 1) : D2_RCOL + 3 * k + (q - 8))], s);
+                    }
+                }
+                // every quarter product of the previous tile has completed (the control warp waited before its bulk copy,
+                // these threads wait here): the dZ rows may be overwritten
+                if (it > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                auto putz = [&](int col, float x) {
+                    const float h = tc::tf32_hi(x);
+                    const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)rp * 16u + (uint32_t)(col & 3) * 4u;
+                    *reinterpret_cast<float *>(sm + o) = h;
+                    *reinterpret_cast<float *>(sm + D2B_DZLO + o) = x - h;
+                };
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = kq + 4 * kk;
+                    if (k < KO) {
+                        putz(k, dz[kk][0]);
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) putz(D2_RCOV + 7 * k + q, dz[kk][1 + q]);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) putz(D2_RCOL + 3 * k + q, dz[kk][8 + q]);
+                    }
+                }
+                if (kq == 3) {                               // this lane has two offsets only: it zeroes the padding columns
+#pragma unroll
+                    for (int c = KO; c < D2_RCOV; ++c) putz(c, 0.f);
+                    putz(D2_RCOV + 7 * KO, 0.f); putz(D2_RCOV + 7 * KO + 1, 0.f);
+                    putz(D2_RCOL + 3 * KO, 0.f); putz(D2_RCOL + 3 * KO + 1, 0.f);
+                }
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            d2_bar_sync_all();                               // 1
+            // ---- gate bits of this thread's 24 hidden columns (for epilogue b1), loaded while b1 runs ---------------------
+            uint32_t hbits = 0u;
+            {
+                const float4 *ht = a.HT + ((size_t)tile * 24 + 6 * grp) * D2_ROWS + r;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const float4 h = __ldg(ht + c * D2_ROWS);
+                    hbits |= ((h.x > 0.f ? 1u : 0u) | (h.y > 0.f ? 2u : 0u) | (h.z > 0.f ? 4u : 0u) | (h.w > 0.f ? 8u : 0u)) << (4 * c);
+                }
+            }
+            tc::mbar_wait(&barB1, par);
+            tc::tc_fence_after();
+            // ---- w2: gW2 += dZ^T H, 32 anchors at a time -------------------------------------------------------------------
+            for (int q = 0; q < 4; ++q) {
+                if (q > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                for (int e = tid; e < D2_RCH * 32; e += D2_WORKERS) {
+                    const int c = e >> 5, rr = 32 * q + (e & 31);
+                    const uint32_t o = (uint32_t)c * D2_CHUNK + (uint32_t)rr * 16u;
+                    d2_put_t(sm, D2B_QW_A, D2B_QW_A + 8 * D2B_LA, D2B_LA, 4 * c, rr, *reinterpret_cast<const float4 *>(sm + o),
+                             *reinterpret_cast<const float4 *>(sm + D2B_DZLO + o));
+                }
+                for (int e = tid; e < 24 * 32; e += D2_WORKERS) {
+                    const int c = e >> 5, rr = 32 * q + (e & 31);
+                    float4 h, l;
+                    d2_split4(__ldg(a.HT + ((size_t)tile * 24 + c) * D2_ROWS + rr), h, l);
+                    d2_put_t(sm, D2B_QW_B, D2B_QW_B + 8 * D2B_LH, D2B_LH, 4 * c, rr, h, l);
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                d2_bar_sync_all();                           // 2..5
+            }
+            // ---- epilogue b1: dH = acc .* [H > 0] (registers) ---------------------------------------------------------------
+            float dh[24];
+#pragma unroll
+            for (int n0 = 0; n0 < 24; n0 += 8) {
+                float v[8];
+                tc::tmem_ld8(tlane + T_DH + 24 * grp + n0, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dh[n0 + e] = (hbits >> (n0 + e)) & 1u ? v[e] : 0.f;
+            }
+            tc::mbar_wait(&barQ, qph & 1); ++qph;            // last w2 quarter done: the dZ rows and the quarter tiles are dead
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                float4 h, l;
+                d2_split4(make_float4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]), h, l);
+                const uint32_t o = (uint32_t)(6 * grp + c) * D2_CHUNK + (uint32_t)r * 16u;
+                *reinterpret_cast<float4 *>(sm + o) = h;
+                *reinterpret_cast<float4 *>(sm + D2B_DHLO + o) = l;
+            }
+            {                                                // direct gradients: [anchor 3 | offsets 30 | scaling 6]
+                float *dg = s_dga + rp * D2B_DGA_LD;
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    const int k = kq + 4 * kk;
+                    if (k < KO) { dg[3 + 3 * k] = dofr[3 * kk]; dg[4 + 3 * k] = dofr[3 * kk + 1]; dg[5 + 3 * k] = dofr[3 * kk + 2]; }
+                }
+                if (kq == 0) {
+                    dg[0] = acc9[0]; dg[1] = acc9[1]; dg[2] = acc9[2];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) dg[33 + q] = acc9[3 + q];
+                }
+            }
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            d2_bar_sync_all();                               // 6
+            tc::mbar_wait(&barB2, par);
+            tc::tc_fence_after();
+            // ---- epilogue b2: dU (+ direct gradients on the anchor / offset / scaling columns) -> DUT ------------------------
+            {
+                float4 *du = a.DUT + (size_t)tile * a.nch * D2_ROWS + r;
+                const float *dg = s_dga + r * D2B_DGA_LD;
+                for (int gi = g_beg; gi < g_end; ++gi) {
+                    float v[8];
+                    tc::tmem_ld8(tlane + T_DU + 8 * gi, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int c = 8 * gi + e;
+                        if (c >= FD && c < GD) v[e] += dg[c - FD];
+                    }
+                    if (2 * gi < a.nch) du[(2 * gi) * D2_ROWS] = make_float4(v[0], v[1], v[2], v[3]);
+                    if (2 * gi + 1 < a.nch) du[(2 * gi + 1) * D2_ROWS] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            // ---- g: GT += dH^T u, 32 anchors at a time -------------------------------------------------------------------------
+            for (int q = 0; q < 4; ++q) {
+                if (q > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                for (int e = tid; e < 24 * 32; e += D2_WORKERS) {
+                    const int c = e >> 5, rr = 32 * q + (e & 31);
+                    const uint32_t o = (uint32_t)c * D2_CHUNK + (uint32_t)rr * 16u;
+                    d2_put_t(sm, D2B_QG_A, D2B_QG_A + 8 * D2B_LA, D2B_LA, 4 * c, rr, *reinterpret_cast<const float4 *>(sm + o),
+                             *reinterpret_cast<const float4 *>(sm + D2B_DHLO + o));
+                }
+                for (int e = tid; e < a.nch * 32; e += D2_WORKERS) {
+                    const int c = e >> 5, rr = 32 * q + (e & 31);
+                    float4 h, l;
+                    d2_split4(__ldg(a.XT + ((size_t)tile * a.nch + c) * D2_ROWS + rr), h, l);
+                    d2_put_t(sm, D2B_QG_B, D2B_QG_B + 8 * D2B_LU, D2B_LU, 4 * c, rr, h, l);
+                }
+                tc::fence_proxy_async();
+                tc::tc_fence_before();
+                d2_bar_sync_all();                           // 7..10
+            }
+        }
+        // ---- the CTA's weight-gradient accumulators leave TMEM once ---------------------------------------------------------------
+        if (ntl > 0) {
+            tc::mbar_wait(&barQ, qph & 1); ++qph;
+            tc::tc_fence_after();
+            float *pw = a.part + (size_t)blockIdx.x * D2_PART + (size_t)r * HD + 24 * grp;
+#pragma unroll
+            for (int n0 = 0; n0 < 24; n0 += 8) {
+                float v[8];
+                tc::tmem_ld8(tlane + T_GW2 + 24 * grp + n0, v);
+                tc::tmem_ld_wait();
+                *reinterpret_cast<float4 *>(pw + n0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(pw + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            float *pg = a.part + (size_t)blockIdx.x * D2_PART + D2_ROWS * HD + (size_t)r * 144;
+            for (int gi = (18 * grp) / 4; gi < (18 * (grp + 1)) / 4; ++gi) {
+                float v[8];
+                tc::tmem_ld8(tlane + T_GT + 8 * gi, v);
+                tc::tmem_ld_wait();
+                *reinterpret_cast<float4 *>(pg + 8 * gi) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(pg + 8 * gi + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid < 128 && s_gb2[tid] != 0.f) atomicAdd(&a.gb2blk[tid], s_gb2[tid]);
+    if (warp == 0) tc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace splatco
+
+namespace {
+
+int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws, int M, const float *d_xyz, const float *d_color,
+                  const float *d_opacity, const float *d_scaling, const float *d_rot, const float *d_neural_opacity,
+                  const splatco_decode_grads *g, void *stream) {
+    if (d->V == 0) return 0;
+    SPLATCO_REQUIRE(fwd_ws && bwd_ws && g, "decode_bwd: null pointer");
+    SPLATCO_REQUIRE(M == 0 || (d_xyz && d_color && d_opacity && d_scaling && d_rot), "decode_bwd: null upstream gradient");
+    SPLATCO_REQUIRE(g->anchor_feat && g->anchor && g->offset && g->scaling, "decode_bwd: null per-anchor gradient");
+    cudaStream_t st = (cudaStream_t)stream;
+    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    F2View f = f2_view(const_cast<void *>(fwd_ws), dd);
+    B2View b = b2_view(bwd_ws, dd);
+    const DecPtrs p = make_ptrs(d);
+    const DecWeights w = make_weights(d);
+    DecWeightGrads gw;
+    DecInputGrads gi;
+    for (int l = 0; l < 3; ++l) {
+        gw.bn_w[l] = g->bn_w[l]; gw.bn_b[l] = g->bn_b[l]; gw.lin_w[l] = g->lin_w[l]; gw.lin_b[l] = g->lin_b[l];
+        gw.cbn_w[l] = g->cbn_w[l]; gw.cbn_b[l] = g->cbn_b[l]; gw.clin_w[l] = g->clin_w[l]; gw.clin_b[l] = g->clin_b[l];
+        gw.w1[l] = g->w1[l]; gw.b1[l] = g->b1[l]; gw.w2[l] = g->w2[l]; gw.b2[l] = g->b2[l];
+        for (int q = 0; q < 3; ++q) gi.plane[l][q] = g->plane[3 * l + q];
+        gi.att[l] = g->att[l];
+    }
+    gw.app_vec = g->app_vec;
+    gi.anchor_feat = g->anchor_feat; gi.anchor = g->anchor; gi.offset = g->offset; gi.scaling = g->scaling;
+
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(b.gb2blk, 0, 128 * sizeof(float), st));
+    static unsigned char attr_dev[64];
+    const int attr_i = current_device() & 63;
+    if (!attr_dev[attr_i]) {
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(dec2_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D2B_SMEM));
+        attr_dev[attr_i] = 1;
+    }
+    D2Bwd a;
+    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = dd.ntiles;
+    a.XT = f.XT; a.HT = f.HT; a.ZT = f.ZT; a.maskbits = f.maskbits; a.offs = f.offs;
+    a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
+    a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.part = b.part; a.gb2blk = b.gb2blk;
+    const int ctas = min(dd.ntiles, D2_MAX_CTAS);
+    dec2_mlp_bwd_kernel<<<ctas, D2_THREADS, D2B_SMEM, st>>>(a);
+    SPLATCO_CHECK_LAUNCH();
+    dec2_reduce_kernel<<<ceil_div(D2_PART, 256), 256, 0, st>>>(ctas, b.part, b.red);
+    SPLATCO_CHECK_LAUNCH();
+    dec2_expand_kernel<<<48, 256, 0, st>>>(dd.DP, dd.LDX, b.red, b.gb2blk, f.WpT, f.WcT, f.bgeo, f.W1T, b.S1, b.S0, b.gW1T, b.gb1,
+                                           b.gW2T, b.gb2);
+    SPLATCO_CHECK_LAUNCH();
+    dec_bwd_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, gw, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+                                                   b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
+    SPLATCO_CHECK_LAUNCH();
+    if (D2_DISPATCH(launch_inputs2, dd.level, dd.rc, d->plane_layout != 0, st, p, gi, dd, f.XT, b.DUT, f.mu, f.rstd, b.m1, b.m2)) return -2;
+    return 0;
+}
+
+}  // namespace

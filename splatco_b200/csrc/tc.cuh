@@ -92,6 +92,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            | (2u << 10)     // B format: TF32
            | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// same with operand majorness bits: a_mn / b_mn = 1 selects an MN-major operand (bit 15 / 16), i.e. a tile whose
+// 16-byte cells hold 4 consecutive M (or N) indices and whose 8-row core matrices run along K: the layout a K-major
+// activation tile [rows = anchors][cols] has when the anchors are the REDUCTION dimension (weight gradients)
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N, int a_mn, int b_mn) {
+    return make_idesc_tf32(M, N) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T   (single CTA); issue from ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(

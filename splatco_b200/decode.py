@@ -3,9 +3,9 @@
 Mirrors the contract of the reference's `generate_neural_gaussians`
 (gaussian_renderer/__init__.py:18-116): same inputs read off the same `pc` attributes, same 7-tuple
 (train) / 5-tuple (eval) of outputs, gradients delivered to the same leaves through autograd.
-All arithmetic runs in libsplatco_b200.so; TriPlaneAttention over the whole planes (a dense conv
-pass, view-independent — SURVEY §8 row f2) is still evaluated by the module the model owns and its
-output planes are handed to the kernels, which return their gradients to autograd.
+All arithmetic runs in libsplatco_b200.so, TriPlaneAttention over the whole planes included (a dense,
+view-independent pass — SURVEY §8 row f2 — evaluated once per iteration by splatco_ta_fwd/_bwd and cached
+across the mv views, `_TACache`).
 """
 from __future__ import annotations
 
@@ -122,7 +122,8 @@ def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, 
     """Descriptor for one view.  The ~100 parameter / buffer pointers only change when the optimizer or
     densification swaps tensors, so a filled template is cached on the config's plan and copied."""
     plan = cfg.plan
-    key = (tuple([t.data_ptr() for t in params]), tuple(cfg.use_dist), cfg.app_dim, cfg.level, cfg.N)
+    key = (tuple([t.data_ptr() for t in params]), tuple(cfg.use_dist), cfg.app_dim, cfg.level, cfg.N, id(cfg.buffers),
+           cfg.xyz_min.data_ptr())
     if plan.desc_key != key:
         d = DecodeDesc()
         d.N, d.K, d.rc, d.level, d.app_dim = cfg.N, cfg.K, cfg.rc, cfg.level, cfg.app_dim
@@ -455,7 +456,7 @@ class _ModelPlan:
     parameter tensors are fetched with dict lookups instead of nn.Module attribute resolution), the
     static sizes, and the descriptor template (_fill_desc)."""
     __slots__ = ("feat_ref", "level", "heads", "levels", "rc", "E", "xyz_min", "xyz_max", "bn_eps", "bn_momentum",
-                 "buffers", "ta_weights", "desc_key", "desc", "param_ids")
+                 "buffers", "ta_weights", "desc_key", "desc", "param_ids", "bbox_src")
 
 
 _plans = {}
@@ -471,7 +472,11 @@ def _par(module, name):
 def _plan_for(pc, feat, level, heads) -> _ModelPlan:
     plan = _plans.get(id(pc))
     if (plan is not None and plan.feat_ref() is feat and plan.level == level
-            and all(a is b for a, b in zip(plan.heads, heads))):
+            and all(a is b for a, b in zip(plan.heads, heads))
+            # buffers are captured as tensor objects: module.to() / load_state_dict(assign=True) replace them
+            and all(lv[1]._buffers.get("running_mean") is bf["bn_rm"] and lv[3]._buffers.get("running_mean") is bf["cbn_rm"]
+                    for lv, bf in zip(plan.levels, plan.buffers))
+            and plan.bbox_src[0] is feat.k0s[0].xyz_min and plan.bbox_src[1] is feat.k0s[0].xyz_max):
         return plan
     k0s = feat.k0s
     for l in range(level + 1):
@@ -483,6 +488,7 @@ def _plan_for(pc, feat, level, heads) -> _ModelPlan:
     plan.rc = int(k0s[0].xy_plane.shape[1])
     plan.E = [int(k0s[min(l, len(k0s) - 1)].xy_plane.shape[2]) for l in range(3)]
     plan.xyz_min, plan.xyz_max = _c(k0s[0].xyz_min), _c(k0s[0].xyz_max)      # stay on the device: no host sync
+    plan.bbox_src = (k0s[0].xyz_min, k0s[0].xyz_max)
     bn0 = feat.models[0][0]
     plan.bn_eps, plan.bn_momentum = float(bn0.eps), float(bn0.momentum if bn0.momentum is not None else 0.1)
     plan.levels, plan.buffers = [], []

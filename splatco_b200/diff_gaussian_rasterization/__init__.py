@@ -134,8 +134,12 @@ def preprocess_speculative(xyz_b, color_b, opacity_b, scaling_b, rot_b, count_pt
     sp.RL = 0
     guess = _r_guess.get((H, W))
     if guess:
-        sp.RL = int(guess * 1.25) + 4096
-        _queue_binning_blend(sp, dev, H, W)
+        RL = int(guess * 1.25) + 4096
+        # only the tile-segmented binning path clamps to a capacity; its radix fallback (sparse views: few instances per
+        # row of the V*K-row buffers) needs the exact count, so nothing is queued ahead of the sync then
+        if L.splatco_binning_accepts_capacity(PL, RL, H, W):
+            sp.RL = RL
+            _queue_binning_blend(sp, dev, H, W)
     return sp
 
 

@@ -29,84 +29,125 @@ def owner_of_view(view: int, world: int) -> int:
 
 
 class GradBucket:
-    """Flat fp32 bucket over a fixed parameter list; `allreduce()` sums .grad across ranks in one
-    collective and scatters the result back (parameters without a grad contribute zeros, so every
-    rank issues the same collective even if it rendered no view that touched them)."""
+    """Sums the parameter gradients of a replicated model across ranks.
 
-    def __init__(self, params: Sequence[torch.Tensor]):
-        self.params = [p for p in params if p.requires_grad]
-        self.sizes = [p.numel() for p in self.params]
-        self.total = sum(self.sizes)
-        dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+    The gradients the decode / TriPlaneAttention kernels accumulate (per-anchor rows, planes, MLP weights) live in ONE
+    flat zero-filled fp32 buffer per backward pass (`_gradacc`): that buffer is all-reduced IN PLACE with one collective
+    and no copies.  Whatever else carries a gradient travels in one small packed bucket.
+
+    No per-step agreement round: replicas run the same program on the same parameter set, so the layout (number and
+    sizes of the flat buffers, which other parameters have gradients) is identical on every rank as long as every rank
+    rendered at least one view of the iteration -- the precondition of `render_views_sharded` (num_views >= world).
+    The layout is verified across ranks when it is first seen and whenever the LOCAL layout changes (densification
+    grows the anchors on every rank at once); SPLATCO_CHECK_ALLREDUCE=1 verifies it on every call.
+
+    `params`: a sequence of tensors or a callable returning the current sequence (densification replaces the
+    per-anchor Parameters: pass `lambda: [g["params"][0] for g in optimizer.param_groups]`)."""
+
+    def __init__(self, params):
+        self._source = params if callable(params) else (lambda p=list(params): p)
+        self._agreed = None
+        self._small = None
+        self.last_bytes = 0
+
+    @property
+    def params(self):
+        return [p for p in self._source() if p.requires_grad]
+
+    @property
+    def total(self) -> int:
+        """Number of gradient elements of the current parameter list."""
+        return sum(p.numel() for p in self.params)
 
     def nbytes(self) -> int:
-        return self.total * 4
+        """Bytes the last allreduce() moved per rank (before the first call: 4 bytes per parameter element)."""
+        return self.last_bytes or 4 * self.total
 
-    def pack(self):
+    # ---- packed path (CPU / gloo tests, and parameters whose gradient is not in the flat buffers) ------------------
+    @staticmethod
+    def _pack(params, flat):
         off = 0
-        for p, n in zip(self.params, self.sizes):
-            seg = self.flat[off:off + n]
+        for p in params:
+            n = p.numel()
             if p.grad is None:
-                seg.zero_()
+                flat[off:off + n].zero_()
             else:
-                seg.copy_(p.grad.reshape(-1))
+                flat[off:off + n].copy_(p.grad.reshape(-1))
             off += n
 
-    def unpack(self):
+    @staticmethod
+    def _unpack(params, flat):
         off = 0
-        for p, n in zip(self.params, self.sizes):
-            seg = self.flat[off:off + n].view_as(p)
+        for p in params:
+            n = p.numel()
+            seg = flat[off:off + n].view_as(p)
             if p.grad is None:
                 p.grad = seg.clone()
             else:
                 p.grad.copy_(seg)
             off += n
 
-    def allreduce(self, group=None):
-        """Sum .grad over ranks.  Gradients that already live in the flat buffers of the last backward pass
-        (everything the decode / TriPlaneAttention kernels accumulate: anchors, planes, MLP weights -- see
-        _gradacc.py) are all-reduced IN PLACE, one collective per buffer and no copies; whatever else has a
-        gradient goes through the packed bucket."""
+    def allreduce(self, group=None, async_op=False):
+        """Sum .grad over ranks.  With async_op=True the collectives are only queued (NCCL orders them after the
+        kernels already on the current stream) and `wait()` must be called before the gradients are read on another
+        stream; on the current stream later kernels are ordered behind them by the process group itself."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return
+            return None
+        import os
         from . import _gradacc
-        dev = self.params[0].device if self.params else torch.device("cpu")
+        params = self.params
+        dev = params[0].device if params else torch.device("cpu")
         flats = _gradacc.last_pass_buffers(dev) if dev.type == "cuda" else []
-        if dev.type == "cuda":
-            # every rank must issue the same collectives: agree on the buffer layout (a rank that rendered no view of
-            # this iteration has none), fall back to the packed bucket everywhere otherwise
-            sig = torch.tensor([len(flats), sum(f.numel() for f in flats)], dtype=torch.int64, device=dev)
-            lo, hi = sig.clone(), sig.clone()
+        owned = {f.untyped_storage().data_ptr() for f in flats}
+        if flats:
+            rest = [p for p in params if p.grad is not None and p.grad.untyped_storage().data_ptr() not in owned]
+        else:
+            rest = params                      # no shared buffers on this device type: everything is packed (zeros for None)
+        sig = (tuple(f.numel() for f in flats), tuple(p.numel() for p in rest))
+        if sig != self._agreed or os.environ.get("SPLATCO_CHECK_ALLREDUCE") == "1":
+            h = torch.tensor([len(flats), sum(sig[0]), len(rest), sum(sig[1])], dtype=torch.int64, device=dev)
+            lo, hi = h.clone(), h.clone()
             dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
             if not torch.equal(lo, hi):
-                flats = []
-        owned = {f.untyped_storage().data_ptr() for f in flats}
-        rest = [p for p in self.params if p.grad is None or p.grad.untyped_storage().data_ptr() not in owned]
-        for f in flats:
-            dist.all_reduce(f, op=dist.ReduceOp.SUM, group=group)
-        if not flats:
-            self.pack()
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.unpack()
-        elif rest:
-            sizes = [p.numel() for p in rest]
-            small = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-            off = 0
-            for p, n in zip(rest, sizes):
-                if p.grad is not None:
-                    small[off:off + n].copy_(p.grad.reshape(-1))
-                off += n
-            dist.all_reduce(small, op=dist.ReduceOp.SUM, group=group)
-            off = 0
-            for p, n in zip(rest, sizes):
-                seg = small[off:off + n].view_as(p)
-                if p.grad is None:
-                    p.grad = seg.clone()
-                else:
-                    p.grad.copy_(seg)
-                off += n
+                raise RuntimeError("GradBucket.allreduce: ranks disagree on the gradient layout "
+                                   f"(local {h.tolist()}, min {lo.tolist()}, max {hi.tolist()}): every rank must render "
+                                   "at least one view per iteration and hold the same parameter set")
+            self._agreed = sig
+        small = None
+        if rest:
+            n = sum(sig[1])
+            if self._small is None or self._small.numel() != n or self._small.device != dev:
+                self._small = torch.empty(n, dtype=torch.float32, device=dev)
+            small = self._small
+            self._pack(rest, small)
+        bufs = list(flats) + ([small] if small is not None else [])
+        self.last_bytes = 4 * sum(b.numel() for b in bufs)
+        works = []
+        if len(bufs) > 1 and dev.type == "cuda" and hasattr(dist, "_coalescing_manager"):
+            # one NCCL group launch for all buffers
+            with dist._coalescing_manager(group=group, device=dev, async_ops=True) as cm:
+                for b in bufs:
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+            works.append(cm)
+        else:
+            for b in bufs:
+                works.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        self._pending = (works, rest, small)
+        if not async_op:
+            self.wait()
+        return self
+
+    def wait(self):
+        pend, self._pending = getattr(self, "_pending", None), None
+        if pend is None:
+            return
+        works, rest, small = pend
+        for w in works:
+            if w is not None:
+                w.wait()                       # NCCL: orders the current stream behind the collective, no host block
+        if small is not None:
+            self._unpack(rest, small)
 
 
 def broadcast_last_view_stats(tensors: Iterable[torch.Tensor], num_views: int, group=None):

@@ -42,6 +42,7 @@ class FusedAdam(torch.optim.Optimizer):
         L = _lib.lib()
         by_cfg = {}
         keep = []
+        touched = []
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             lr = float(group["lr"])
@@ -72,6 +73,7 @@ class FusedAdam(torch.optim.Optimizer):
                 if items is None:
                     items = by_cfg.setdefault((p.device, float(beta1), float(beta2), float(group["eps"])), [])
                 items.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), step, lr))
+                touched += (p, m, v)
         for (dev, beta1, beta2, eps), items in by_cfg.items():
             n = len(items)
             if self._table is None or len(self._table) < n:
@@ -83,4 +85,9 @@ class FusedAdam(torch.optim.Optimizer):
             with _lib.on_device(dev):
                 with stage("adam_step"):
                     check(L.splatco_adam_step(n, C.byref(tab), beta1, beta2, eps, _lib.raw_stream(dev)), "splatco_adam_step")
+        # the kernel writes through raw pointers: tell autograd (and every cache keyed on `_version` -- the decode's
+        # TriPlaneAttention / channel-last plane copies, the renderer's exp(_scaling) stash) that these tensors changed,
+        # as torch.optim.Adam's in-place ops would
+        if touched:
+            torch.autograd.graph.increment_version(touched)
         return loss

@@ -9,6 +9,8 @@ from contextlib import contextmanager, nullcontext
 
 import torch
 
+import os
+
 ACTIVE = None
 
 
@@ -32,7 +34,32 @@ class StageTimer:
         return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in self.events.items()}
 
 
+NVTX = False
+
+
+def enable_nvtx(on: bool = True):
+    """Wrap every stage of the path (visible_filter, decode_fwd, preprocess_fwd, binning, blend_fwd, blend_bwd, ...)
+    in an NVTX range so Nsight timelines show the stages; also switched on by SPLATCO_NVTX=1."""
+    global NVTX
+    NVTX = bool(on)
+
+
+@contextmanager
+def _nvtx_stage(name):
+    torch.cuda.nvtx.range_push("splatco/" + name)
+    try:
+        if ACTIVE is not None:
+            with ACTIVE.stage(name):
+                yield
+        else:
+            yield
+    finally:
+        torch.cuda.nvtx.range_pop()
+
+
 def stage(name):
+    if NVTX:
+        return _nvtx_stage(name)
     return ACTIVE.stage(name) if ACTIVE is not None else nullcontext()
 
 
@@ -44,3 +71,7 @@ def collect():
         yield ACTIVE
     finally:
         ACTIVE = prev
+
+
+if os.environ.get("SPLATCO_NVTX") == "1":
+    NVTX = True
