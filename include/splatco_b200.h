@@ -129,6 +129,16 @@ int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg, const voi
                       const void *binning, const void *image, const float *dL_dpix /* [3,H,W] */,
                       float *dL_dmean2D, float *dL_dconic, float *dL_dopacity, float *dL_dcolor,
                       void *stream);
+
+/* Same-GPU comparator (NOT used by the product path): the upstream rasterizer's blend STRUCTURE restated -- 256-instance
+ * batches, every pixel evaluates every staged instance, nine global atomicAdds per (pixel, instance) in the backward
+ * (builder-authored, the reference's own source is absent).  Same arguments, workspaces
+ * and results as splatco_blend_fwd / splatco_blend_bwd; bench.py times both (`gpu_baseline`). */
+int splatco_blend_fwd_upstream(int64_t R, int H, int W, const float *bg, const void *geom, const void *binning,
+                               void *image, float *out_color, void *stream);
+int splatco_blend_bwd_upstream(int P, int64_t R, int H, int W, const float *bg, const void *geom, const void *binning,
+                               const void *image, const float *dL_dpix, float *dL_dmean2D, float *dL_dconic,
+                               float *dL_dopacity, float *dL_dcolor, void *stream);
 int splatco_preprocess_bwd(int P, const float *means3D, const float *scales, int scale_stride,
                            const float *rots, float scale_mod, const float *view, const float *proj,
                            float tanfovx, float tanfovy, int H, int W, const int32_t *radii,
@@ -208,6 +218,10 @@ int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opa
  * (environment: SPLATCO_DECODE_IMPL=1|2). */
 int splatco_decode_set_impl(int impl);
 int splatco_decode_get_impl(void);
+/* Introspection for the tests: the gathered rows [V, LDX] of a finished splatco_decode_fwd (LDX = round_up4(DP + 71),
+ * columns [plane features DP | anchor_feat 32 | anchor 3 | offsets 30 | scaling 6 | zero padding]), whatever the
+ * implementation's internal layout. */
+int splatco_decode_gathered_rows(const void *ws, int V, int rc, int level, float *out, void *stream);
 /* Device address (inside ws) of the survivor count M that splatco_decode_fwd leaves behind. */
 const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc, int level);
 /* Stage 2: stable compaction + post-processing into the M surviving Gaussians.  M is only tested for

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsplatco_b200.so")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "decode.cu", "tc_test.cu", "triplane_attention.cu", "statis.cu", "loss.cu", "regularizer.cu", "densify.cu", "optim.cu", "cvpm.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "blend_upstream.cu", "decode.cu", "tc_test.cu", "triplane_attention.cu", "statis.cu", "loss.cu", "regularizer.cu", "densify.cu", "optim.cu", "cvpm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -1428,6 +1428,36 @@ int v2_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *x
 
 #include "decode2_bwd.cuh"
 
+namespace splatco {
+__global__ void __launch_bounds__(256)
+dec2_untile_kernel(int V, int nch, int DP, int LDX, const float4 *__restrict__ XT, float *__restrict__ out) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= V * LDX) return;
+    const int v = t / LDX, c = t - v * LDX;
+    float val = 0.f;
+    if (c < DP + GD) {
+        const int uc = c < DP ? D2_UP0 + c : c - DP;
+        val = reinterpret_cast<const float *>(XT + ((size_t)(v >> 7) * nch) * D2_ROWS + (v & 127))[d2_tile_idx(uc)];
+    }
+    out[t] = val;
+}
+}  // namespace splatco
+
+extern "C" int splatco_decode_gathered_rows(const void *ws, int V, int rc, int level, float *out, void *stream) {
+    SPLATCO_REQUIRE(ws && out && V > 0 && rc >= 1 && level >= 0 && level <= 2, "decode_gathered_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (use_v2(rc)) {
+        const D2Dims dd = d2_dims(V, rc, level);
+        dec2_untile_kernel<<<ceil_div(V * dd.LDX, 256), 256, 0, st>>>(V, dd.nch, dd.DP, dd.LDX, f2_view(const_cast<void *>(ws), dd).XT, out);
+        SPLATCO_CHECK_LAUNCH();
+    } else {
+        const DecDims dd = dec_dims(V, rc, level);
+        SPLATCO_CHECK_CUDA(cudaMemcpyAsync(out, fwd_view(const_cast<void *>(ws), dd).X, (size_t)V * dd.LDX * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
 extern "C" int splatco_decode_set_impl(int impl) {
     SPLATCO_REQUIRE(impl == 1 || impl == 2, "decode_set_impl: 1 (three-stage chain) or 2 (collapsed two-stage pipeline)");
     g_decode_impl = impl;

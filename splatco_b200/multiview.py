@@ -124,7 +124,7 @@ class GradBucket:
         bufs = list(flats) + ([small] if small is not None else [])
         self.last_bytes = 4 * sum(b.numel() for b in bufs)
         works = []
-        if len(bufs) > 1 and dev.type == "cuda" and hasattr(dist, "_coalescing_manager"):
+        if len(bufs) > 1 and dev.type == "cuda" and dist.get_backend(group) == "nccl" and hasattr(dist, "_coalescing_manager"):
             # one NCCL group launch for all buffers
             with dist._coalescing_manager(group=group, device=dev, async_ops=True) as cm:
                 for b in bufs:

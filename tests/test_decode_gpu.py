@@ -136,13 +136,14 @@ def test_eval_returns_five_and_no_visible_mask():
     assert outs[0].shape[0] == outs[2].shape[0] <= int(d["N"]) * int(d["K"])
 
 
-@pytest.mark.parametrize("level,rc", [(2, 5), (1, 3)])
-def test_decode_matches_oracle_large(level, rc):
-    """8k anchors, planes 128/128/256 (plane_size 512): GPU vs the CPU oracle restatement, fwd + grads."""
+@pytest.mark.parametrize("level,rc,N", [(2, 5, 8000), (1, 3, 8000), (2, 5, 60000), (0, 4, 30000)])
+def test_decode_matches_oracle_large(level, rc, N):
+    """8k .. 60k anchors (the larger cases give every persistent CTA of the tensor-core kernels several 128-anchor tiles),
+    planes 128/128/256 (plane_size 512): GPU vs the CPU oracle restatement, fwd + grads."""
     from oracle import decode_oracle as D
     from splatco_b200.gaussian_renderer import generate_neural_gaussians
     from splatco_b200.model import AnchorModel
-    N, K = 8000, 10
+    K = 10
     pc = AnchorModel(N, n_offsets=K, plane_size=512, num_channels=3 * rc, device="cuda", seed=3)
     pc.feat_planes.Q0 = 0.0
     pc.feat_planes._feat.activate_level = level
@@ -199,6 +200,7 @@ def test_decode_matches_oracle_large(level, rc):
 def test_plane_feature_noise_generated_in_kernel():
     """Q0 != 0 (training): U(-.5,.5)*Q is added to the plane features of levels >= 1 only (scene/grids.py:159-181:
     the TA level's noisy tensor is discarded), a fresh draw per call.  Read back from the gathered rows X."""
+    from splatco_b200 import _lib
     from splatco_b200.gaussian_renderer import generate_neural_gaussians
     from splatco_b200.model import AnchorModel
     N, K, rc = 6000, 10, 5
@@ -211,7 +213,11 @@ def test_plane_feature_noise_generated_in_kernel():
         pc.feat_planes.Q0 = Q
         outs = generate_neural_gaussians(cam, pc, None, is_training=True)
         ws = outs[0].grad_fn.ws
-        return ws[: N * LDX * 4].view(torch.float32).view(N, LDX).clone()
+        rows = torch.empty(N, LDX, device="cuda")
+        L = _lib.lib()
+        _lib.check(L.splatco_decode_gathered_rows(_lib.ptr(ws), N, rc, 2, _lib.ptr(rows), _lib.raw_stream(rows.device)),
+                   "splatco_decode_gathered_rows")
+        return rows
 
     Q = 0.03
     x0, x1, x2 = gathered(0.0), gathered(Q), gathered(Q)

@@ -272,3 +272,44 @@ def test_large_image_binning_paths_agree():
     assert np.array_equal(chunk(image, io[0], torch.int32, 2 * T).view(T, 2).cpu().numpy(), g["ranges"])
     img = color.cpu().numpy()
     assert np.isfinite(img).all() and img.min() >= -1e-6 and img.max() <= 1.0 + 1e-5
+
+
+def test_upstream_structure_comparator_matches_product_and_oracle():
+    """bench.py's same-GPU comparator (csrc/blend_upstream.cu: upstream's blend structure restated -- 256-instance batches,
+    per-pixel atomics) must compute what the product kernels compute: same image / n_contrib as the oracle, same
+    per-Gaussian blend gradients as splatco_blend_bwd."""
+    from splatco_b200 import _lib
+    from splatco_b200._lib import check, ptr
+    W, H, M = 300, 200, 30_000
+    cam, means, colors, opac, scales, rots = scene(M, W, H, 19)
+    bg = [0.3, 0.5, 0.7]
+    fw = oracle_forward(cam, means, colors, opac, scales, rots, bg)
+    color, radii, state, st = gpu_forward(cam, means, colors, opac, scales, rots, bg)
+    L = _lib.lib()
+    stream = _lib.raw_stream(color.device)
+    bgd = torch.tensor(bg, device="cuda")
+    n_prod = unpack_state(state)["n_contrib"].copy()
+    img_up = torch.empty_like(color)
+    check(L.splatco_blend_fwd_upstream(state.RL, H, W, ptr(bgd), ptr(state.geom), ptr(state.binning), ptr(state.image), ptr(img_up), stream),
+          "splatco_blend_fwd_upstream")
+    torch.cuda.synchronize()
+    err = np.abs(img_up.cpu().numpy() - fw["image"])
+    assert err[:, ~fw["fragile"]].max() <= 1e-4
+    g_up = unpack_state(state)
+    assert np.array_equal(g_up["n_contrib"][~fw["fragile"]], n_prod[~fw["fragile"]])
+    dL = torch.randn(3, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(2)) * 1e-3
+    P = state.P
+
+    def run(fn):
+        z = lambda c: torch.zeros(P, c, device="cuda")
+        g2d, gcon, gop, gcol = z(3), z(3), z(1), z(3)
+        check(fn(P, state.RL, H, W, ptr(bgd), ptr(state.geom), ptr(state.binning), ptr(state.image), ptr(dL), ptr(g2d), ptr(gcon),
+                 ptr(gop), ptr(gcol), stream), "blend_bwd")
+        torch.cuda.synchronize()
+        return [t.cpu().numpy() for t in (g2d, gcon, gop, gcol)]
+
+    up = run(L.splatco_blend_bwd_upstream)
+    # (the forward above re-wrote final_T / n_contrib with the comparator's values: both backward kernels replay from them)
+    prod = run(L.splatco_blend_bwd)
+    for name, a, b in zip(("mean2D", "conic", "opacity", "colour"), up, prod):
+        assert rel_err(a, b) < 2e-3, name
