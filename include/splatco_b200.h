@@ -139,6 +139,12 @@ int splatco_blend_fwd_upstream(int64_t R, int H, int W, const float *bg, const v
 int splatco_blend_bwd_upstream(int P, int64_t R, int H, int W, const float *bg, const void *geom, const void *binning,
                                const void *image, const float *dL_dpix, float *dL_dmean2D, float *dL_dconic,
                                float *dL_dopacity, float *dL_dcolor, void *stream);
+
+/* Work census of a view's blend (measurement aid, bench.py's issue-slot roofline): out2[0] = (pixel, instance) pairs
+ * the front-to-back walk visits before each pixel terminates, out2[1] = LIVE pairs among them (alpha >= 1/255: the pairs
+ * that contribute colour and receive gradients).  out2: two device uint64. */
+int splatco_blend_census(int64_t R, int H, int W, const void *geom, const void *binning, const void *image,
+                         unsigned long long *out2, void *stream);
 int splatco_preprocess_bwd(int P, const float *means3D, const float *scales, int scale_stride,
                            const float *rots, float scale_mod, const float *view, const float *proj,
                            float tanfovx, float tanfovy, int H, int W, const int32_t *radii,
@@ -217,6 +223,11 @@ int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opa
  * is process-wide, must not change between a forward and its backward, and is meant for A/B timing and debugging
  * (environment: SPLATCO_DECODE_IMPL=1|2). */
 int splatco_decode_set_impl(int impl);
+/* Measurement aid: with profiling enabled the library brackets the tensor-core MLP kernel of every splatco_decode_fwd /
+ * splatco_decode_bwd with CUDA events on the caller's stream; splatco_decode_profile_read returns the device time (ms)
+ * of the most recent forward / backward MLP kernel once the stream has been synchronised. */
+int splatco_decode_profile(int enable);
+int splatco_decode_profile_read(float *fwd_mlp_ms, float *bwd_mlp_ms);
 int splatco_decode_get_impl(void);
 /* Introspection for the tests: the gathered rows [V, LDX] of a finished splatco_decode_fwd (LDX = round_up4(DP + 71),
  * columns [plane features DP | anchor_feat 32 | anchor 3 | offsets 30 | scaling 6 | zero padding]), whatever the

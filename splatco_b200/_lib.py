@@ -43,6 +43,7 @@ SIGNATURES = {
     "splatco_blend_bwd": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_blend_fwd_upstream": (_i, [_i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_blend_bwd_upstream": (_i, [_i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "splatco_blend_census": (_i, [_i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_bwd": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     # decode: descriptor / gradient structs are passed with ctypes.byref (see decode.py)
     "splatco_pack_planes": (_i, [_i, _i] + [_vp] * 7),
@@ -52,6 +53,8 @@ SIGNATURES = {
     "splatco_decode_count_ptr": (_vp, [_vp, _i, _i, _i]),
     "splatco_decode_gathered_rows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "splatco_decode_set_impl": (_i, [_i]),
+    "splatco_decode_profile": (_i, [_i]),
+    "splatco_decode_profile_read": (_i, [_vp, _vp]),
     "splatco_decode_get_impl": (_i, []),
     "splatco_decode_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

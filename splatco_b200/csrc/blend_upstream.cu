@@ -143,9 +143,75 @@ blend_bwd_upstream_kernel(const int2 *__restrict__ ranges, const uint32_t *__res
     }
 }
 
+// Work census of a view's blend (for the issue-slot roofline bench.py reports): per pixel, how many instances the
+// front-to-back walk visits before it terminates, and how many of those are LIVE (power <= 0 and alpha >= 1/255, i.e.
+// they contribute colour and receive gradients).  out[0] = visited (pixel, instance) pairs, out[1] = live pairs.
+__global__ void __launch_bounds__(UP_THREADS)
+blend_census_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list, const float4 *__restrict__ rec,
+                    int W, int H, int gx, unsigned long long *__restrict__ out) {
+    __shared__ float2 s_xy[UP_THREADS];
+    __shared__ float4 s_co[UP_THREADS];
+    const int tile = blockIdx.y * gx + blockIdx.x;
+    const int px = blockIdx.x * TILE + (threadIdx.x & 15), py = blockIdx.y * TILE + (threadIdx.x >> 4);
+    const bool inside = px < W && py < H;
+    const float fx = (float)px, fy = (float)py;
+    const int2 range = ranges[tile];
+    int todo = range.y - range.x;
+    bool done = !inside;
+    float T = 1.f;
+    unsigned visited = 0, live = 0;
+    for (int base = range.x; todo > 0; base += UP_THREADS, todo -= UP_THREADS) {
+        if (__syncthreads_count(done) == UP_THREADS) break;
+        if ((int)threadIdx.x < todo) {
+            const uint32_t id = point_list[base + threadIdx.x];
+            const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1];
+            s_xy[threadIdx.x] = make_float2(r0.x, r0.y);
+            s_co[threadIdx.x] = make_float4(r0.z, r0.w, r1.x, r1.y);
+        }
+        __syncthreads();
+        for (int j = 0; !done && j < min(UP_THREADS, todo); ++j) {
+            ++visited;
+            const float dx = s_xy[j].x - fx, dy = s_xy[j].y - fy;
+            const float4 co = s_co[j];
+            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+            if (power > 0.f) continue;
+            const float alpha = fminf(0.99f, co.w * __expf(power));
+            if (alpha < 1.f / 255.f) continue;
+            const float test_T = T * (1.f - alpha);
+            if (test_T < 0.0001f) { done = true; continue; }
+            T = test_T;
+            ++live;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        visited += __shfl_xor_sync(0xffffffffu, visited, d);
+        live += __shfl_xor_sync(0xffffffffu, live, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], (unsigned long long)visited);
+        atomicAdd(&out[1], (unsigned long long)live);
+    }
+}
+
 }  // namespace splatco
 
 using namespace splatco;
+
+extern "C" int splatco_blend_census(int64_t R, int H, int W, const void *geom, const void *binning, const void *image,
+                                    unsigned long long *out2, void *stream) {
+    SPLATCO_REQUIRE(H > 0 && W > 0 && R >= 0 && R < 0x7fffffff && image && out2, "blend_census: bad arguments");
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+    if (R == 0) return 0;
+    SPLATCO_REQUIRE(geom && binning, "blend_census: null workspace");
+    ImgWs im = img_view(const_cast<void *>(image), H, W);
+    const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
+    const uint32_t *plist = bin_view(const_cast<void *>(binning), R).vals[splatco_sorted_buffer_index(H, W)];
+    blend_census_kernel<<<dim3(gx, gy), UP_THREADS, 0, (cudaStream_t)stream>>>(im.ranges, plist, reinterpret_cast<const float4 *>(geom),
+                                                                              W, H, gx, out2);
+    SPLATCO_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int splatco_blend_fwd_upstream(int64_t R, int H, int W, const float *bg, const void *geom, const void *binning,
                                           void *image, float *out_color, void *stream) {

@@ -714,6 +714,7 @@ struct DecWeightGrads {
     float *app_vec;
 };
 
+constexpr int BWD_FOLD_CTAS = 4, BWD_FOLD_SECTIONS = 11;
 __global__ void __launch_bounds__(256)
 dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, int DP, int LDX,
                     const float *__restrict__ mu, const float *__restrict__ rstd, const float *__restrict__ WpG,
@@ -721,10 +722,15 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
                     const float *__restrict__ S0 /*[64]*/, const float *__restrict__ gW1T, const float *__restrict__ gb1,
                     const float *__restrict__ gW2T, const float *__restrict__ gb2, float *__restrict__ m1,
                     float *__restrict__ m2) {
-    const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;      // every output is independent
+    // Every output is independent: blockIdx.y selects one SECTION of the outputs (BN-backward constants, one level's plane
+    // branch, one level's context branch, one head, the appearance vector) so that the sections -- each a short chain of
+    // dependent global loads -- run side by side instead of one after the other in every CTA.
+    const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
+    const int sec = blockIdx.y;
     const int ncols = DP + GD;
     const float invV = 1.f / (float)V;
     // S1[o][c] = sum_rows dgeo[o] * xhat[c] = rstd[c] * (S1raw[o][c] - mu[c] * S0branch[o])
+    if (sec == 0)
     for (int c = tid; c < LDX; c += nthr) {
         if (c >= ncols) { m1[c] = 0.f; m2[c] = 0.f; continue; }
         const bool pl = c < DP;
@@ -743,6 +749,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
     // plane branch parameter grads
     for (int l = 0; l <= level; ++l) {
         const int d = level_dim(l, rc), base = level_base(l, rc);
+        if (sec == 1 + l) {
         for (int e = tid; e < 32 * d; e += nthr) {
             const int o = e / d, cl = e - o * d, c = base + cl;
             const float s1 = rstd[c] * (S1raw[o * LDX + c] - mu[c] * S0[o]);
@@ -760,6 +767,8 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
             if (gw.bn_b[l]) gw.bn_b[l][cl] += gb;
         }
         if (tid < 32 && gw.lin_b[l]) gw.lin_b[l][tid] += S0[tid];      // tid is grid-wide: only CTA 0 has tid < 32
+        }
+        if (sec != 4 + l) continue;
         // context branch
         for (int e = tid; e < 32 * GD; e += nthr) {
             const int o = e / GD, g = e - o * GD, c = DP + g;
@@ -781,6 +790,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
     }
     // heads: un-fold gW1T[k][n] / gW2T[i][j] into torch layouts
     for (int hd = 0; hd < 3; ++hd) {
+        if (sec != 7 + hd) continue;
         const int dd = w.use_dist[hd];
         const int app = hd == 2 ? w.app_dim : 0;
         const int in_h = 35 + dd + 64 + app;
@@ -806,7 +816,7 @@ dec_bwd_fold_kernel(DecWeights w, DecWeightGrads gw, int V, int rc, int level, i
         if (gw.b2[hd])
             for (int j = tid; j < nout; j += nthr) gw.b2[hd][j] += gb2[j0 + j];
     }
-    if (gw.app_vec && w.app_dim > 0) {
+    if (sec == 10 && gw.app_vec && w.app_dim > 0) {
         const int dd = w.use_dist[2];
         const int in_h = 35 + dd + 64 + w.app_dim;
         for (int a = tid; a < w.app_dim; a += nthr) {
@@ -1184,7 +1194,7 @@ static int v1_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void 
         dec_wgrad_kernel<<<ctas, 256, 0, st>>>(grp, V);
         SPLATCO_CHECK_LAUNCH();
     }
-    dec_bwd_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+    dec_bwd_fold_kernel<<<dim3(BWD_FOLD_CTAS, BWD_FOLD_SECTIONS), 256, 0, st>>>(w, gw, V, dd.rc, dd.level, DP, LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                            b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();
     dec_bwd_inputs_kernel<<<gather_grid(V), GATHER_WARPS * 32, 0, st>>>(p, gi, V, dd.rc, DP, LDX, f.X, f.XIN, f.mu, f.rstd,
@@ -1257,6 +1267,18 @@ extern "C" int splatco_unpack_planes_add(int rc, int E, const float *gpxy, const
 namespace {
 
 int g_decode_impl = 0;      // 0: not read yet, 1: v1, 2: v2
+int g_decode_profile = 0;
+cudaEvent_t g_prof_ev[64][4];          // per device: fwd begin / end, bwd begin / end
+unsigned char g_prof_have[64];
+void prof_record(int which, cudaStream_t st) {
+    if (!g_decode_profile) return;
+    const int d = current_device() & 63;
+    if (!g_prof_have[d]) {
+        for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof_ev[d][i]);
+        g_prof_have[d] = 1;
+    }
+    cudaEventRecord(g_prof_ev[d][which], st);
+}
 int decode_impl() {
     if (!g_decode_impl) {
         const char *e = getenv("SPLATCO_DECODE_IMPL");
@@ -1402,8 +1424,10 @@ int v2_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity,
     a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.ntiles = dd.ntiles;
     a.XT = f.XT; a.W1S = f.W1S; a.W2B = f.W2B; a.b2blk = f.b2blk; a.HT = f.HT; a.ZT = f.ZT;
     a.nopac = neural_opacity; a.mask_out = mask; a.maskbits = f.maskbits; a.block_sums = f.bsum;
+    prof_record(0, st);
     dec2_mlp_fwd_kernel<<<min(dd.ntiles, D2_MAX_CTAS), D2_THREADS, D2F_SMEM, st>>>(a);
     SPLATCO_CHECK_LAUNCH();
+    prof_record(1, st);
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
     SPLATCO_CHECK_LAUNCH();
     dec_offsets_kernel<<<nb, 256, 0, st>>>(dd.V, f.maskbits, f.boff, f.offs);
@@ -1464,6 +1488,14 @@ extern "C" int splatco_decode_set_impl(int impl) {
     return 0;
 }
 extern "C" int splatco_decode_get_impl(void) { return decode_impl(); }
+extern "C" int splatco_decode_profile(int enable) { g_decode_profile = enable ? 1 : 0; return 0; }
+extern "C" int splatco_decode_profile_read(float *fwd_mlp_ms, float *bwd_mlp_ms) {
+    const int d = current_device() & 63;
+    SPLATCO_REQUIRE(g_prof_have[d], "decode_profile_read: nothing recorded on this device");
+    if (fwd_mlp_ms) SPLATCO_CHECK_CUDA(cudaEventElapsedTime(fwd_mlp_ms, g_prof_ev[d][0], g_prof_ev[d][1]));
+    if (bwd_mlp_ms) SPLATCO_CHECK_CUDA(cudaEventElapsedTime(bwd_mlp_ms, g_prof_ev[d][2], g_prof_ev[d][3]));
+    return 0;
+}
 
 // workspaces are sized for whichever implementation is larger, so the choice may change between calls
 extern "C" size_t splatco_decode_fwd_ws_bytes(int V, int rc, int level) {

@@ -30,11 +30,16 @@ constexpr uint32_t D2B_W1R = 2 * D2B_DHLO;                           // 98304
 constexpr uint32_t D2B_DGA = D2B_W1R + 2 * 24 * 144 * 16;            // 208896
 constexpr int D2B_DGA_LD = 41;
 constexpr uint32_t D2B_SMEM = D2B_DGA + D2_ROWS * D2B_DGA_LD * 4;    // 229888
-constexpr uint32_t D2B_LA = 129 * 16, D2B_LH = 97 * 16, D2B_LU = 145 * 16;   // chunk strides of the transposed quarter tiles
-// w2 quarter: dZ^T hi | lo | H^T hi | lo       g quarter: dH^T hi | lo | u^T hi | lo
+// chunk strides of the transposed quarter tiles ((rows + 1) * 16 B).  The 96-row tiles (H^T, dH^T) are read with M or N = 96
+// .. 128: an M = 128 product reads rows 96..127 of a chunk from the next chunk's first rows -- finite data that only
+// reaches accumulator rows nobody reads.
+constexpr uint32_t D2B_LA = 129 * 16, D2B_LH = 97 * 16, D2B_LU = 145 * 16;
+// w2 quarter: dZ^T hi | lo | H^T hi | lo (single buffer)     g quarter: dH^T hi | lo | u^T hi | lo (two buffers)
 constexpr uint32_t D2B_QW_A = D2B_W2R, D2B_QW_B = D2B_QW_A + 2 * 8 * D2B_LA;
-constexpr uint32_t D2B_QG_A = D2B_W1R, D2B_QG_B = D2B_QG_A + 2 * 8 * D2B_LA;
-static_assert(D2B_QW_B + 2 * 8 * D2B_LH <= D2B_DGA && D2B_QG_B + 2 * 8 * D2B_LU <= D2B_DGA, "quarter tiles overlap the direct gradients");
+constexpr uint32_t D2B_QG_BYTES = 2 * 8 * D2B_LH + 2 * 8 * D2B_LU;   // 61952
+constexpr uint32_t D2B_QG_A = D2B_W1R, D2B_QG_B = D2B_QG_A + 2 * 8 * D2B_LH;
+static_assert(D2B_QW_B + 2 * 8 * D2B_LH <= D2B_DGA, "w2 quarter tiles overlap the direct gradients");
+static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_DGA + D2_ROWS * 41 * 4, "g quarter tiles exceed the shared memory");
 
 struct D2Bwd {
     int V, nch, nk, NB, ntiles;
@@ -75,13 +80,14 @@ __device__ __forceinline__ void d2_split4(const float4 &x, float4 &h, float4 &l)
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dec2_mlp_bwd_kernel(D2Bwd a) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ;
+    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2];
     __shared__ uint32_t tmem_s;
     __shared__ float s_gb2[128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
     if (tid == 0) {
         tc::mbar_init(&barWa, 1); tc::mbar_init(&barWb, 1); tc::mbar_init(&barB1, 1); tc::mbar_init(&barB2, 1); tc::mbar_init(&barQ, 1);
+        tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1);
         tc::fence_barrier_init();
     }
     if (tid < 128) s_gb2[tid] = 0.f;
@@ -93,7 +99,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
     const int ntl = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t w1r_half = 24u * (uint32_t)a.NB * 16u;
     constexpr uint32_t T_DH = 0, T_DU = 96, T_GW2 = 240, T_GT = 336;
-    uint32_t qph = 0;                                        // phases of barQ this thread has waited for
+    uint32_t qph = 0, gph[2] = {0, 0};                       // phases of barQ / barG[] this thread has waited for
 
     if (warp == D2_WORKERS / 32) {
         // =========================== control warp ===========================
@@ -101,7 +107,11 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
         const uint32_t idNB = tc::make_idesc_tf32(128, a.NB);
         for (int it = 0; it < ntl; ++it) {
             const uint32_t par = it & 1;
-            if (lane == 0) {                                 // (all quarter products of the previous tile have completed)
+            if (it > 0) {                                    // the last two g products of the previous tile still read their tiles
+                tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
+                tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
+            }
+            if (lane == 0) {
                 tc::mbar_arrive_expect_tx(&barWa, 2 * D2_W2R_HALF);
                 tc::bulk_g2s(sm + D2B_W2R, a.W2R, 2 * D2_W2R_HALF, &barWa);
             }
@@ -142,15 +152,15 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             __syncwarp();
             tc::mbar_wait(&barB2, par);
             for (int q = 0; q < 4; ++q) {
-                d2_bar_sync_all();                           // 7..10: g quarter operands written
+                d2_bar_sync_all();                           // 7..10: g quarter operands written (buffer q & 1)
                 tc::tc_fence_after();
+                if (q >= 2) { tc::mbar_wait(&barG[q & 1], gph[q & 1] & 1); ++gph[q & 1]; }   // (keeps this thread's phase count in step)
                 if (lane == 0) {
-                    d2_issue_lbo(tmem + T_GT, sb + D2B_QG_A, sb + D2B_QG_A + 8 * D2B_LA, D2B_LA, sb + D2B_QG_B, sb + D2B_QG_B + 8 * D2B_LU,
-                                 D2B_LU, 4, id144, it > 0 || q > 0);
-                    tc::mma_commit(&barQ);
+                    const uint32_t qa = sb + D2B_QG_A + (q & 1) * D2B_QG_BYTES, qb = sb + D2B_QG_B + (q & 1) * D2B_QG_BYTES;
+                    d2_issue_lbo(tmem + T_GT, qa, qa + 8 * D2B_LH, D2B_LH, qb, qb + 8 * D2B_LU, D2B_LU, 4, id144, it > 0 || q > 0);
+                    tc::mma_commit(&barG[q & 1]);
                 }
                 __syncwarp();
-                tc::mbar_wait(&barQ, qph & 1); ++qph;
             }
         }
     } else {
@@ -247,9 +257,12 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                             atomicAdd(&s_gb2[q == 0 ? k : (q < 8 ? D2_RCOV + 7 * k + (q - 1) : D2_RCOL + 3 * k + (q - 8))], s);
                     }
                 }
-                // every quarter product of the previous tile has completed (the control warp waited before its bulk copy,
+                // the last two g products of the previous tile have completed (the control warp waited before its bulk copy,
                 // these threads wait here): the dZ rows may be overwritten
-                if (it > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                if (it > 0) {
+                    tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
+                    tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
+                }
                 auto putz = [&](int col, float x) {
                     const float h = tc::tf32_hi(x);
                     const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)rp * 16u + (uint32_t)(col & 3) * 4u;
@@ -287,9 +300,20 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                     hbits |= ((h.x > 0.f ? 1u : 0u) | (h.y > 0.f ? 2u : 0u) | (h.z > 0.f ? 4u : 0u) | (h.w > 0.f ? 8u : 0u)) << (4 * c);
                 }
             }
+            // ---- w2: gW2 += dZ^T H, 32 anchors at a time; the H cells of the next quarter are fetched while the current
+            //      one multiplies ---------------------------------------------------------------------------------------------
+            const float4 *ht_tile = a.HT + (size_t)tile * 24 * D2_ROWS;
+            float4 hpre[2];
+            auto load_h = [&](int q) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int e = tid + i * D2_WORKERS;
+                    if (e < 24 * 32) hpre[i] = __ldg(ht_tile + (e >> 5) * D2_ROWS + 32 * q + (e & 31));
+                }
+            };
+            load_h(0);
             tc::mbar_wait(&barB1, par);
             tc::tc_fence_after();
-            // ---- w2: gW2 += dZ^T H, 32 anchors at a time -------------------------------------------------------------------
             for (int q = 0; q < 4; ++q) {
                 if (q > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
                 for (int e = tid; e < D2_RCH * 32; e += D2_WORKERS) {
@@ -298,12 +322,16 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                     d2_put_t(sm, D2B_QW_A, D2B_QW_A + 8 * D2B_LA, D2B_LA, 4 * c, rr, *reinterpret_cast<const float4 *>(sm + o),
                              *reinterpret_cast<const float4 *>(sm + D2B_DZLO + o));
                 }
-                for (int e = tid; e < 24 * 32; e += D2_WORKERS) {
-                    const int c = e >> 5, rr = 32 * q + (e & 31);
-                    float4 h, l;
-                    d2_split4(__ldg(a.HT + ((size_t)tile * 24 + c) * D2_ROWS + rr), h, l);
-                    d2_put_t(sm, D2B_QW_B, D2B_QW_B + 8 * D2B_LH, D2B_LH, 4 * c, rr, h, l);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int e = tid + i * D2_WORKERS;
+                    if (e < 24 * 32) {
+                        float4 h, l;
+                        d2_split4(hpre[i], h, l);
+                        d2_put_t(sm, D2B_QW_B, D2B_QW_B + 8 * D2B_LH, D2B_LH, 4 * (e >> 5), 32 * q + (e & 31), h, l);
+                    }
                 }
+                if (q < 3) load_h(q + 1);
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
                 d2_bar_sync_all();                           // 2..5
@@ -343,6 +371,16 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             tc::fence_proxy_async();
             tc::tc_fence_before();
             d2_bar_sync_all();                               // 6
+            const float4 *xt_tile = a.XT + (size_t)tile * a.nch * D2_ROWS;
+            float4 upre[3];
+            auto load_u = [&](int q) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int e = tid + i * D2_WORKERS;
+                    if (e < a.nch * 32) upre[i] = __ldg(xt_tile + (e >> 5) * D2_ROWS + 32 * q + (e & 31));
+                }
+            };
+            load_u(0);
             tc::mbar_wait(&barB2, par);
             tc::tc_fence_after();
             // ---- epilogue b2: dU (+ direct gradients on the anchor / offset / scaling columns) -> DUT ------------------------
@@ -362,21 +400,27 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                     if (2 * gi + 1 < a.nch) du[(2 * gi + 1) * D2_ROWS] = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
-            // ---- g: GT += dH^T u, 32 anchors at a time -------------------------------------------------------------------------
+            // ---- g: GT += dH^T u, 32 anchors at a time, two tile buffers: quarter q + 1 is written while quarter q multiplies;
+            //      the u cells are fetched one quarter ahead ---------------------------------------------------------------------
             for (int q = 0; q < 4; ++q) {
-                if (q > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                const uint32_t qo = (q & 1) * D2B_QG_BYTES;
+                if (q >= 2) { tc::mbar_wait(&barG[q & 1], gph[q & 1] & 1); ++gph[q & 1]; }
                 for (int e = tid; e < 24 * 32; e += D2_WORKERS) {
                     const int c = e >> 5, rr = 32 * q + (e & 31);
                     const uint32_t o = (uint32_t)c * D2_CHUNK + (uint32_t)rr * 16u;
-                    d2_put_t(sm, D2B_QG_A, D2B_QG_A + 8 * D2B_LA, D2B_LA, 4 * c, rr, *reinterpret_cast<const float4 *>(sm + o),
+                    d2_put_t(sm, D2B_QG_A + qo, D2B_QG_A + qo + 8 * D2B_LH, D2B_LH, 4 * c, rr, *reinterpret_cast<const float4 *>(sm + o),
                              *reinterpret_cast<const float4 *>(sm + D2B_DHLO + o));
                 }
-                for (int e = tid; e < a.nch * 32; e += D2_WORKERS) {
-                    const int c = e >> 5, rr = 32 * q + (e & 31);
-                    float4 h, l;
-                    d2_split4(__ldg(a.XT + ((size_t)tile * a.nch + c) * D2_ROWS + rr), h, l);
-                    d2_put_t(sm, D2B_QG_B, D2B_QG_B + 8 * D2B_LU, D2B_LU, 4 * c, rr, h, l);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int e = tid + i * D2_WORKERS;
+                    if (e < a.nch * 32) {
+                        float4 h, l;
+                        d2_split4(upre[i], h, l);
+                        d2_put_t(sm, D2B_QG_B + qo, D2B_QG_B + qo + 8 * D2B_LU, D2B_LU, 4 * (e >> 5), 32 * q + (e & 31), h, l);
+                    }
                 }
+                if (q < 3) load_u(q + 1);
                 tc::fence_proxy_async();
                 tc::tc_fence_before();
                 d2_bar_sync_all();                           // 7..10
@@ -384,7 +428,8 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
         }
         // ---- the CTA's weight-gradient accumulators leave TMEM once ---------------------------------------------------------------
         if (ntl > 0) {
-            tc::mbar_wait(&barQ, qph & 1); ++qph;
+            tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
+            tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
             tc::tc_fence_after();
             float *pw = a.part + (size_t)blockIdx.x * D2_PART + (size_t)r * HD + 24 * grp;
 #pragma unroll
@@ -453,14 +498,16 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
     a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.part = b.part; a.gb2blk = b.gb2blk;
     const int ctas = min(dd.ntiles, D2_MAX_CTAS);
+    prof_record(2, st);
     dec2_mlp_bwd_kernel<<<ctas, D2_THREADS, D2B_SMEM, st>>>(a);
     SPLATCO_CHECK_LAUNCH();
+    prof_record(3, st);
     dec2_reduce_kernel<<<ceil_div(D2_PART, 256), 256, 0, st>>>(ctas, b.part, b.red);
     SPLATCO_CHECK_LAUNCH();
     dec2_expand_kernel<<<48, 256, 0, st>>>(dd.DP, dd.LDX, b.red, b.gb2blk, f.WpT, f.WcT, f.bgeo, f.W1T, b.S1, b.S0, b.gW1T, b.gb1,
                                            b.gW2T, b.gb2);
     SPLATCO_CHECK_LAUNCH();
-    dec_bwd_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, gw, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+    dec_bwd_fold_kernel<<<dim3(BWD_FOLD_CTAS, BWD_FOLD_SECTIONS), 256, 0, st>>>(w, gw, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                                    b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();
     if (D2_DISPATCH(launch_inputs2, dd.level, dd.rc, d->plane_layout != 0, st, p, gi, dd, f.XT, b.DUT, f.mu, f.rstd, b.m1, b.m2)) return -2;

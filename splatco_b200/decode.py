@@ -357,7 +357,9 @@ class _PackPlanes(torch.autograd.Function):
 
 
 # "auto": pack when the mv views of an iteration amortise the two extra passes over the planes; True / False force it
-PACK_PLANES = "auto"
+# (SPLATCO_PACK_PLANES=0|1 in the environment forces it for A/B timing)
+import os as _os
+PACK_PLANES = {"0": False, "1": True}.get(_os.environ.get("SPLATCO_PACK_PLANES", ""), "auto")
 
 
 class _PackCache:
@@ -378,11 +380,12 @@ class _PackCache:
         self.key, self.uses = key, 1
         want = PACK_PLANES
         if want == "auto":
-            # measured on B200 (profiles/README.md, r1p): the channel-last layout saves ~0.7 ns per visible anchor and
-            # view in the gather + scatter kernels, packing / unpacking / zero-filling costs ~1.2 us per MB of planes
-            # per iteration -> worth it from roughly 2200 anchor-views per MB (C3: yes, C2 at mv=4: break-even, no)
+            # measured on B200 (round 2, C2): with the one-thread-per-anchor gather / scatter kernels (16-byte texel
+            # loads, vector REDs) the channel-last layout saves ~1.2 ns per visible anchor and view; packing, unpacking
+            # and zero-filling cost ~0.6 us per MB of planes per iteration -> worth it from ~500 anchor-views per MB
+            # (C2 at mv = 4: 1850 per MB, yes: 2.26 -> 2.16 ms/view)
             plane_mb = sum(t.numel() for t in planes) * 4 / 1e6
-            want = V * self.last_uses > 2200.0 * plane_mb
+            want = V * self.last_uses > 600.0 * plane_mb
         if not want or int(planes[0].shape[1]) > 8:
             self.value = None
             return None

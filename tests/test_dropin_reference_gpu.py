@@ -10,8 +10,9 @@ import-time-only packages, the test
   * option A: the reference's own `gaussian_renderer.prefilter_voxel` / `render` (its PyTorch decode,
     gaussian_renderer/__init__.py:18-188) on top of `splatco_b200.diff_gaussian_rasterization`;
   * option B: `splatco_b200.gaussian_renderer.prefilter_voxel` / `render` on the same model object;
-and requires the two to agree: prefilter mask and opacity mask identical, image <= 1e-4, every trained leaf's gradient
-<= 1e-3 relative (TriPlaneAttention's conv weights 3e-3), BatchNorm running statistics updated identically.
+and requires the two to agree: prefilter mask and opacity mask identical, image <= 1e-4 on 99.99 % of the pixels, every
+trained leaf's gradient within 1e-3 in norm (TriPlaneAttention's conv weights 3e-3; tests/util.full_path_grad_errors),
+BatchNorm running statistics updated identically.
 """
 import os
 import sys
@@ -21,7 +22,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import rel_err
+from tests.util import full_path_grad_errors
 
 pytestmark = pytest.mark.gpu
 # the reference's decode runs through torch / cuDNN here: keep its convolutions and matmuls in true fp32
@@ -48,7 +49,8 @@ def _reference_modules():
 
 
 def _real_model(gm, N=20000, K=10, plane_size=512, seed=3):
-    mp = SimpleNamespace(plane_size=plane_size, num_channels=15, mlp_dim=168, subplane_multiplier=1)
+    mp = SimpleNamespace(plane_size=plane_size, num_channels=15, mlp_dim=168, subplane_multiplier=1, bbox_scale=1.0,
+                         scene_center=[0.0, 0.0, 0.0], scene_length=[4.0, 4.0, 4.0], contractor=True)
     torch.manual_seed(seed)
     pc = gm.GaussianModel(feat_dim=32, n_offsets=K, voxel_size=0.01, update_depth=3, update_init_factor=16,
                           update_hierachy_factor=4, use_feat_bank=False, appearance_dim=0, ratio=1,
@@ -139,10 +141,11 @@ def test_real_reference_model_renders_through_the_dropin():
             assert (ga is None) == (gb is None), k
             if ga is None or float(np.abs(ga).max()) == 0.0:
                 continue
-            tol = 3e-3 if ".TA." in k else 1e-3
-            assert rel_err(gb, ga, floor_frac=3e-3) < tol, (k, rel_err(gb, ga, floor_frac=3e-3))
+            e = full_path_grad_errors(gb, ga)
+            assert e["l2"] < (3e-3 if ".TA." in k else 1e-3) and e["amax"] < 5e-3, (k, e)
             checked += 1
         assert checked >= 30
-        assert rel_err(b["vsp"][:, :2], a["vsp"][:, :2], floor_frac=3e-3) < 1e-3
+        e = full_path_grad_errors(b["vsp"][:, :2], a["vsp"][:, :2])
+        assert e["l2"] < 1e-3 and e["amax"] < 5e-3, e
     for k in bn_keys:
         assert torch.allclose(a["bn"][k].float(), b["bn"][k].float(), rtol=1e-4, atol=1e-6), k
