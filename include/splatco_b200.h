@@ -226,7 +226,10 @@ int splatco_decode_set_impl(int impl);
 /* Measurement aid: with profiling enabled the library brackets the tensor-core MLP kernel of every splatco_decode_fwd /
  * splatco_decode_bwd with CUDA events on the caller's stream; splatco_decode_profile_read returns the device time (ms)
  * of the most recent forward / backward MLP kernel once the stream has been synchronised. */
-int splatco_decode_profile(int enable);
+int splatco_decode_profile(int enable);      /* 0 off, 1 event timing of the MLP kernels, 2 phase trace (below) */
+/* With splatco_decode_profile(2): clock64 stamps of CTA 0 at the phase boundaries of its first tiles, [0..63] forward
+ * MLP kernel (8 per tile), [64..127] backward MLP kernel (16 per tile); read after synchronising.  tools/decode_trace.py. */
+int splatco_decode_trace_read(unsigned long long *out128);
 int splatco_decode_profile_read(float *fwd_mlp_ms, float *bwd_mlp_ms);
 int splatco_decode_get_impl(void);
 /* Introspection for the tests: the gathered rows [V, LDX] of a finished splatco_decode_fwd (LDX = round_up4(DP + 71),

@@ -55,6 +55,7 @@ SIGNATURES = {
     "splatco_decode_set_impl": (_i, [_i]),
     "splatco_decode_profile": (_i, [_i]),
     "splatco_decode_profile_read": (_i, [_vp, _vp]),
+    "splatco_decode_trace_read": (_i, [_vp]),
     "splatco_decode_get_impl": (_i, []),
     "splatco_decode_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_decode_emit": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -1271,7 +1271,7 @@ int g_decode_profile = 0;
 cudaEvent_t g_prof_ev[64][4];          // per device: fwd begin / end, bwd begin / end
 unsigned char g_prof_have[64];
 void prof_record(int which, cudaStream_t st) {
-    if (!g_decode_profile) return;
+    if (g_decode_profile != 1) return;
     const int d = current_device() & 63;
     if (!g_prof_have[d]) {
         for (int i = 0; i < 4; ++i) cudaEventCreate(&g_prof_ev[d][i]);
@@ -1421,7 +1421,7 @@ int v2_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity,
         attr_dev[attr_i] = 1;
     }
     D2Fwd a;
-    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.ntiles = dd.ntiles;
+    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.ntiles = dd.ntiles; a.trace = g_decode_profile == 2;
     a.XT = f.XT; a.W1S = f.W1S; a.W2B = f.W2B; a.b2blk = f.b2blk; a.HT = f.HT; a.ZT = f.ZT;
     a.nopac = neural_opacity; a.mask_out = mask; a.maskbits = f.maskbits; a.block_sums = f.bsum;
     prof_record(0, st);
@@ -1488,7 +1488,12 @@ extern "C" int splatco_decode_set_impl(int impl) {
     return 0;
 }
 extern "C" int splatco_decode_get_impl(void) { return decode_impl(); }
-extern "C" int splatco_decode_profile(int enable) { g_decode_profile = enable ? 1 : 0; return 0; }
+extern "C" int splatco_decode_profile(int enable) { g_decode_profile = enable; return 0; }
+extern "C" int splatco_decode_trace_read(unsigned long long *out128) {
+    SPLATCO_REQUIRE(out128, "decode_trace_read: null pointer");
+    SPLATCO_CHECK_CUDA(cudaMemcpyFromSymbol(out128, g_d2_trace, sizeof(unsigned long long) * 128));
+    return 0;
+}
 extern "C" int splatco_decode_profile_read(float *fwd_mlp_ms, float *bwd_mlp_ms) {
     const int d = current_device() & 63;
     SPLATCO_REQUIRE(g_prof_have[d], "decode_profile_read: nothing recorded on this device");

@@ -35,6 +35,12 @@ constexpr int D2_ZCH = 32;                           // ZT chunks: block columns
 constexpr int D2_ZCOV = 16, D2_ZCOL = 96;
 constexpr int D2_RCOV = 16, D2_RCOL = 88, D2_RCH = 30;   // dZ operand columns (backward): [opacity 16 | cov 72 | colour 32]
 
+// phase trace (measurement aid, splatco_decode_profile(2)): CTA 0's worker thread 0 stamps clock64 at the phase boundaries
+// of its first tiles; [0] = forward kernel, [1] = backward kernel
+__device__ unsigned long long g_d2_trace[2][64];
+#define D2_TRACE(which, slot)                                                                         \
+    do { if (a.trace && blockIdx.x == 0 && tid == 0 && (slot) < 64) g_d2_trace[which][slot] = clock64(); } while (0)
+
 struct D2Dims { int V, rc, level, DP, LDX, npc, nch, nk, NB, ntiles; };
 inline D2Dims d2_dims(int V, int rc, int level) {
     D2Dims d;
@@ -309,7 +315,7 @@ constexpr uint32_t D2F_RING = 2 * D2F_ULO;                          // 147456
 constexpr uint32_t D2F_SMEM = D2F_RING + 2 * D2_RING_SLOT;          // 221184
 
 struct D2Fwd {
-    int V, nch, nk, ntiles;
+    int V, nch, nk, ntiles, trace;
     const float4 *XT;
     const uint8_t *W1S, *W2B;
     const float *b2blk;
@@ -420,7 +426,9 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
             const int row = tile * D2_ROWS + r;
             const bool valid = row < a.V;
             const uint32_t par = it & 1;
+            D2_TRACE(0, 8 * it + 0);
             tc::mbar_wait(&barU, par);
+            D2_TRACE(0, 8 * it + 1);
             for (int e = tid; e < ncell; e += D2_WORKERS) {
                 float4 *ph = reinterpret_cast<float4 *>(sm + (size_t)e * 16);
                 const float4 x = *ph;
@@ -430,9 +438,11 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
+            D2_TRACE(0, 8 * it + 2);
             d2_bar_sync_all();                                  // A
             tc::mbar_wait(&barM1, par);
             tc::tc_fence_after();
+            D2_TRACE(0, 8 * it + 3);
             // ---- epilogue 1: H = relu(acc) -> HT (for the backward) and the stage-2 operand --------------------------
             {
                 float4 *ht = a.HT + ((size_t)tile * 24 + 6 * grp) * D2_ROWS + r;
@@ -458,9 +468,11 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
+            D2_TRACE(0, 8 * it + 4);
             d2_bar_sync_all();                                  // B
             tc::mbar_wait(&barM2, par);
             tc::tc_fence_after();
+            D2_TRACE(0, 8 * it + 5);
             // ---- epilogue 2: bias, tanh / sigmoid, mask bits, survivor counts -> ZT ----------------------------------
             uint32_t bits = 0;
             {
@@ -498,6 +510,7 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
                 for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
                 if (lane == 0 && cnt) atomicAdd(&a.block_sums[(tile * D2_ROWS + warp * 32) / 256], cnt);
             }
+            D2_TRACE(0, 8 * it + 6);
         }
     }
     tc::tc_fence_before();

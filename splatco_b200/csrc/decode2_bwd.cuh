@@ -15,7 +15,8 @@
 // Both products accumulate in TMEM over all tiles of the CTA and leave it once, as a per-CTA partial (dec2_reduce_kernel).
 //
 // Shared memory (bytes), regions alias across the phases of a tile:
-//   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600), then the w2 quarter tiles from 122880
+//   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600) | ZT tile [153600,219136) (P0 only), then the
+//             w2 quarter tiles from 122880
 //   b2/g    : dH rows hi [0,49152) lo [49152,98304) | W1R [98304,208896), then the g quarter tiles from 98304 |
 //             direct gradients [208896, 229888)
 // TMEM: dH acc [0,96) | dU acc [96,240) | gW2 acc [240,336) | GT acc [336,480).
@@ -25,6 +26,7 @@ namespace splatco {
 
 constexpr uint32_t D2B_DZLO = D2_RCH * D2_CHUNK;                     // 61440
 constexpr uint32_t D2B_W2R = 2 * D2B_DZLO;                           // 122880
+constexpr uint32_t D2B_ZST = D2B_W2R + 2 * D2_W2R_HALF;              // 153600: the tile's head outputs, staged for the un-compaction
 constexpr uint32_t D2B_DHLO = 24 * D2_CHUNK;                         // 49152
 constexpr uint32_t D2B_W1R = 2 * D2B_DHLO;                           // 98304
 constexpr uint32_t D2B_DGA = D2B_W1R + 2 * 24 * 144 * 16;            // 208896
@@ -42,7 +44,7 @@ static_assert(D2B_QW_B + 2 * 8 * D2B_LH <= D2B_DGA, "w2 quarter tiles overlap th
 static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_DGA + D2_ROWS * 41 * 4, "g quarter tiles exceed the shared memory");
 
 struct D2Bwd {
-    int V, nch, nk, NB, ntiles;
+    int V, nch, nk, NB, ntiles, trace;
     const float4 *XT, *HT, *ZT;
     const uint32_t *maskbits, *offs;
     const float *d_xyz, *d_color, *d_opacity, *d_scaling, *d_rot, *d_nopac;
@@ -53,14 +55,7 @@ struct D2Bwd {
 
 __device__ __forceinline__ void d2_issue_lbo(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lboA, uint32_t b_hi,
                                              uint32_t b_lo, uint32_t lboB, int ksteps, uint32_t idesc, bool accumulate_first) {
-    for (int s = 0; s < ksteps; ++s) {
-        const uint32_t ao = (uint32_t)(2 * s) * lboA, bo = (uint32_t)(2 * s) * lboB;
-        const uint64_t dah = tc::make_desc(a_hi + ao, lboA, 128), dal = tc::make_desc(a_lo + ao, lboA, 128);
-        const uint64_t dbh = tc::make_desc(b_hi + bo, lboB, 128), dbl = tc::make_desc(b_lo + bo, lboB, 128);
-        tc::mma_tf32(d_tmem, dal, dbh, idesc, accumulate_first || s > 0);
-        tc::mma_tf32(d_tmem, dah, dbl, idesc, true);
-        tc::mma_tf32(d_tmem, dah, dbh, idesc, true);
-    }
+    tc::issue_3xtf32_lbo(d_tmem, a_hi, a_lo, lboA, 0, b_hi, b_lo, lboB, 0, ksteps, idesc, accumulate_first);
 }
 
 // transposed hi/lo store of one 16-byte cell (4 consecutive columns m0.. of anchor row rr) into a quarter tile
@@ -80,14 +75,14 @@ __device__ __forceinline__ void d2_split4(const float4 &x, float4 &h, float4 &l)
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dec2_mlp_bwd_kernel(D2Bwd a) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2];
+    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2], barS;
     __shared__ uint32_t tmem_s;
     __shared__ float s_gb2[128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
     if (tid == 0) {
         tc::mbar_init(&barWa, 1); tc::mbar_init(&barWb, 1); tc::mbar_init(&barB1, 1); tc::mbar_init(&barB2, 1); tc::mbar_init(&barQ, 1);
-        tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1);
+        tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1); tc::mbar_init(&barS, 1);
         tc::fence_barrier_init();
     }
     if (tid < 128) s_gb2[tid] = 0.f;
@@ -112,6 +107,8 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                 tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
             }
             if (lane == 0) {
+                tc::mbar_arrive_expect_tx(&barS, D2_ZCH * D2_CHUNK);
+                tc::bulk_g2s(sm + D2B_ZST, a.ZT + (size_t)(blockIdx.x + it * gridDim.x) * D2_ZCH * D2_ROWS, D2_ZCH * D2_CHUNK, &barS);
                 tc::mbar_arrive_expect_tx(&barWa, 2 * D2_W2R_HALF);
                 tc::bulk_g2s(sm + D2B_W2R, a.W2R, 2 * D2_W2R_HALF, &barWa);
             }
@@ -173,96 +170,49 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
         for (int it = 0; it < ntl; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const uint32_t par = it & 1;
+            D2_TRACE(1, 16 * it + 0);
             // ---- P0: un-compaction (gaussian_renderer/__init__.py:96-111 backwards) --------------------------------------
+            // phase 1: every global load of this thread (upstream gradients of its <= 3 offsets, its offsets / scaling),
+            // issued together; phase 2: the head outputs come from the staged ZT tile in shared memory
             float dofr[9], acc9[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) { dofr[q] = 0.f; acc9[q] = 0.f; }
             {
                 const int v = tile * D2_ROWS + rp;
                 const bool valid = v < a.V;
-                const uint32_t bits = valid ? a.maskbits[v] : 0u;
-                const uint32_t off0 = valid ? a.offs[v] : 0u;
+                const uint32_t bits = valid ? __ldg(a.maskbits + v) : 0u;
+                const uint32_t off0 = valid ? __ldg(a.offs + v) : 0u;
                 const float *g = reinterpret_cast<const float *>(a.XT + (size_t)tile * a.nch * D2_ROWS + rp);
-                const float *z = reinterpret_cast<const float *>(a.ZT + (size_t)tile * D2_ZCH * D2_ROWS + rp);
-                float s6[6];
+                float s6[6], up[3][14], of[3][3], dnp[3];
 #pragma unroll
                 for (int q = 0; q < 6; ++q) s6[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + q));
-                float dz[3][11];
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) {
                     const int k = kq + 4 * kk;
+                    const bool live = k < KO && valid;
+                    const bool m = live && ((bits >> k) & 1u);
+                    dnp[kk] = (live && a.d_nopac) ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
+                    const size_t j = m ? off0 + __popc(bits & ((1u << k) - 1u)) : 0;
+                    up[kk][0] = m ? __ldg(a.d_opacity + j) : 0.f;
 #pragma unroll
-                    for (int q = 0; q < 11; ++q) dz[kk][q] = 0.f;
-                    if (k < KO && valid) {
-                        const bool m = (bits >> k) & 1u;
-                        const float no = __ldg(z + d2_tile_idx(d2_zcol_op(k)));
-                        float dno = a.d_nopac ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
-                        if (m) {
-                            const size_t j = off0 + __popc(bits & ((1u << k) - 1u));
-                            dno += __ldg(a.d_opacity + j);
-                            const float gx = __ldg(a.d_xyz + 3 * j), gy = __ldg(a.d_xyz + 3 * j + 1), gz = __ldg(a.d_xyz + 3 * j + 2);
-                            const float ox = __ldg(g + d2_tile_idx(FD + 3 + 3 * k)), oy = __ldg(g + d2_tile_idx(FD + 3 + 3 * k + 1)),
-                                        oz = __ldg(g + d2_tile_idx(FD + 3 + 3 * k + 2));
-                            dofr[3 * kk] = gx * s6[0]; dofr[3 * kk + 1] = gy * s6[1]; dofr[3 * kk + 2] = gz * s6[2];
-                            acc9[0] += gx; acc9[1] += gy; acc9[2] += gz;
-                            acc9[3] += gx * ox; acc9[4] += gy * oy; acc9[5] += gz * oz;
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const float c = __ldg(z + d2_tile_idx(d2_zcol_col(k, q)));
-                                dz[kk][8 + q] = __ldg(a.d_color + 3 * j + q) * c * (1.f - c);
-                            }
-                            float sr[7];
-#pragma unroll
-                            for (int q = 0; q < 7; ++q) sr[q] = __ldg(z + d2_tile_idx(d2_zcol_cov(k, q)));
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const float sg = 1.f / (1.f + expf(-sr[q]));
-                                const float gsc = __ldg(a.d_scaling + 3 * j + q);
-                                dz[kk][1 + q] = gsc * s6[3 + q] * sg * (1.f - sg);
-                                acc9[6 + q] += gsc * sg;
-                            }
-                            const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
-                            const float n = fmaxf(nrm, 1e-12f);
-                            const float r0 = sr[3] / n, r1 = sr[4] / n, r2 = sr[5] / n, r3 = sr[6] / n;
-                            const float g0 = __ldg(a.d_rot + 4 * j), g1 = __ldg(a.d_rot + 4 * j + 1), g2 = __ldg(a.d_rot + 4 * j + 2),
-                                        g3 = __ldg(a.d_rot + 4 * j + 3);
-                            if (nrm > 1e-12f) {
-                                const float dot = r0 * g0 + r1 * g1 + r2 * g2 + r3 * g3;
-                                dz[kk][4] = (g0 - r0 * dot) / n; dz[kk][5] = (g1 - r1 * dot) / n;
-                                dz[kk][6] = (g2 - r2 * dot) / n; dz[kk][7] = (g3 - r3 * dot) / n;
-                            } else {
-                                dz[kk][4] = g0 / n; dz[kk][5] = g1 / n; dz[kk][6] = g2 / n; dz[kk][7] = g3 / n;
-                            }
-                        }
-                        dz[kk][0] = dno * (1.f - no * no);
+                    for (int q = 0; q < 3; ++q) {
+                        up[kk][1 + q] = m ? __ldg(a.d_xyz + 3 * j + q) : 0.f;
+                        up[kk][4 + q] = m ? __ldg(a.d_color + 3 * j + q) : 0.f;
+                        up[kk][7 + q] = m ? __ldg(a.d_scaling + 3 * j + q) : 0.f;
+                        of[kk][q] = m ? __ldg(g + d2_tile_idx(FD + 3 + 3 * k + q)) : 0.f;
                     }
-                }
-                // the 4 lanes of a row hold partial sums over their offsets
 #pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 1);
-                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 2);
+                    for (int q = 0; q < 4; ++q) up[kk][10 + q] = m ? __ldg(a.d_rot + 4 * j + q) : 0.f;
                 }
-                // column sums of dZ (= the output-bias gradients): over the 8 rows of the warp, then one shared-memory add
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const int k = kq + 4 * kk;
-#pragma unroll
-                    for (int q = 0; q < 11; ++q) {
-                        float s = dz[kk][q];
-                        s += __shfl_xor_sync(0xffffffffu, s, 4);
-                        s += __shfl_xor_sync(0xffffffffu, s, 8);
-                        s += __shfl_xor_sync(0xffffffffu, s, 16);
-                        if (lane < 4 && k < KO && s != 0.f)
-                            atomicAdd(&s_gb2[q == 0 ? k : (q < 8 ? D2_RCOV + 7 * k + (q - 1) : D2_RCOL + 3 * k + (q - 8))], s);
-                    }
-                }
-                // the last two g products of the previous tile have completed (the control warp waited before its bulk copy,
-                // these threads wait here): the dZ rows may be overwritten
+                D2_TRACE(1, 16 * it + 1);
+                // the last two g products of the previous tile have completed (the control warp waited before its bulk
+                // copies, these threads wait here): the dZ rows may be overwritten
                 if (it > 0) {
                     tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
                     tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
                 }
+                tc::mbar_wait(&barS, par);
+                const float *z = reinterpret_cast<const float *>(sm + D2B_ZST) + rp * 4;
                 auto putz = [&](int col, float x) {
                     const float h = tc::tf32_hi(x);
                     const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)rp * 16u + (uint32_t)(col & 3) * 4u;
@@ -272,13 +222,72 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) {
                     const int k = kq + 4 * kk;
-                    if (k < KO) {
-                        putz(k, dz[kk][0]);
+                    const bool live = k < KO && valid;
+                    const bool m = live && ((bits >> k) & 1u);
+                    float dz[11];
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) putz(D2_RCOV + 7 * k + q, dz[kk][1 + q]);
+                    for (int q = 0; q < 11; ++q) dz[q] = 0.f;
+                    if (live) {
+                        const float no = z[d2_tile_idx(d2_zcol_op(k))];
+                        float dno = dnp[kk];
+                        if (m) {
+                            dno += up[kk][0];
+                            const float gx = up[kk][1], gy = up[kk][2], gz = up[kk][3];
+                            dofr[3 * kk] = gx * s6[0]; dofr[3 * kk + 1] = gy * s6[1]; dofr[3 * kk + 2] = gz * s6[2];
+                            acc9[0] += gx; acc9[1] += gy; acc9[2] += gz;
+                            acc9[3] += gx * of[kk][0]; acc9[4] += gy * of[kk][1]; acc9[5] += gz * of[kk][2];
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) putz(D2_RCOL + 3 * k + q, dz[kk][8 + q]);
+                            for (int q = 0; q < 3; ++q) {
+                                const float c = z[d2_tile_idx(d2_zcol_col(k, q))];
+                                dz[8 + q] = up[kk][4 + q] * c * (1.f - c);
+                            }
+                            float sr[7];
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) sr[q] = z[d2_tile_idx(d2_zcol_cov(k, q))];
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float sg = 1.f / (1.f + expf(-sr[q]));
+                                const float gsc = up[kk][7 + q];
+                                dz[1 + q] = gsc * s6[3 + q] * sg * (1.f - sg);
+                                acc9[6 + q] += gsc * sg;
+                            }
+                            const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
+                            const float n = fmaxf(nrm, 1e-12f);
+                            const float r0 = sr[3] / n, r1 = sr[4] / n, r2 = sr[5] / n, r3 = sr[6] / n;
+                            const float g0 = up[kk][10], g1 = up[kk][11], g2 = up[kk][12], g3 = up[kk][13];
+                            if (nrm > 1e-12f) {
+                                const float dot = r0 * g0 + r1 * g1 + r2 * g2 + r3 * g3;
+                                dz[4] = (g0 - r0 * dot) / n; dz[5] = (g1 - r1 * dot) / n;
+                                dz[6] = (g2 - r2 * dot) / n; dz[7] = (g3 - r3 * dot) / n;
+                            } else {
+                                dz[4] = g0 / n; dz[5] = g1 / n; dz[6] = g2 / n; dz[7] = g3 / n;
+                            }
+                        }
+                        dz[0] = dno * (1.f - no * no);
                     }
+                    // column sums of dZ (= the output-bias gradients): over the 8 rows of the warp, then one shared-memory add
+#pragma unroll
+                    for (int q = 0; q < 11; ++q) {
+                        float s_ = dz[q];
+                        s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
+                        s_ += __shfl_xor_sync(0xffffffffu, s_, 8);
+                        s_ += __shfl_xor_sync(0xffffffffu, s_, 16);
+                        if (lane < 4 && k < KO && s_ != 0.f)
+                            atomicAdd(&s_gb2[q == 0 ? k : (q < 8 ? D2_RCOV + 7 * k + (q - 1) : D2_RCOL + 3 * k + (q - 8))], s_);
+                    }
+                    if (k < KO) {
+                        putz(k, dz[0]);
+#pragma unroll
+                        for (int q = 0; q < 7; ++q) putz(D2_RCOV + 7 * k + q, dz[1 + q]);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) putz(D2_RCOL + 3 * k + q, dz[8 + q]);
+                    }
+                }
+                // the 4 lanes of a row hold partial sums over their offsets
+#pragma unroll
+                for (int q = 0; q < 9; ++q) {
+                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 1);
+                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 2);
                 }
                 if (kq == 3) {                               // this lane has two offsets only: it zeroes the padding columns
 #pragma unroll
@@ -289,6 +298,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
+            D2_TRACE(1, 16 * it + 2);
             d2_bar_sync_all();                               // 1
             // ---- gate bits of this thread's 24 hidden columns (for epilogue b1), loaded while b1 runs ---------------------
             uint32_t hbits = 0u;
@@ -314,8 +324,10 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             load_h(0);
             tc::mbar_wait(&barB1, par);
             tc::tc_fence_after();
+            D2_TRACE(1, 16 * it + 3);
             for (int q = 0; q < 4; ++q) {
                 if (q > 0) { tc::mbar_wait(&barQ, qph & 1); ++qph; }
+                D2_TRACE(1, 16 * it + 4 + q);
                 for (int e = tid; e < D2_RCH * 32; e += D2_WORKERS) {
                     const int c = e >> 5, rr = 32 * q + (e & 31);
                     const uint32_t o = (uint32_t)c * D2_CHUNK + (uint32_t)rr * 16u;
@@ -346,6 +358,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) dh[n0 + e] = (hbits >> (n0 + e)) & 1u ? v[e] : 0.f;
             }
+            D2_TRACE(1, 16 * it + 8);
             tc::mbar_wait(&barQ, qph & 1); ++qph;            // last w2 quarter done: the dZ rows and the quarter tiles are dead
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -370,6 +383,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
+            D2_TRACE(1, 16 * it + 9);
             d2_bar_sync_all();                               // 6
             const float4 *xt_tile = a.XT + (size_t)tile * a.nch * D2_ROWS;
             float4 upre[3];
@@ -383,6 +397,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             load_u(0);
             tc::mbar_wait(&barB2, par);
             tc::tc_fence_after();
+            D2_TRACE(1, 16 * it + 10);
             // ---- epilogue b2: dU (+ direct gradients on the anchor / offset / scaling columns) -> DUT ------------------------
             {
                 float4 *du = a.DUT + (size_t)tile * a.nch * D2_ROWS + r;
@@ -404,6 +419,7 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             //      the u cells are fetched one quarter ahead ---------------------------------------------------------------------
             for (int q = 0; q < 4; ++q) {
                 const uint32_t qo = (q & 1) * D2B_QG_BYTES;
+                D2_TRACE(1, 16 * it + 11 + q);
                 if (q >= 2) { tc::mbar_wait(&barG[q & 1], gph[q & 1] & 1); ++gph[q & 1]; }
                 for (int e = tid; e < 24 * 32; e += D2_WORKERS) {
                     const int c = e >> 5, rr = 32 * q + (e & 31);
@@ -497,6 +513,7 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     a.XT = f.XT; a.HT = f.HT; a.ZT = f.ZT; a.maskbits = f.maskbits; a.offs = f.offs;
     a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
     a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.part = b.part; a.gb2blk = b.gb2blk;
+    a.trace = g_decode_profile == 2;
     const int ctas = min(dd.ntiles, D2_MAX_CTAS);
     prof_record(2, st);
     dec2_mlp_bwd_kernel<<<ctas, D2_THREADS, D2B_SMEM, st>>>(a);

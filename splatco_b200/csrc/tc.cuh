@@ -126,19 +126,29 @@ __device__ __forceinline__ float tf32_hi(float x) {
 __device__ __forceinline__ uint32_t cell_off(int r, int c, int R) { return (uint32_t)(c * R + r) * 16u; }
 
 // Issue the 3xTF32 product of one operand pair over `ksteps` K=8 steps.
-//   a_hi/a_lo: tiles of RA rows (chunk stride RA*16 B), b_hi/b_lo: tiles of RB rows; chunks a0.., b0.. first chunk ids
-__device__ __forceinline__ void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int RA, int a0,
-                                             uint32_t b_hi, uint32_t b_lo, int RB, int b0, int ksteps,
-                                             uint32_t idesc, bool accumulate_first) {
-    const uint32_t lboA = RA * 16u, lboB = RB * 16u;
+//   a_hi/a_lo: tiles whose chunk stride is lboA bytes, b_hi/b_lo: chunk stride lboB; a0, b0: first chunk ids.
+// ONE thread issues every MMA of the kernel, so the issue loop itself is on the critical path (measured with the phase
+// trace: building four descriptors from scratch per K step made 150 MMAs cost 6 us): the four descriptors are built once
+// and stepped by adding the chunk-pair stride to their 14-bit address field (shared memory < 256 KB: no carry out).
+__device__ __forceinline__ void issue_3xtf32_lbo(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lboA, int a0,
+                                                 uint32_t b_hi, uint32_t b_lo, uint32_t lboB, int b0, int ksteps,
+                                                 uint32_t idesc, bool accumulate_first) {
+    const uint32_t ao = (uint32_t)a0 * lboA, bo = (uint32_t)b0 * lboB;
+    uint64_t dah = make_desc(a_hi + ao, lboA, 128), dal = make_desc(a_lo + ao, lboA, 128);
+    uint64_t dbh = make_desc(b_hi + bo, lboB, 128), dbl = make_desc(b_lo + bo, lboB, 128);
+    const uint64_t sa = (uint64_t)((2u * lboA) >> 4), sbb = (uint64_t)((2u * lboB) >> 4);
+#pragma unroll 4
     for (int s = 0; s < ksteps; ++s) {
-        const uint32_t ao = (uint32_t)(a0 + 2 * s) * lboA, bo = (uint32_t)(b0 + 2 * s) * lboB;
-        const uint64_t dah = make_desc(a_hi + ao, lboA, 128), dal = make_desc(a_lo + ao, lboA, 128);
-        const uint64_t dbh = make_desc(b_hi + bo, lboB, 128), dbl = make_desc(b_lo + bo, lboB, 128);
         mma_tf32(d_tmem, dal, dbh, idesc, accumulate_first || s > 0);     // small terms first
         mma_tf32(d_tmem, dah, dbl, idesc, true);
         mma_tf32(d_tmem, dah, dbh, idesc, true);
+        dah += sa; dal += sa; dbh += sbb; dbl += sbb;
     }
+}
+__device__ __forceinline__ void issue_3xtf32(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int RA, int a0,
+                                             uint32_t b_hi, uint32_t b_lo, int RB, int b0, int ksteps,
+                                             uint32_t idesc, bool accumulate_first) {
+    issue_3xtf32_lbo(d_tmem, a_hi, a_lo, (uint32_t)RA * 16u, a0, b_hi, b_lo, (uint32_t)RB * 16u, b0, ksteps, idesc, accumulate_first);
 }
 
 }  // namespace tc

@@ -87,3 +87,13 @@ def full_path_grad_errors(a, b):
     if nb == 0.0:
         return {"l2": float(np.linalg.norm(a)), "amax": float(np.abs(a).max()) if a.size else 0.0}
     return {"l2": float(np.linalg.norm(a - b)) / nb, "amax": float(np.abs(a - b).max()) / mb}
+
+
+def worst_entry(a, b, floor_frac=1e-3):
+    """(rel err, flat index, got, want, max|want|) of the entry with the largest rel_err: for assertion messages."""
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    floor = max(float(np.abs(b).max()) * floor_frac, 1e-30)
+    e = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    i = int(e.argmax())
+    return float(e[i]), i, float(a[i]), float(b[i]), float(np.abs(b).max())
