@@ -1336,27 +1336,27 @@ F2View f2_view(void *ws, const D2Dims &d) {
     return v;
 }
 
-enum B2Chunk { H_DUT, H_PART, H_RED, H_GB2BLK, H_GW2T, H_GB2, H_GW1T, H_GB1, H_S1, H_S0, H_M1, H_M2, H_NCHUNK };
+enum B2Chunk { H_DUT, H_DGA, H_PART, H_RED, H_GW2T, H_GB2, H_GW1T, H_GB1, H_S1, H_S0, H_M1, H_M2, H_NCHUNK };
 constexpr int D2_MAX_CTAS = 148;
 
 size_t d2_bwd_offsets(const D2Dims &d, size_t off[H_NCHUNK + 1]) {
     size_t o = 0;
     auto put = [&](int c, size_t bytes) { off[c] = o; o += align_up(bytes); };
-    put(H_DUT, (size_t)d.ntiles * d.nch * D2_CHUNK);
-    put(H_PART, (size_t)D2_MAX_CTAS * D2_PART * 4); put(H_RED, (size_t)D2_PART * 4); put(H_GB2BLK, 128 * 4);
+    put(H_DUT, (size_t)d.ntiles * d.nch * D2_CHUNK); put(H_DGA, (size_t)d.ntiles * 10 * D2_CHUNK);
+    put(H_PART, (size_t)D2_MAX_CTAS * D2_PART * 4); put(H_RED, (size_t)D2_PART * 4);
     put(H_GW2T, HD * ZD * 4); put(H_GB2, ZD * 4); put(H_GW1T, XI * HD * 4); put(H_GB1, HD * 4);
     put(H_S1, 32 * (size_t)d.LDX * 4); put(H_S0, 64 * 4); put(H_M1, d.LDX * 4); put(H_M2, d.LDX * 4);
     off[H_NCHUNK] = o;
     return o;
 }
-struct B2View { float4 *DUT; float *part, *red, *gb2blk, *gW2T, *gb2, *gW1T, *gb1, *S1, *S0, *m1, *m2; };
+struct B2View { float4 *DUT, *DGA; float *part, *red, *gW2T, *gb2, *gW1T, *gb1, *S1, *S0, *m1, *m2; };
 B2View b2_view(void *ws, const D2Dims &d) {
     size_t off[H_NCHUNK + 1];
     d2_bwd_offsets(d, off);
     char *b = (char *)ws;
     B2View v;
-    v.DUT = (float4 *)(b + off[H_DUT]); v.part = (float *)(b + off[H_PART]); v.red = (float *)(b + off[H_RED]);
-    v.gb2blk = (float *)(b + off[H_GB2BLK]);
+    v.DUT = (float4 *)(b + off[H_DUT]); v.DGA = (float4 *)(b + off[H_DGA]); v.part = (float *)(b + off[H_PART]);
+    v.red = (float *)(b + off[H_RED]);
     v.gW2T = (float *)(b + off[H_GW2T]); v.gb2 = (float *)(b + off[H_GB2]); v.gW1T = (float *)(b + off[H_GW1T]);
     v.gb1 = (float *)(b + off[H_GB1]); v.S1 = (float *)(b + off[H_S1]); v.S0 = (float *)(b + off[H_S0]);
     v.m1 = (float *)(b + off[H_M1]); v.m2 = (float *)(b + off[H_M2]);

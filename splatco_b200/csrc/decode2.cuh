@@ -55,6 +55,13 @@ inline D2Dims d2_dims(int V, int rc, int level) {
     return d;
 }
 
+// The stage-1 weights travel through the ring as three K slices (all 96 outputs each): chunks [c0, c0 + nc) of slice s
+__host__ __device__ inline void d2_kslice(int nk, int s, int &c0, int &nc) {
+    const int ks = nk / 2, q = ks / 3, r = ks % 3;
+    c0 = 2 * (s * q + (s < r ? s : r));
+    nc = 2 * (q + (s < r ? 1 : 0));
+}
+
 __device__ __forceinline__ int d2_zcol_op(int k) { return k; }
 __device__ __forceinline__ int d2_zcol_cov(int k, int q) { return D2_ZCOV + 7 * k + q; }
 __device__ __forceinline__ int d2_zcol_col(int k, int q) { return D2_ZCOL + 3 * k + q; }
@@ -237,14 +244,14 @@ dec2_gather_kernel(DecPtrs p, int V, int LDX, float4 *__restrict__ XT, double *_
 
 // =======================================================================================================
 // Combined weights (after dec_fold_kernel): Wc1 = the affine map u -> hidden pre-activation, packed hi/lo into
-//   W1S  forward B tiles, three N = 32 slices (one per head): [slice][hi | lo][nk chunks][32 rows]
+//   W1S  forward B tiles, three K slices (d2_kslice) of all 96 outputs: [slice][hi | lo][chunks of the slice][96 rows]
 //   W1R  backward B tile (dU = dH Wc1^T): [hi | lo][24 chunks][NB rows]   (row 71, the bias row, is zero)
 //   W2B  forward block tiles [hi | lo]{[8][16] opacity, [8][80] cov, [8][32] colour};  b2blk[128]
 //   W2R  backward block tiles (dH_h = dZ_h W2_h^T): [hi | lo]{[4][32], [18][32], [8][32]}
 // =======================================================================================================
 constexpr uint32_t D2_W2B_HALF = 8 * (16 + 80 + 32) * 16;           // 16384
 constexpr uint32_t D2_W2R_HALF = (4 + 18 + 8) * 32 * 16;            // 15360
-constexpr uint32_t D2_RING_SLOT = D2_MAX_NK * 32 * 16 * 2;          // 36864
+constexpr uint32_t D2_RING_SLOT = 12 * HD * 16 * 2;                 // 36864: the largest K slice (6 K steps = 12 chunks x 96 rows, hi + lo)
 static_assert(2 * D2_W2B_HALF <= D2_RING_SLOT, "W2 blocks travel through a ring slot");
 
 __device__ __forceinline__ void d2_put(uint8_t *dst, uint32_t half, size_t cell, int sub, float w) {
@@ -260,7 +267,7 @@ dec2_combine_kernel(int DP, int nk, int NB, const float *__restrict__ WpT, const
                     uint8_t *__restrict__ W1R, uint8_t *__restrict__ W2B, float *__restrict__ b2blk,
                     uint8_t *__restrict__ W2R) {
     const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
-    const uint32_t s_half = (uint32_t)nk * 32 * 16, r_half = 24u * NB * 16;
+    const uint32_t r_half = 24u * NB * 16;
     for (int e = tid; e < NB * HD; e += nthr) {
         const int uc = e / HD, n = e - uc * HD;
         float w = 0.f;
@@ -276,8 +283,15 @@ dec2_combine_kernel(int DP, int nk, int NB, const float *__restrict__ WpT, const
             const int c = uc - D2_UP0;
             for (int o = 0; o < 32; ++o) w = fmaf(WpT[c * 32 + o], W1T[(36 + o) * HD + n], w);
         }
-        if (uc < 4 * nk)
-            d2_put(W1S + (size_t)(n >> 5) * 2 * s_half, s_half, (size_t)(uc >> 2) * 32 + (n & 31), uc & 3, w);
+        if (uc < 4 * nk) {
+            int sl = 0, c0, nc;
+            d2_kslice(nk, 1, c0, nc);
+            if ((uc >> 2) >= c0) sl = 1;
+            d2_kslice(nk, 2, c0, nc);
+            if ((uc >> 2) >= c0) sl = 2;
+            d2_kslice(nk, sl, c0, nc);
+            d2_put(W1S + (size_t)c0 * HD * 32, (uint32_t)nc * HD * 16, (size_t)((uc >> 2) - c0) * HD + n, uc & 3, w);
+        }
         d2_put(W1R, r_half, (size_t)(n >> 2) * NB + uc, n & 3, uc == D2_ONE ? 0.f : w);
     }
     // W2 blocks.  compact output index j: [0,10) opacity, [10,80) cov, [80,110) colour
@@ -303,8 +317,10 @@ dec2_combine_kernel(int DP, int nk, int NB, const float *__restrict__ WpT, const
 // =======================================================================================================
 // Forward MLP: persistent, one CTA per SM, 128 anchors per tile.
 //   workers (16 warps): split the TMA-loaded u tile hi/lo in place, epilogues;  control warp: bulk copies + tcgen05.mma.
-//   stage 1: H[128,96] = u Wc1 as three N = 32 slices whose weights stream through a 2-slot ring (the u operand and
-//            the full weight set do not fit shared memory together; a slice is fetched while the previous one multiplies)
+//   stage 1: H[128,96] = u Wc1 in three K slices whose weights stream through a 2-slot ring (the u operand and the full
+//            weight set do not fit shared memory together; a slice is fetched while the previous one multiplies).  K
+//            slices, not N slices: every tcgen05.mma reads its 128 x 8 A block (4 KB) from shared memory whatever its N,
+//            and at N = 32 that read -- not the tensor pipe -- set the pace (phase trace: 51 MMAs = 1.4 us)
 //   stage 2: Z = H W2, three block products (K = 32 each), weights = the ring's fourth item
 //   the next tile's u rows are fetched during epilogue 2, the next tile's first two slices during epilogues 1 and 2.
 // Shared memory: U hi [0, 73728) | U lo [73728, 147456) | ring 2 x 36864;  H hi / lo reuse the U regions.
@@ -351,7 +367,12 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
     tc::tc_fence_after();
     const uint32_t tmem = tmem_s;
     const uint32_t u_hi = tc::smem_u32(sm), u_lo = u_hi + D2F_ULO, ring = u_hi + D2F_RING;
-    const uint32_t tile_bytes = (uint32_t)a.nch * D2_CHUNK, slice_bytes = (uint32_t)a.nk * 32 * 16 * 2;
+    const uint32_t tile_bytes = (uint32_t)a.nch * D2_CHUNK;
+    int sl_c0[3], sl_nc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) d2_kslice(a.nk, q, sl_c0[q], sl_nc[q]);
+    auto slice_src = [&](int q) { return a.W1S + (size_t)sl_c0[q] * HD * 32; };
+    auto slice_bytes = [&](int q) { return (uint32_t)sl_nc[q] * HD * 32; };
     const int ntl = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
 
     if (warp == D2_WORKERS / 32) {
@@ -367,34 +388,39 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
             }
         };
         auto wait_item = [&](int slot) { tc::mbar_wait(&full[slot], pf[slot]); pf[slot] ^= 1; tc::tc_fence_after(); };
-        constexpr uint32_t id32 = tc::make_idesc_tf32(128, 32), id16 = tc::make_idesc_tf32(128, 16), id80 = tc::make_idesc_tf32(128, 80);
-        const uint32_t s_half = (uint32_t)a.nk * 32 * 16;
+        constexpr uint32_t id32 = tc::make_idesc_tf32(128, 32), id16 = tc::make_idesc_tf32(128, 16), id80 = tc::make_idesc_tf32(128, 80),
+                           id96 = tc::make_idesc_tf32(128, HD);
         if (ntl > 0) {
             if (lane == 0) {
                 tc::mbar_arrive_expect_tx(&barU, tile_bytes);
                 tc::bulk_g2s(sm, a.XT + (size_t)blockIdx.x * a.nch * D2_ROWS, tile_bytes, &barU);
             }
-            load_item(0, a.W1S, slice_bytes);
-            load_item(1, a.W1S + slice_bytes, slice_bytes);
+            load_item(0, slice_src(0), slice_bytes(0));
+            load_item(1, slice_src(1), slice_bytes(1));
         }
         for (int it = 0; it < ntl; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             d2_bar_sync_all();                                  // A: operand split done
             tc::tc_fence_after();
+#define D2_CTRACE(slot) do { if (a.trace && blockIdx.x == 0 && lane == 0 && it < 4) g_d2_trace[0][32 + 8 * it + (slot)] = clock64(); } while (0)
+            D2_CTRACE(0);
             for (int s = 0; s < 3; ++s) {
                 const int slot = s & 1;
                 wait_item(slot);
+                D2_CTRACE(1 + 2 * s);
                 if (lane == 0) {
                     const uint32_t b = ring + slot * D2_RING_SLOT;
-                    tc::issue_3xtf32(tmem + 32 * s, u_hi, u_lo, D2_ROWS, 0, b, b + s_half, 32, 0, a.nk / 2, id32, false);
+                    tc::issue_3xtf32_lbo(tmem, u_hi, u_lo, D2_CHUNK, sl_c0[s], b, b + (uint32_t)sl_nc[s] * HD * 16, HD * 16, 0, sl_nc[s] / 2, id96, s > 0);
                     tc::mma_commit(&empty[slot]);
                     if (s == 2) tc::mma_commit(&barM1);
                 }
                 __syncwarp();
+                D2_CTRACE(2 + 2 * s);
                 // refill the slots behind the running products
-                if (s == 1) load_item(0, a.W1S + 2 * (size_t)slice_bytes, slice_bytes);
+                if (s == 1) load_item(0, slice_src(2), slice_bytes(2));
                 if (s == 2) load_item(1, a.W2B, 2 * D2_W2B_HALF);
             }
+            D2_CTRACE(7);
             d2_bar_sync_all();                                  // B: H operand written
             tc::tc_fence_after();
             wait_item(1);
@@ -408,8 +434,8 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
             }
             __syncwarp();
             if (it + 1 < ntl) {
-                load_item(0, a.W1S, slice_bytes);               // slot 0: slice 2 has been consumed
-                load_item(1, a.W1S + slice_bytes, slice_bytes); // waits for stage 2 => the H operand is dead
+                load_item(0, slice_src(0), slice_bytes(0));     // slot 0: slice 2 has been consumed
+                load_item(1, slice_src(1), slice_bytes(1));     // waits for stage 2 => the H operand is dead
                 if (lane == 0) {
                     tc::mbar_arrive_expect_tx(&barU, tile_bytes);
                     tc::bulk_g2s(sm, a.XT + (size_t)(tile + gridDim.x) * a.nch * D2_ROWS, tile_bytes, &barU);
@@ -560,7 +586,8 @@ namespace splatco {
 // weight-gradient products   gW2b[j][i] = sum_v dZ[v][j] H[v][i]   (j in the dZ operand's column order)
 // and   GT[n][uc] = sum_v dH[v][n] u[v][uc].
 // =======================================================================================================
-constexpr int D2_PART = D2_ROWS * HD + D2_ROWS * 144;        // floats per CTA partial: gW2b [128][96] | GT [128][144]
+constexpr int D2_GW2_LD = 112;                                // gW2b row: 96 hidden columns + column 96 = sum_v dZ[v][j] (ones row of H^T)
+constexpr int D2_PART = D2_ROWS * D2_GW2_LD + D2_ROWS * 144;  // floats per CTA partial: gW2b [128][112] | GT [128][144]
 
 // sum of the per-CTA partials (deterministic; the MLP kernel writes its TMEM accumulators once per CTA)
 __global__ void __launch_bounds__(256)
@@ -577,12 +604,12 @@ dec2_reduce_kernel(int nparts, const float *__restrict__ part, float *__restrict
 //   S1raw[o][c] = sum_v dgeo[v][o] x[v][c] = sum_n W1g[o][n] GT[n][u(c)]
 //   gW1T[k][n]: feat / dir rows straight from GT, geo rows = sum_c Wgeo'[c][o] GT[n][u(c)] + bgeo[o] gb1[n]
 __global__ void __launch_bounds__(256)
-dec2_expand_kernel(int DP, int LDX, const float *__restrict__ red, const float *__restrict__ gb2blk,
+dec2_expand_kernel(int DP, int LDX, const float *__restrict__ red,
                    const float *__restrict__ WpT, const float *__restrict__ WcT, const float *__restrict__ bgeo,
                    const float *__restrict__ W1T, float *__restrict__ S1, float *__restrict__ S0,
                    float *__restrict__ gW1T, float *__restrict__ gb1, float *__restrict__ gW2T, float *__restrict__ gb2) {
     const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
-    const float *gW2b = red, *GT = red + D2_ROWS * HD;
+    const float *gW2b = red, *GT = red + D2_ROWS * D2_GW2_LD;
     auto gt = [&](int n, int uc) { return GT[n * 144 + uc]; };
     for (int n = tid; n < HD; n += nthr) gb1[n] = gt(n, D2_ONE);
     for (int o = tid; o < 64; o += nthr) {
@@ -616,11 +643,11 @@ dec2_expand_kernel(int DP, int LDX, const float *__restrict__ red, const float *
     for (int e = tid; e < HD * ZD; e += nthr) {
         const int i = e / ZD, j = e - i * ZD;
         const int jb = j < KO ? j : (j < 8 * KO ? D2_RCOV + (j - KO) : (j < 11 * KO ? D2_RCOL + (j - 8 * KO) : -1));
-        gW2T[e] = jb >= 0 ? gW2b[jb * HD + i] : 0.f;
+        gW2T[e] = jb >= 0 ? gW2b[jb * D2_GW2_LD + i] : 0.f;
     }
     for (int j = tid; j < ZD; j += nthr) {
         const int jb = j < KO ? j : (j < 8 * KO ? D2_RCOV + (j - KO) : (j < 11 * KO ? D2_RCOL + (j - 8 * KO) : -1));
-        gb2[j] = jb >= 0 ? gb2blk[jb] : 0.f;
+        gb2[j] = jb >= 0 ? gW2b[jb * D2_GW2_LD + HD] : 0.f;
     }
 }
 

@@ -3,9 +3,13 @@
 // Persistent, one CTA per SM, 128 anchors per tile, 16 worker warps + 1 control warp (bulk copies, tcgen05.mma).
 // Per tile:
 //   P0   un-compaction: upstream gradients of the compacted Gaussians -> dZ rows (pre-activation), written straight
-//        into the K-major operand tile; the direct anchor / offset / scaling gradients stay in registers
+//        into the K-major operand tile; the direct anchor / offset / scaling gradients go to a small global tile (DGA).
+//        One thread per (anchor row, kind of output: opacity+position | colour | scale | rotation), the ten offsets
+//        unrolled so that every column index is a compile-time constant; the head outputs come from the ZT tile,
+//        staged in shared memory by one bulk copy
 //   b1   dH = (dZ W2^T) .* [H > 0]        three block products (K = 16 | 72 | 32), accumulator in TMEM
-//   w2   gW2[j][i] += sum_v dZ[v][j] H[v][i]       reduction over the tile's anchors
+//   w2   gW2[j][i] += sum_v dZ[v][j] H[v][i]       reduction over the tile's anchors; a row of ones appended to H^T makes
+//        column 96 of the result the column sums of dZ (the output-bias gradients) for free
 //   b2   dU = dH Wc1^T                              (N = NB <= 144)  -> DUT (+ the direct gradients)
 //   g    GT[n][uc]  += sum_v dH[v][n] u[v][uc]
 // The two weight-gradient products reduce over anchors, i.e. over the ROWS of the activation tiles.  kind::tf32 reads
@@ -17,9 +21,8 @@
 // Shared memory (bytes), regions alias across the phases of a tile:
 //   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600) | ZT tile [153600,219136) (P0 only), then the
 //             w2 quarter tiles from 122880
-//   b2/g    : dH rows hi [0,49152) lo [49152,98304) | W1R [98304,208896), then the g quarter tiles from 98304 |
-//             direct gradients [208896, 229888)
-// TMEM: dH acc [0,96) | dU acc [96,240) | gW2 acc [240,336) | GT acc [336,480).
+//   b2/g    : dH rows hi [0,49152) lo [49152,98304) | W1R [98304,208896), then the g quarter tiles from 98304
+// TMEM: dH acc [0,96) | dU acc [96,240) | gW2 acc [240,352) | GT acc [352,496).
 #pragma once
 
 namespace splatco {
@@ -29,19 +32,17 @@ constexpr uint32_t D2B_W2R = 2 * D2B_DZLO;                           // 122880
 constexpr uint32_t D2B_ZST = D2B_W2R + 2 * D2_W2R_HALF;              // 153600: the tile's head outputs, staged for the un-compaction
 constexpr uint32_t D2B_DHLO = 24 * D2_CHUNK;                         // 49152
 constexpr uint32_t D2B_W1R = 2 * D2B_DHLO;                           // 98304
-constexpr uint32_t D2B_DGA = D2B_W1R + 2 * 24 * 144 * 16;            // 208896
-constexpr int D2B_DGA_LD = 41;
-constexpr uint32_t D2B_SMEM = D2B_DGA + D2_ROWS * D2B_DGA_LD * 4;    // 229888
+constexpr uint32_t D2B_SMEM = 222720;                                // the two g quarter buffers end at 98304 + 2 * 61952 (+ overrun of the last 96-row chunk)
 // chunk strides of the transposed quarter tiles ((rows + 1) * 16 B).  The 96-row tiles (H^T, dH^T) are read with M or N = 96
 // .. 128: an M = 128 product reads rows 96..127 of a chunk from the next chunk's first rows -- finite data that only
 // reaches accumulator rows nobody reads.
-constexpr uint32_t D2B_LA = 129 * 16, D2B_LH = 97 * 16, D2B_LU = 145 * 16;
+constexpr uint32_t D2B_LA = 129 * 16, D2B_LH = 97 * 16, D2B_LHW = 113 * 16, D2B_LU = 145 * 16;
 // w2 quarter: dZ^T hi | lo | H^T hi | lo (single buffer)     g quarter: dH^T hi | lo | u^T hi | lo (two buffers)
 constexpr uint32_t D2B_QW_A = D2B_W2R, D2B_QW_B = D2B_QW_A + 2 * 8 * D2B_LA;
 constexpr uint32_t D2B_QG_BYTES = 2 * 8 * D2B_LH + 2 * 8 * D2B_LU;   // 61952
 constexpr uint32_t D2B_QG_A = D2B_W1R, D2B_QG_B = D2B_QG_A + 2 * 8 * D2B_LH;
-static_assert(D2B_QW_B + 2 * 8 * D2B_LH <= D2B_DGA, "w2 quarter tiles overlap the direct gradients");
-static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_DGA + D2_ROWS * 41 * 4, "g quarter tiles exceed the shared memory");
+static_assert(D2B_QW_B + 2 * 8 * D2B_LHW <= D2B_SMEM && D2B_W1R + 2 * 24 * 144 * 16 <= D2B_SMEM, "shared memory map");
+static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_SMEM && D2B_ZST + D2_ZCH * D2_CHUNK <= D2B_SMEM, "shared memory map");
 
 struct D2Bwd {
     int V, nch, nk, NB, ntiles, trace;
@@ -49,8 +50,8 @@ struct D2Bwd {
     const uint32_t *maskbits, *offs;
     const float *d_xyz, *d_color, *d_opacity, *d_scaling, *d_rot, *d_nopac;
     const uint8_t *W2R, *W1R;
-    float4 *DUT;
-    float *part, *gb2blk;
+    float4 *DUT, *DGA;
+    float *part;
 };
 
 __device__ __forceinline__ void d2_issue_lbo(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t lboA, uint32_t b_hi,
@@ -77,7 +78,6 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2], barS;
     __shared__ uint32_t tmem_s;
-    __shared__ float s_gb2[128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
     if (tid == 0) {
@@ -85,7 +85,6 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
         tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1); tc::mbar_init(&barS, 1);
         tc::fence_barrier_init();
     }
-    if (tid < 128) s_gb2[tid] = 0.f;
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -93,12 +92,12 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
     const uint32_t sb = tc::smem_u32(sm);
     const int ntl = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const uint32_t w1r_half = 24u * (uint32_t)a.NB * 16u;
-    constexpr uint32_t T_DH = 0, T_DU = 96, T_GW2 = 240, T_GT = 336;
+    constexpr uint32_t T_DH = 0, T_DU = 96, T_GW2 = 240, T_GT = 352;
     uint32_t qph = 0, gph[2] = {0, 0};                       // phases of barQ / barG[] this thread has waited for
 
     if (warp == D2_WORKERS / 32) {
         // =========================== control warp ===========================
-        constexpr uint32_t id32 = tc::make_idesc_tf32(128, 32), id96 = tc::make_idesc_tf32(128, HD), id144 = tc::make_idesc_tf32(128, 144);
+        constexpr uint32_t id32 = tc::make_idesc_tf32(128, 32), id112 = tc::make_idesc_tf32(128, D2_GW2_LD), id144 = tc::make_idesc_tf32(128, 144);
         const uint32_t idNB = tc::make_idesc_tf32(128, a.NB);
         for (int it = 0; it < ntl; ++it) {
             const uint32_t par = it & 1;
@@ -128,8 +127,8 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                 d2_bar_sync_all();                           // 2..5: w2 quarter operands written
                 tc::tc_fence_after();
                 if (lane == 0) {
-                    d2_issue_lbo(tmem + T_GW2, sb + D2B_QW_A, sb + D2B_QW_A + 8 * D2B_LA, D2B_LA, sb + D2B_QW_B, sb + D2B_QW_B + 8 * D2B_LH,
-                                 D2B_LH, 4, id96, it > 0 || q > 0);
+                    d2_issue_lbo(tmem + T_GW2, sb + D2B_QW_A, sb + D2B_QW_A + 8 * D2B_LA, D2B_LA, sb + D2B_QW_B, sb + D2B_QW_B + 8 * D2B_LHW,
+                                 D2B_LHW, 4, id112, it > 0 || q > 0);
                     tc::mma_commit(&barQ);
                 }
                 __syncwarp();
@@ -164,136 +163,135 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
         // =========================== workers ===========================
         const int r = tid & (D2_ROWS - 1), grp = tid >> 7;
         const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        const int rp = tid >> 2, kq = tid & 3;               // un-compaction: row, offsets kq, kq + 4, kq + 8
         const int ng = a.NB / 8, g_beg = (ng * grp) / 4, g_end = (ng * (grp + 1)) / 4;      // dU column groups of this thread
-        float *s_dga = reinterpret_cast<float *>(sm + D2B_DGA);
         for (int it = 0; it < ntl; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const uint32_t par = it & 1;
             D2_TRACE(1, 16 * it + 0);
             // ---- P0: un-compaction (gaussian_renderer/__init__.py:96-111 backwards) --------------------------------------
-            // phase 1: every global load of this thread (upstream gradients of its <= 3 offsets, its offsets / scaling),
-            // issued together; phase 2: the head outputs come from the staged ZT tile in shared memory
-            float dofr[9], acc9[9];
-#pragma unroll
-            for (int q = 0; q < 9; ++q) { dofr[q] = 0.f; acc9[q] = 0.f; }
             {
-                const int v = tile * D2_ROWS + rp;
+                const int v = tile * D2_ROWS + r;
                 const bool valid = v < a.V;
                 const uint32_t bits = valid ? __ldg(a.maskbits + v) : 0u;
                 const uint32_t off0 = valid ? __ldg(a.offs + v) : 0u;
-                const float *g = reinterpret_cast<const float *>(a.XT + (size_t)tile * a.nch * D2_ROWS + rp);
-                float s6[6], up[3][14], of[3][3], dnp[3];
-#pragma unroll
-                for (int q = 0; q < 6; ++q) s6[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + q));
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const int k = kq + 4 * kk;
-                    const bool live = k < KO && valid;
-                    const bool m = live && ((bits >> k) & 1u);
-                    dnp[kk] = (live && a.d_nopac) ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
-                    const size_t j = m ? off0 + __popc(bits & ((1u << k) - 1u)) : 0;
-                    up[kk][0] = m ? __ldg(a.d_opacity + j) : 0.f;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        up[kk][1 + q] = m ? __ldg(a.d_xyz + 3 * j + q) : 0.f;
-                        up[kk][4 + q] = m ? __ldg(a.d_color + 3 * j + q) : 0.f;
-                        up[kk][7 + q] = m ? __ldg(a.d_scaling + 3 * j + q) : 0.f;
-                        of[kk][q] = m ? __ldg(g + d2_tile_idx(FD + 3 + 3 * k + q)) : 0.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) up[kk][10 + q] = m ? __ldg(a.d_rot + 4 * j + q) : 0.f;
-                }
-                D2_TRACE(1, 16 * it + 1);
-                // the last two g products of the previous tile have completed (the control warp waited before its bulk
-                // copies, these threads wait here): the dZ rows may be overwritten
-                if (it > 0) {
-                    tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
-                    tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
-                }
-                tc::mbar_wait(&barS, par);
-                const float *z = reinterpret_cast<const float *>(sm + D2B_ZST) + rp * 4;
+                const float *g = reinterpret_cast<const float *>(a.XT + (size_t)tile * a.nch * D2_ROWS + r);
+                float *dga = reinterpret_cast<float *>(a.DGA + (size_t)tile * 10 * D2_ROWS + r);
+                const float *z = reinterpret_cast<const float *>(sm + D2B_ZST) + r * 4;
                 auto putz = [&](int col, float x) {
                     const float h = tc::tf32_hi(x);
-                    const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)rp * 16u + (uint32_t)(col & 3) * 4u;
+                    const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)r * 16u + (uint32_t)(col & 3) * 4u;
                     *reinterpret_cast<float *>(sm + o) = h;
                     *reinterpret_cast<float *>(sm + D2B_DZLO + o) = x - h;
                 };
+                auto row_of = [&](int k) -> size_t { return off0 + __popc(bits & ((1u << k) - 1u)); };
+                auto waits = [&]() {
+                    D2_TRACE(1, 16 * it + 1);
+                    // the last two g products of the previous tile have completed (the control warp waited before its
+                    // bulk copies, these threads wait here): the dZ rows may be overwritten; then the staged ZT tile
+                    if (it > 0) {
+                        tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
+                        tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
+                    }
+                    tc::mbar_wait(&barS, par);
+                };
+                if (grp == 0) {
+                    // opacity column and the position path: xyz = anchor + offset * scaling[:3]
+                    float s3[3], dnp[KO], up[KO][4], of[KO][3];
 #pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const int k = kq + 4 * kk;
-                    const bool live = k < KO && valid;
-                    const bool m = live && ((bits >> k) & 1u);
-                    float dz[11];
+                    for (int q = 0; q < 3; ++q) s3[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + q));
 #pragma unroll
-                    for (int q = 0; q < 11; ++q) dz[q] = 0.f;
-                    if (live) {
-                        const float no = z[d2_tile_idx(d2_zcol_op(k))];
-                        float dno = dnp[kk];
-                        if (m) {
-                            dno += up[kk][0];
-                            const float gx = up[kk][1], gy = up[kk][2], gz = up[kk][3];
-                            dofr[3 * kk] = gx * s6[0]; dofr[3 * kk + 1] = gy * s6[1]; dofr[3 * kk + 2] = gz * s6[2];
-                            acc9[0] += gx; acc9[1] += gy; acc9[2] += gz;
-                            acc9[3] += gx * of[kk][0]; acc9[4] += gy * of[kk][1]; acc9[5] += gz * of[kk][2];
+                    for (int k = 0; k < KO; ++k) {
+                        const bool m = (bits >> k) & 1u;
+                        const size_t j = m ? row_of(k) : 0;
+                        dnp[k] = (valid && a.d_nopac) ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
+                        up[k][0] = m ? __ldg(a.d_opacity + j) : 0.f;
 #pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const float c = z[d2_tile_idx(d2_zcol_col(k, q))];
-                                dz[8 + q] = up[kk][4 + q] * c * (1.f - c);
-                            }
-                            float sr[7];
-#pragma unroll
-                            for (int q = 0; q < 7; ++q) sr[q] = z[d2_tile_idx(d2_zcol_cov(k, q))];
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const float sg = 1.f / (1.f + expf(-sr[q]));
-                                const float gsc = up[kk][7 + q];
-                                dz[1 + q] = gsc * s6[3 + q] * sg * (1.f - sg);
-                                acc9[6 + q] += gsc * sg;
-                            }
-                            const float nrm = sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]);
-                            const float n = fmaxf(nrm, 1e-12f);
-                            const float r0 = sr[3] / n, r1 = sr[4] / n, r2 = sr[5] / n, r3 = sr[6] / n;
-                            const float g0 = up[kk][10], g1 = up[kk][11], g2 = up[kk][12], g3 = up[kk][13];
-                            if (nrm > 1e-12f) {
-                                const float dot = r0 * g0 + r1 * g1 + r2 * g2 + r3 * g3;
-                                dz[4] = (g0 - r0 * dot) / n; dz[5] = (g1 - r1 * dot) / n;
-                                dz[6] = (g2 - r2 * dot) / n; dz[7] = (g3 - r3 * dot) / n;
-                            } else {
-                                dz[4] = g0 / n; dz[5] = g1 / n; dz[6] = g2 / n; dz[7] = g3 / n;
-                            }
+                        for (int q = 0; q < 3; ++q) {
+                            up[k][1 + q] = m ? __ldg(a.d_xyz + 3 * j + q) : 0.f;
+                            of[k][q] = m ? __ldg(g + d2_tile_idx(FD + 3 + 3 * k + q)) : 0.f;
                         }
-                        dz[0] = dno * (1.f - no * no);
                     }
-                    // column sums of dZ (= the output-bias gradients): over the 8 rows of the warp, then one shared-memory add
+                    waits();
+                    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                    for (int q = 0; q < 11; ++q) {
-                        float s_ = dz[q];
-                        s_ += __shfl_xor_sync(0xffffffffu, s_, 4);
-                        s_ += __shfl_xor_sync(0xffffffffu, s_, 8);
-                        s_ += __shfl_xor_sync(0xffffffffu, s_, 16);
-                        if (lane < 4 && k < KO && s_ != 0.f)
-                            atomicAdd(&s_gb2[q == 0 ? k : (q < 8 ? D2_RCOV + 7 * k + (q - 1) : D2_RCOL + 3 * k + (q - 8))], s_);
+                    for (int k = 0; k < KO; ++k) {
+                        const float no = z[d2_tile_idx(d2_zcol_op(k))];
+                        putz(k, valid ? (dnp[k] + up[k][0]) * (1.f - no * no) : 0.f);
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            dga[d2_tile_idx(3 + 3 * k + q)] = up[k][1 + q] * s3[q];
+                            acc[q] += up[k][1 + q];
+                            acc[3 + q] = fmaf(up[k][1 + q], of[k][q], acc[3 + q]);
+                        }
                     }
-                    if (k < KO) {
-                        putz(k, dz[0]);
 #pragma unroll
-                        for (int q = 0; q < 7; ++q) putz(D2_RCOV + 7 * k + q, dz[1 + q]);
+                    for (int q = 0; q < 3; ++q) { dga[d2_tile_idx(q)] = acc[q]; dga[d2_tile_idx(33 + q)] = acc[3 + q]; }
 #pragma unroll
-                        for (int q = 0; q < 3; ++q) putz(D2_RCOL + 3 * k + q, dz[8 + q]);
+                    for (int c = KO; c < D2_RCOV; ++c) putz(c, 0.f);          // padding columns of the opacity block
+                } else if (grp == 1) {
+                    float up[KO][3];
+#pragma unroll
+                    for (int k = 0; k < KO; ++k) {
+                        const bool m = (bits >> k) & 1u;
+                        const size_t j = m ? row_of(k) : 0;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) up[k][q] = m ? __ldg(a.d_color + 3 * j + q) : 0.f;
                     }
-                }
-                // the 4 lanes of a row hold partial sums over their offsets
+                    waits();
 #pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 1);
-                    acc9[q] += __shfl_xor_sync(0xffffffffu, acc9[q], 2);
-                }
-                if (kq == 3) {                               // this lane has two offsets only: it zeroes the padding columns
+                    for (int k = 0; k < KO; ++k)
 #pragma unroll
-                    for (int c = KO; c < D2_RCOV; ++c) putz(c, 0.f);
-                    putz(D2_RCOV + 7 * KO, 0.f); putz(D2_RCOV + 7 * KO + 1, 0.f);
+                        for (int q = 0; q < 3; ++q) {
+                            const float c = z[d2_tile_idx(d2_zcol_col(k, q))];
+                            putz(D2_RCOL + 3 * k + q, up[k][q] * c * (1.f - c));
+                        }
                     putz(D2_RCOL + 3 * KO, 0.f); putz(D2_RCOL + 3 * KO + 1, 0.f);
+                } else if (grp == 2) {
+                    float s3[3], up[KO][3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) s3[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + 3 + q));
+#pragma unroll
+                    for (int k = 0; k < KO; ++k) {
+                        const bool m = (bits >> k) & 1u;
+                        const size_t j = m ? row_of(k) : 0;
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) up[k][q] = m ? __ldg(a.d_scaling + 3 * j + q) : 0.f;
+                    }
+                    waits();
+                    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < KO; ++k)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const float sg = 1.f / (1.f + expf(-z[d2_tile_idx(d2_zcol_cov(k, q))]));
+                            putz(D2_RCOV + 7 * k + q, up[k][q] * s3[q] * sg * (1.f - sg));
+                            acc[q] = fmaf(up[k][q], sg, acc[q]);
+                        }
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) dga[d2_tile_idx(36 + q)] = acc[q];
+                    dga[d2_tile_idx(39)] = 0.f;
+                    putz(D2_RCOV + 7 * KO, 0.f); putz(D2_RCOV + 7 * KO + 1, 0.f);
+                } else {
+                    float4 up[KO];
+#pragma unroll
+                    for (int k = 0; k < KO; ++k) {
+                        const bool m = (bits >> k) & 1u;
+                        up[k] = m ? __ldg(reinterpret_cast<const float4 *>(a.d_rot) + row_of(k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    waits();
+#pragma unroll
+                    for (int k = 0; k < KO; ++k) {
+                        const float s0 = z[d2_tile_idx(d2_zcol_cov(k, 3))], s1 = z[d2_tile_idx(d2_zcol_cov(k, 4))],
+                                    s2 = z[d2_tile_idx(d2_zcol_cov(k, 5))], s3 = z[d2_tile_idx(d2_zcol_cov(k, 6))];
+                        const float nrm = sqrtf(s0 * s0 + s1 * s1 + s2 * s2 + s3 * s3);
+                        const float n = fmaxf(nrm, 1e-12f);
+                        const float r0 = s0 / n, r1 = s1 / n, r2 = s2 / n, r3 = s3 / n;
+                        const float dot = nrm > 1e-12f ? r0 * up[k].x + r1 * up[k].y + r2 * up[k].z + r3 * up[k].w : 0.f;
+                        putz(D2_RCOV + 7 * k + 3, (up[k].x - r0 * dot) / n);
+                        putz(D2_RCOV + 7 * k + 4, (up[k].y - r1 * dot) / n);
+                        putz(D2_RCOV + 7 * k + 5, (up[k].z - r2 * dot) / n);
+                        putz(D2_RCOV + 7 * k + 6, (up[k].w - r3 * dot) / n);
+                    }
                 }
             }
             tc::fence_proxy_async();
@@ -340,8 +338,13 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                     if (e < 24 * 32) {
                         float4 h, l;
                         d2_split4(hpre[i], h, l);
-                        d2_put_t(sm, D2B_QW_B, D2B_QW_B + 8 * D2B_LH, D2B_LH, 4 * (e >> 5), 32 * q + (e & 31), h, l);
+                        d2_put_t(sm, D2B_QW_B, D2B_QW_B + 8 * D2B_LHW, D2B_LHW, 4 * (e >> 5), 32 * q + (e & 31), h, l);
                     }
+                }
+                if (tid < 16) {                              // row 96 of H^T: ones (hi) / zeros (lo) -> column 96 of gW2 = column sums of dZ
+                    const float o1 = tid < 8 ? 1.f : 0.f;
+                    *reinterpret_cast<float4 *>(sm + D2B_QW_B + (tid < 8 ? 0u : 8 * D2B_LHW) + (uint32_t)(tid & 7) * D2B_LHW + HD * 16) =
+                        make_float4(o1, o1, o1, o1);
                 }
                 if (q < 3) load_h(q + 1);
                 tc::fence_proxy_async();
@@ -368,19 +371,6 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                 *reinterpret_cast<float4 *>(sm + o) = h;
                 *reinterpret_cast<float4 *>(sm + D2B_DHLO + o) = l;
             }
-            {                                                // direct gradients: [anchor 3 | offsets 30 | scaling 6]
-                float *dg = s_dga + rp * D2B_DGA_LD;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk) {
-                    const int k = kq + 4 * kk;
-                    if (k < KO) { dg[3 + 3 * k] = dofr[3 * kk]; dg[4 + 3 * k] = dofr[3 * kk + 1]; dg[5 + 3 * k] = dofr[3 * kk + 2]; }
-                }
-                if (kq == 0) {
-                    dg[0] = acc9[0]; dg[1] = acc9[1]; dg[2] = acc9[2];
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) dg[33 + q] = acc9[3 + q];
-                }
-            }
             tc::fence_proxy_async();
             tc::tc_fence_before();
             D2_TRACE(1, 16 * it + 9);
@@ -401,15 +391,19 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             // ---- epilogue b2: dU (+ direct gradients on the anchor / offset / scaling columns) -> DUT ------------------------
             {
                 float4 *du = a.DUT + (size_t)tile * a.nch * D2_ROWS + r;
-                const float *dg = s_dga + r * D2B_DGA_LD;
+                const float4 *dg = a.DGA + (size_t)tile * 10 * D2_ROWS + r;      // written by this CTA in P0 (bar.sync in between)
                 for (int gi = g_beg; gi < g_end; ++gi) {
                     float v[8];
                     tc::tmem_ld8(tlane + T_DU + 8 * gi, v);
                     tc::tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int c = 8 * gi + e;
-                        if (c >= FD && c < GD) v[e] += dg[c - FD];
+                    // u columns 32..71 = [anchor | offsets | scaling | 1]: chunks 8..17 <-> DGA cells 0..9 (cell 9's last entry is 0)
+                    if (2 * gi >= 8 && 2 * gi < 18) {
+                        const float4 d = __ldcg(dg + (2 * gi - 8) * D2_ROWS);
+                        v[0] += d.x; v[1] += d.y; v[2] += d.z; v[3] += d.w;
+                    }
+                    if (2 * gi + 1 >= 8 && 2 * gi + 1 < 18) {
+                        const float4 d = __ldcg(dg + (2 * gi + 1 - 8) * D2_ROWS);
+                        v[4] += d.x; v[5] += d.y; v[6] += d.z; v[7] += d.w;
                     }
                     if (2 * gi < a.nch) du[(2 * gi) * D2_ROWS] = make_float4(v[0], v[1], v[2], v[3]);
                     if (2 * gi + 1 < a.nch) du[(2 * gi + 1) * D2_ROWS] = make_float4(v[4], v[5], v[6], v[7]);
@@ -447,16 +441,15 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
             tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
             tc::tc_fence_after();
-            float *pw = a.part + (size_t)blockIdx.x * D2_PART + (size_t)r * HD + 24 * grp;
-#pragma unroll
-            for (int n0 = 0; n0 < 24; n0 += 8) {
+            float *pw = a.part + (size_t)blockIdx.x * D2_PART + (size_t)r * D2_GW2_LD;
+            for (int gi = (14 * grp) / 4; gi < (14 * (grp + 1)) / 4; ++gi) {
                 float v[8];
-                tc::tmem_ld8(tlane + T_GW2 + 24 * grp + n0, v);
+                tc::tmem_ld8(tlane + T_GW2 + 8 * gi, v);
                 tc::tmem_ld_wait();
-                *reinterpret_cast<float4 *>(pw + n0) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4 *>(pw + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                *reinterpret_cast<float4 *>(pw + 8 * gi) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(pw + 8 * gi + 4) = make_float4(v[4], v[5], v[6], v[7]);
             }
-            float *pg = a.part + (size_t)blockIdx.x * D2_PART + D2_ROWS * HD + (size_t)r * 144;
+            float *pg = a.part + (size_t)blockIdx.x * D2_PART + D2_ROWS * D2_GW2_LD + (size_t)r * 144;
             for (int gi = (18 * grp) / 4; gi < (18 * (grp + 1)) / 4; ++gi) {
                 float v[8];
                 tc::tmem_ld8(tlane + T_GT + 8 * gi, v);
@@ -468,7 +461,6 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (tid < 128 && s_gb2[tid] != 0.f) atomicAdd(&a.gb2blk[tid], s_gb2[tid]);
     if (warp == 0) tc::tmem_dealloc<512>(tmem);
 }
 
@@ -501,7 +493,6 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     gw.app_vec = g->app_vec;
     gi.anchor_feat = g->anchor_feat; gi.anchor = g->anchor; gi.offset = g->offset; gi.scaling = g->scaling;
 
-    SPLATCO_CHECK_CUDA(cudaMemsetAsync(b.gb2blk, 0, 128 * sizeof(float), st));
     static unsigned char attr_dev[64];
     const int attr_i = current_device() & 63;
     if (!attr_dev[attr_i]) {
@@ -512,7 +503,7 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = dd.ntiles;
     a.XT = f.XT; a.HT = f.HT; a.ZT = f.ZT; a.maskbits = f.maskbits; a.offs = f.offs;
     a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
-    a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.part = b.part; a.gb2blk = b.gb2blk;
+    a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.DGA = b.DGA; a.part = b.part;
     a.trace = g_decode_profile == 2;
     const int ctas = min(dd.ntiles, D2_MAX_CTAS);
     prof_record(2, st);
@@ -521,7 +512,7 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     prof_record(3, st);
     dec2_reduce_kernel<<<ceil_div(D2_PART, 256), 256, 0, st>>>(ctas, b.part, b.red);
     SPLATCO_CHECK_LAUNCH();
-    dec2_expand_kernel<<<48, 256, 0, st>>>(dd.DP, dd.LDX, b.red, b.gb2blk, f.WpT, f.WcT, f.bgeo, f.W1T, b.S1, b.S0, b.gW1T, b.gb1,
+    dec2_expand_kernel<<<48, 256, 0, st>>>(dd.DP, dd.LDX, b.red, f.WpT, f.WcT, f.bgeo, f.W1T, b.S1, b.S0, b.gW1T, b.gb1,
                                            b.gW2T, b.gb2);
     SPLATCO_CHECK_LAUNCH();
     dec_bwd_fold_kernel<<<dim3(BWD_FOLD_CTAS, BWD_FOLD_SECTIONS), 256, 0, st>>>(w, gw, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,

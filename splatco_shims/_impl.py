@@ -50,6 +50,9 @@ def scatter_max(src: torch.Tensor, index: torch.Tensor, dim: int = 0, out=None, 
 
 def never_executed(modname: str):
     def _getattr(name):
+        if name.startswith("__"):          # module introspection (inspect.getmodule reads __file__ of every sys.modules entry)
+            raise AttributeError(name)
+
         def _raise(*a, **k):
             raise NotImplementedError(
                 f"{modname}.{name}: the reference imports this extension but never runs it (Spatial_CTX is constructed and "

@@ -186,21 +186,33 @@ def test_decode_matches_oracle_large(level, rc, N):
         loss_r.backward()
         # both sides reduce the BatchNorm-backward sums over ~5.6k rows in fp32 in different orders, which
         # shows up at the 1e-3*max|g| floor: 3e-3 here (the reference-generated fixtures above hold 1e-3)
-        # (N > 8000: the CPU oracle's own fp32 reductions over 20-40 k rows carry ~1e-5 max|g| of rounding, which the
-        #  1e-3 max|g| floor turns into ~1e-2; both GPU implementations agree with each other to 1e-6 there)
-        ff = 1e-3 if N <= 8000 else 3e-2
+        def close(got, want, what):
+            if N <= 8000:
+                assert rel_err(got, want) < 3e-3, (what, worst_entry(got, want))
+                return
+            # The large cases (20-40 k visible anchors, 350 k Gaussians with RANDOM head weights) contain Gaussians whose
+            # four rotation outputs are all ~1e-3: rot = sr / |sr| and its backward (g - r (r.g)) / |sr| amplify the ~1e-6
+            # difference between the 3xTF32 and the torch-CPU evaluation of sr by 1 / |sr|, which shows up as a ~1 % error
+            # on a few entries (identical for both GPU implementations).  They are held in norm and by a bound on the
+            # worst entry relative to the tensor's largest; everything else still has to agree element-wise.
+            from tests.util import full_path_grad_errors
+            e = full_path_grad_errors(got, want)
+            assert e["l2"] < 1e-3 and e["amax"] < 5e-3, (what, e, worst_entry(got, want))
+            a_, b_ = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
+            bad = np.abs(a_ - b_) > 3e-3 * np.maximum(np.abs(b_), 1e-2 * np.abs(b_).max())
+            assert bad.mean() < 1e-4, (what, int(bad.sum()), bad.size)
+
         for k in ("_anchor", "_offset", "_anchor_feat", "_scaling"):
-            assert rel_err(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), floor_frac=ff) < 3e-3, \
-                (k, worst_entry(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), ff))
+            close(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), k)
         for k, v in pc.feat_planes._feat.named_parameters():
             gr = pw["feat." + k].grad
             if gr is None:
                 assert v.grad is None or float(v.grad.abs().max()) == 0.0, k
                 continue
-            assert rel_err(v.grad.cpu().numpy(), gr.numpy(), floor_frac=ff) < 3e-3, k
+            close(v.grad.cpu().numpy(), gr.numpy(), k)
         for name in ("mlp_opacity", "mlp_cov", "mlp_color"):
             for k, v in getattr(pc, name).named_parameters():
-                assert rel_err(v.grad.cpu().numpy(), pw[f"{name}.{k}"].grad.numpy(), floor_frac=ff) < 3e-3, (name, k)
+                close(v.grad.cpu().numpy(), pw[f"{name}.{k}"].grad.numpy(), (name, k))
 
 
 def test_plane_feature_noise_generated_in_kernel():

@@ -29,7 +29,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 traffic = {}
 if os.path.exists(os.path.join(src, f"launches_{tag}.csv")):
     shutil.copy(os.path.join(src, f"launches_{tag}.csv"), os.path.join(dst, f"{tag}_launches.csv"))
-for name in ("blend_bwd", "blend_fwd", "rest", "optim"):
+for name in ("blend_bwd", "blend_fwd", "decode", "rest", "optim"):
     rep = os.path.join(src, f"prof_{name}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -47,12 +47,15 @@ for name in ("blend_bwd", "blend_fwd", "rest", "optim"):
 
     for r in rows[2:]:
         k = r[h.index("Kernel Name")].split("(")[0]
-        e = traffic.setdefault(k, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0, "issue_active_pct": 0.0, "tensor_active_pct": 0.0})
+        e = traffic.setdefault(k, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0, "issue_active_pct": 0.0, "tensor_active_pct": 0.0,
+                                   "warp_instructions": 0.0, "threads_per_instruction": 0.0})
         e["launches"] += 1
         e["time_us"] += get(r, "gpu__time_duration.sum") or 0.0
         e["dram_bytes"] += (get(r, "dram__bytes_read.sum") or 0.0) + (get(r, "dram__bytes_write.sum") or 0.0)
         e["issue_active_pct"] += get(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0
         e["tensor_active_pct"] += get(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") or 0.0
+        e["warp_instructions"] += get(r, "smsp__inst_executed.sum") or 0.0
+        e["threads_per_instruction"] += get(r, "smsp__thread_inst_executed_per_inst_executed.ratio") or 0.0
 for k, e in traffic.items():
     n = e.pop("launches")
     traffic[k] = {"captured_launches": n, **{kk: round(v / n, 3) for kk, v in e.items()}}

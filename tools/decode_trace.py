@@ -38,6 +38,12 @@ def main(name="c2"):
         if s[6] == 0:
             break
         print(f"fwd tile {it}: " + ", ".join(f"{n} {(b - a) / 1.965e3:.2f}us" for n, a, b in zip(FWD, s[:-1], s[1:])) + f" | total {(s[6] - s[0]) / 1.965e3:.2f}us")
+    CT = ["slice0 landed", "slice0 issued", "slice1 landed", "slice1 issued", "slice2 landed (after slice0 done + its copy)", "slice2 issued", "W2 copy queued"]
+    for it in range(4):
+        c = t[32 + 8 * it: 32 + 8 * it + 8]
+        if c[7] == 0:
+            break
+        print(f"fwd control tile {it}: " + ", ".join(f"{n} +{(b - a) / 1.965e3:.2f}us" for n, a, b in zip(CT, c[:-1], c[1:])))
     BWD = ["P0 compute", "wait prev g", "write dZ", "sync1 + b1", "w2 q0", "w2 q1", "w2 q2", "w2 q3 (+dH regs)", "wait last w2", "write dH", "sync6 + b2",
            "epilogue b2", "g q0", "g q1", "g q2"]
     for it in range(4):
