@@ -5,8 +5,10 @@
 //   P0   un-compaction: upstream gradients of the compacted Gaussians -> dZ rows (pre-activation), written straight
 //        into the K-major operand tile; the direct anchor / offset / scaling gradients go to a small global tile (DGA).
 //        One thread per (anchor row, kind of output: opacity+position | colour | scale | rotation), the ten offsets
-//        unrolled so that every column index is a compile-time constant; the head outputs come from the ZT tile,
-//        staged in shared memory by one bulk copy
+//        unrolled so that every column index is a compile-time constant.  The tile's Gaussians are one contiguous
+//        range of the compacted outputs: their upstream gradients are staged into shared memory with coalesced
+//        4-byte cp.async copies (read straight from global, every (anchor, offset) touched its own sectors and the
+//        sector traffic, not the arithmetic, set the pace: 15 us per tile in the phase trace)
 //   b1   dH = (dZ W2^T) .* [H > 0]        three block products (K = 16 | 72 | 32), accumulator in TMEM
 //   w2   gW2[j][i] += sum_v dZ[v][j] H[v][i]       reduction over the tile's anchors; a row of ones appended to H^T makes
 //        column 96 of the result the column sums of dZ (the output-bias gradients) for free
@@ -19,20 +21,23 @@
 // Both products accumulate in TMEM over all tiles of the CTA and leave it once, as a per-CTA partial (dec2_reduce_kernel).
 //
 // Shared memory (bytes), regions alias across the phases of a tile:
-//   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600) | ZT tile [153600,219136) (P0 only), then the
-//             w2 quarter tiles from 122880
+//   P0/b1/w2: dZ rows hi [0,61440) lo [61440,122880) | W2R [122880,153600) | upstream gradient rows of the tile
+//             [153600,225280) (P0 only), then the w2 quarter tiles from 122880
 //   b2/g    : dH rows hi [0,49152) lo [49152,98304) | W1R [98304,208896), then the g quarter tiles from 98304
 // TMEM: dH acc [0,96) | dU acc [96,240) | gW2 acc [240,352) | GT acc [352,496).
 #pragma once
+#include <type_traits>
 
 namespace splatco {
 
 constexpr uint32_t D2B_DZLO = D2_RCH * D2_CHUNK;                     // 61440
 constexpr uint32_t D2B_W2R = 2 * D2B_DZLO;                           // 122880
-constexpr uint32_t D2B_ZST = D2B_W2R + 2 * D2_W2R_HALF;              // 153600: the tile's head outputs, staged for the un-compaction
+constexpr uint32_t D2B_UST = D2B_W2R + 2 * D2_W2R_HALF;              // 153600: the tile's upstream gradient rows, staged for the un-compaction
+constexpr int D2B_UMAX = D2_ROWS * KO;                               // Gaussians of a tile: [opacity n | xyz 3n | colour 3n | scale 3n | rot 4n]
+constexpr int D2B_U_XYZ = D2B_UMAX, D2B_U_COL = 4 * D2B_UMAX, D2B_U_SCL = 7 * D2B_UMAX, D2B_U_ROT = 10 * D2B_UMAX;
 constexpr uint32_t D2B_DHLO = 24 * D2_CHUNK;                         // 49152
 constexpr uint32_t D2B_W1R = 2 * D2B_DHLO;                           // 98304
-constexpr uint32_t D2B_SMEM = 222720;                                // the two g quarter buffers end at 98304 + 2 * 61952 (+ overrun of the last 96-row chunk)
+constexpr uint32_t D2B_SMEM = 225280;                                // upstream staging ends here; the two g quarter buffers at 222720
 // chunk strides of the transposed quarter tiles ((rows + 1) * 16 B).  The 96-row tiles (H^T, dH^T) are read with M or N = 96
 // .. 128: an M = 128 product reads rows 96..127 of a chunk from the next chunk's first rows -- finite data that only
 // reaches accumulator rows nobody reads.
@@ -42,10 +47,10 @@ constexpr uint32_t D2B_QW_A = D2B_W2R, D2B_QW_B = D2B_QW_A + 2 * 8 * D2B_LA;
 constexpr uint32_t D2B_QG_BYTES = 2 * 8 * D2B_LH + 2 * 8 * D2B_LU;   // 61952
 constexpr uint32_t D2B_QG_A = D2B_W1R, D2B_QG_B = D2B_QG_A + 2 * 8 * D2B_LH;
 static_assert(D2B_QW_B + 2 * 8 * D2B_LHW <= D2B_SMEM && D2B_W1R + 2 * 24 * 144 * 16 <= D2B_SMEM, "shared memory map");
-static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_SMEM && D2B_ZST + D2_ZCH * D2_CHUNK <= D2B_SMEM, "shared memory map");
+static_assert(D2B_QG_A + 2 * D2B_QG_BYTES + 32 * 16 <= D2B_SMEM && D2B_UST + 14 * D2B_UMAX * 4 <= D2B_SMEM, "shared memory map");
 
 struct D2Bwd {
-    int V, nch, nk, NB, ntiles, trace;
+    int V, M, nch, nk, NB, ntiles, trace;
     const float4 *XT, *HT, *ZT;
     const uint32_t *maskbits, *offs;
     const float *d_xyz, *d_color, *d_opacity, *d_scaling, *d_rot, *d_nopac;
@@ -76,13 +81,14 @@ __device__ __forceinline__ void d2_split4(const float4 &x, float4 &h, float4 &l)
 __global__ void __launch_bounds__(D2_THREADS, 1)
 dec2_mlp_bwd_kernel(D2Bwd a) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2], barS;
+    __shared__ uint64_t barWa, barWb, barB1, barB2, barQ, barG[2];
+    __shared__ float s_ex[D2_ROWS][3];                       // un-compaction: scale-sum partials handed from column group 2 to 3
     __shared__ uint32_t tmem_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc<512>(&tmem_s);
     if (tid == 0) {
         tc::mbar_init(&barWa, 1); tc::mbar_init(&barWb, 1); tc::mbar_init(&barB1, 1); tc::mbar_init(&barB2, 1); tc::mbar_init(&barQ, 1);
-        tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1); tc::mbar_init(&barS, 1);
+        tc::mbar_init(&barG[0], 1); tc::mbar_init(&barG[1], 1);
         tc::fence_barrier_init();
     }
     tc::tc_fence_before();
@@ -106,8 +112,6 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
                 tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
             }
             if (lane == 0) {
-                tc::mbar_arrive_expect_tx(&barS, D2_ZCH * D2_CHUNK);
-                tc::bulk_g2s(sm + D2B_ZST, a.ZT + (size_t)(blockIdx.x + it * gridDim.x) * D2_ZCH * D2_ROWS, D2_ZCH * D2_CHUNK, &barS);
                 tc::mbar_arrive_expect_tx(&barWa, 2 * D2_W2R_HALF);
                 tc::bulk_g2s(sm + D2B_W2R, a.W2R, 2 * D2_W2R_HALF, &barWa);
             }
@@ -169,135 +173,166 @@ dec2_mlp_bwd_kernel(D2Bwd a) {
             const uint32_t par = it & 1;
             D2_TRACE(1, 16 * it + 0);
             // ---- P0: un-compaction (gaussian_renderer/__init__.py:96-111 backwards) --------------------------------------
+            float scl_part[3] = {0.f, 0.f, 0.f};             // column group 3: its half of the scale sums, finished after sync 1
             {
-                const int v = tile * D2_ROWS + r;
+                const int row0 = tile * D2_ROWS, v = row0 + r;
                 const bool valid = v < a.V;
                 const uint32_t bits = valid ? __ldg(a.maskbits + v) : 0u;
                 const uint32_t off0 = valid ? __ldg(a.offs + v) : 0u;
-                const float *g = reinterpret_cast<const float *>(a.XT + (size_t)tile * a.nch * D2_ROWS + r);
-                float *dga = reinterpret_cast<float *>(a.DGA + (size_t)tile * 10 * D2_ROWS + r);
-                const float *z = reinterpret_cast<const float *>(sm + D2B_ZST) + r * 4;
+                // the tile's Gaussians: rows [j0, j1) of the compacted outputs
+                const uint32_t j0 = __ldg(a.offs + row0);
+                const uint32_t j1 = row0 + D2_ROWS < a.V ? __ldg(a.offs + row0 + D2_ROWS) : (uint32_t)a.M;
+                const int n = (int)(j1 - j0);
+                const float4 *ztile = a.ZT + (size_t)tile * D2_ZCH * D2_ROWS + r;
+                const float4 *gtile = a.XT + (size_t)tile * a.nch * D2_ROWS + r;
+                float *ust = reinterpret_cast<float *>(sm + D2B_UST);
+                D2_TRACE(1, 16 * it + 1);
+                // the last two g products of the previous tile have completed (the control warp waited before its bulk
+                // copy, these threads wait here): the staging area and the dZ rows may be overwritten
+                if (it > 0) {
+                    tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
+                    tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
+                }
+                auto stage = [&](int dst, const float *src, int count) {
+                    for (int e = tid; e < count; e += D2_WORKERS)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sb + D2B_UST + 4u * (uint32_t)(dst + e)), "l"(src + e) : "memory");
+                };
+                if (n > 0) {
+                    stage(0, a.d_opacity + j0, n);
+                    stage(D2B_U_XYZ, a.d_xyz + 3 * (size_t)j0, 3 * n);
+                    stage(D2B_U_COL, a.d_color + 3 * (size_t)j0, 3 * n);
+                    stage(D2B_U_SCL, a.d_scaling + 3 * (size_t)j0, 3 * n);
+                    stage(D2B_U_ROT, a.d_rot + 4 * (size_t)j0, 4 * n);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                auto putcell = [&](int cell, float x0, float x1, float x2, float x3) {
+                    float4 h, l;
+                    d2_split4(make_float4(x0, x1, x2, x3), h, l);
+                    const uint32_t o = (uint32_t)cell * D2_CHUNK + (uint32_t)r * 16u;
+                    *reinterpret_cast<float4 *>(sm + o) = h;
+                    *reinterpret_cast<float4 *>(sm + D2B_DZLO + o) = l;
+                };
                 auto putz = [&](int col, float x) {
                     const float h = tc::tf32_hi(x);
                     const uint32_t o = (uint32_t)(col >> 2) * D2_CHUNK + (uint32_t)r * 16u + (uint32_t)(col & 3) * 4u;
                     *reinterpret_cast<float *>(sm + o) = h;
                     *reinterpret_cast<float *>(sm + D2B_DZLO + o) = x - h;
                 };
-                auto row_of = [&](int k) -> size_t { return off0 + __popc(bits & ((1u << k) - 1u)); };
-                auto waits = [&]() {
-                    D2_TRACE(1, 16 * it + 1);
-                    // the last two g products of the previous tile have completed (the control warp waited before its
-                    // bulk copies, these threads wait here): the dZ rows may be overwritten; then the staged ZT tile
-                    if (it > 0) {
-                        tc::mbar_wait(&barG[0], gph[0] & 1); ++gph[0];
-                        tc::mbar_wait(&barG[1], gph[1] & 1); ++gph[1];
-                    }
-                    tc::mbar_wait(&barS, par);
+                // local index (in the staging area) of offset k's Gaussian; meaningful when bit k is set
+                auto jl = [&](int k) -> int { return (int)(off0 - j0) + __popc(bits & ((1u << k) - 1u)); };
+                auto staged = [&]() {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    asm volatile("bar.sync 1, %0;" ::"n"(D2_WORKERS) : "memory");
                 };
                 if (grp == 0) {
                     // opacity column and the position path: xyz = anchor + offset * scaling[:3]
-                    float s3[3], dnp[KO], up[KO][4], of[KO][3];
+                    float no[12], ga[36];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) s3[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + q));
+                    for (int c = 0; c < 3; ++c) { const float4 t = __ldg(ztile + c * D2_ROWS); no[4 * c] = t.x; no[4 * c + 1] = t.y; no[4 * c + 2] = t.z; no[4 * c + 3] = t.w; }
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) { const float4 t = __ldg(gtile + (8 + c) * D2_ROWS); ga[4 * c] = t.x; ga[4 * c + 1] = t.y; ga[4 * c + 2] = t.z; ga[4 * c + 3] = t.w; }
+                    float dnp[KO];
+#pragma unroll
+                    for (int k = 0; k < KO; ++k) dnp[k] = (valid && a.d_nopac) ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
+                    staged();
+                    float *dga = reinterpret_cast<float *>(a.DGA + (size_t)tile * 10 * D2_ROWS + r);
+                    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dzo[12];
 #pragma unroll
                     for (int k = 0; k < KO; ++k) {
                         const bool m = (bits >> k) & 1u;
-                        const size_t j = m ? row_of(k) : 0;
-                        dnp[k] = (valid && a.d_nopac) ? __ldg(a.d_nopac + (size_t)v * KO + k) : 0.f;
-                        up[k][0] = m ? __ldg(a.d_opacity + j) : 0.f;
+                        const int j = m ? jl(k) : 0;
+                        const float dno = dnp[k] + (m ? ust[j] : 0.f);
+                        dzo[k] = valid ? dno * (1.f - no[k] * no[k]) : 0.f;
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            up[k][1 + q] = m ? __ldg(a.d_xyz + 3 * j + q) : 0.f;
-                            of[k][q] = m ? __ldg(g + d2_tile_idx(FD + 3 + 3 * k + q)) : 0.f;
+                            const float gq = m ? ust[D2B_U_XYZ + 3 * j + q] : 0.f;
+                            dga[d2_tile_idx(3 + 3 * k + q)] = gq * ga[33 + q];            // ga: u columns 32..67; scaling at 65..67
+                            acc[q] += gq;
+                            acc[3 + q] = fmaf(gq, ga[3 + 3 * k + q], acc[3 + q]);         // offsets at u columns 35..64
                         }
                     }
-                    waits();
-                    float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int k = 0; k < KO; ++k) {
-                        const float no = z[d2_tile_idx(d2_zcol_op(k))];
-                        putz(k, valid ? (dnp[k] + up[k][0]) * (1.f - no * no) : 0.f);
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            dga[d2_tile_idx(3 + 3 * k + q)] = up[k][1 + q] * s3[q];
-                            acc[q] += up[k][1 + q];
-                            acc[3 + q] = fmaf(up[k][1 + q], of[k][q], acc[3 + q]);
-                        }
-                    }
+                    dzo[10] = 0.f; dzo[11] = 0.f;
 #pragma unroll
                     for (int q = 0; q < 3; ++q) { dga[d2_tile_idx(q)] = acc[q]; dga[d2_tile_idx(33 + q)] = acc[3 + q]; }
-#pragma unroll
-                    for (int c = KO; c < D2_RCOV; ++c) putz(c, 0.f);          // padding columns of the opacity block
+                    putcell(0, dzo[0], dzo[1], dzo[2], dzo[3]); putcell(1, dzo[4], dzo[5], dzo[6], dzo[7]);
+                    putcell(2, dzo[8], dzo[9], 0.f, 0.f); putcell(3, 0.f, 0.f, 0.f, 0.f);
                 } else if (grp == 1) {
-                    float up[KO][3];
+                    float zc[32];                            // colour block: Z columns 96..127
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) { const float4 t = __ldg(ztile + (24 + c) * D2_ROWS); zc[4 * c] = t.x; zc[4 * c + 1] = t.y; zc[4 * c + 2] = t.z; zc[4 * c + 3] = t.w; }
+                    staged();
+                    float dz[32];
 #pragma unroll
                     for (int k = 0; k < KO; ++k) {
                         const bool m = (bits >> k) & 1u;
-                        const size_t j = m ? row_of(k) : 0;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) up[k][q] = m ? __ldg(a.d_color + 3 * j + q) : 0.f;
-                    }
-                    waits();
-#pragma unroll
-                    for (int k = 0; k < KO; ++k)
+                        const int j = m ? jl(k) : 0;
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
-                            const float c = z[d2_tile_idx(d2_zcol_col(k, q))];
-                            putz(D2_RCOL + 3 * k + q, up[k][q] * c * (1.f - c));
+                            const float c = zc[3 * k + q];
+                            dz[3 * k + q] = m ? ust[D2B_U_COL + 3 * j + q] * c * (1.f - c) : 0.f;
                         }
-                    putz(D2_RCOL + 3 * KO, 0.f); putz(D2_RCOL + 3 * KO + 1, 0.f);
-                } else if (grp == 2) {
-                    float s3[3], up[KO][3];
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) s3[q] = __ldg(g + d2_tile_idx(FD + 3 + 3 * KO + 3 + q));
-#pragma unroll
-                    for (int k = 0; k < KO; ++k) {
-                        const bool m = (bits >> k) & 1u;
-                        const size_t j = m ? row_of(k) : 0;
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) up[k][q] = m ? __ldg(a.d_scaling + 3 * j + q) : 0.f;
                     }
-                    waits();
-                    float acc[3] = {0.f, 0.f, 0.f};
+                    dz[30] = 0.f; dz[31] = 0.f;
 #pragma unroll
-                    for (int k = 0; k < KO; ++k)
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            const float sg = 1.f / (1.f + expf(-z[d2_tile_idx(d2_zcol_cov(k, q))]));
-                            putz(D2_RCOV + 7 * k + q, up[k][q] * s3[q] * sg * (1.f - sg));
-                            acc[q] = fmaf(up[k][q], sg, acc[q]);
-                        }
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) dga[d2_tile_idx(36 + q)] = acc[q];
-                    dga[d2_tile_idx(39)] = 0.f;
-                    putz(D2_RCOV + 7 * KO, 0.f); putz(D2_RCOV + 7 * KO + 1, 0.f);
+                    for (int c = 0; c < 8; ++c) putcell(D2_RCOL / 4 + c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
                 } else {
-                    float4 up[KO];
+                    // covariance block: column group 2 takes offsets 0..4 (Z columns 16..50), group 3 offsets 5..9 (51..85).
+                    // (generic lambda: the two halves are separate instantiations, so every index below is a constant)
+                    auto cov = [&](auto KB, auto CELL0) {
+                        constexpr int kb = decltype(KB)::value;
+                        constexpr int cell0 = decltype(CELL0)::value;      // first Z cell this thread loads (columns 16.. / 48..)
+                        float zc[40];
 #pragma unroll
-                    for (int k = 0; k < KO; ++k) {
-                        const bool m = (bits >> k) & 1u;
-                        up[k] = m ? __ldg(reinterpret_cast<const float4 *>(a.d_rot) + row_of(k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    waits();
+                        for (int c = 0; c < 10; ++c) { const float4 t = __ldg(ztile + (cell0 + c) * D2_ROWS); zc[4 * c] = t.x; zc[4 * c + 1] = t.y; zc[4 * c + 2] = t.z; zc[4 * c + 3] = t.w; }
+                        const float4 sc = __ldg(gtile + 17 * D2_ROWS);      // u columns 68..71: scaling[3..5], 1
+                        const float s3[3] = {sc.x, sc.y, sc.z};
+                        staged();
+                        float dz[35];
 #pragma unroll
-                    for (int k = 0; k < KO; ++k) {
-                        const float s0 = z[d2_tile_idx(d2_zcol_cov(k, 3))], s1 = z[d2_tile_idx(d2_zcol_cov(k, 4))],
-                                    s2 = z[d2_tile_idx(d2_zcol_cov(k, 5))], s3 = z[d2_tile_idx(d2_zcol_cov(k, 6))];
-                        const float nrm = sqrtf(s0 * s0 + s1 * s1 + s2 * s2 + s3 * s3);
-                        const float n = fmaxf(nrm, 1e-12f);
-                        const float r0 = s0 / n, r1 = s1 / n, r2 = s2 / n, r3 = s3 / n;
-                        const float dot = nrm > 1e-12f ? r0 * up[k].x + r1 * up[k].y + r2 * up[k].z + r3 * up[k].w : 0.f;
-                        putz(D2_RCOV + 7 * k + 3, (up[k].x - r0 * dot) / n);
-                        putz(D2_RCOV + 7 * k + 4, (up[k].y - r1 * dot) / n);
-                        putz(D2_RCOV + 7 * k + 5, (up[k].z - r2 * dot) / n);
-                        putz(D2_RCOV + 7 * k + 6, (up[k].w - r3 * dot) / n);
-                    }
+                        for (int kk = 0; kk < 5; ++kk) {
+                            const int k = kb + kk;
+                            const bool m = (bits >> k) & 1u;
+                            const int j = m ? jl(k) : 0;
+                            // Z column of (k, q) = 16 + 7 k + q; this thread's zc[] starts at column 4 * cell0
+                            const int zb = D2_ZCOV + 7 * k - 4 * cell0;
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const float sg = 1.f / (1.f + expf(-zc[zb + q]));
+                                const float gq = m ? ust[D2B_U_SCL + 3 * j + q] : 0.f;
+                                dz[7 * kk + q] = gq * s3[q] * sg * (1.f - sg);
+                                scl_part[q] = fmaf(gq, sg, scl_part[q]);
+                            }
+                            const float4 gr = m ? *reinterpret_cast<const float4 *>(ust + D2B_U_ROT + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float q0 = zc[zb + 3], q1 = zc[zb + 4], q2 = zc[zb + 5], q3 = zc[zb + 6];
+                            const float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+                            const float inv = 1.f / fmaxf(nrm, 1e-12f);
+                            const float r0 = q0 * inv, r1 = q1 * inv, r2 = q2 * inv, r3 = q3 * inv;
+                            const float dot = nrm > 1e-12f ? r0 * gr.x + r1 * gr.y + r2 * gr.z + r3 * gr.w : 0.f;
+                            dz[7 * kk + 3] = (gr.x - r0 * dot) * inv; dz[7 * kk + 4] = (gr.y - r1 * dot) * inv;
+                            dz[7 * kk + 5] = (gr.z - r2 * dot) * inv; dz[7 * kk + 6] = (gr.w - r3 * dot) * inv;
+                        }
+                        if constexpr (kb == 0) {             // dZ columns 16..50: cells 4..11, then 48, 49, 50
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) putcell(4 + c, dz[4 * c], dz[4 * c + 1], dz[4 * c + 2], dz[4 * c + 3]);
+                            putz(48, dz[32]); putz(49, dz[33]); putz(50, dz[34]);
+                            s_ex[r][0] = scl_part[0]; s_ex[r][1] = scl_part[1]; s_ex[r][2] = scl_part[2];
+                        } else {                             // dZ columns 51..85 (+ padding 86, 87): 51, then cells 13..21
+                            putz(51, dz[0]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) putcell(13 + c, dz[1 + 4 * c], dz[2 + 4 * c], dz[3 + 4 * c], dz[4 + 4 * c]);
+                            putcell(21, dz[33], dz[34], 0.f, 0.f);
+                        }
+                    };
+                    if (grp == 2) cov(std::integral_constant<int, 0>{}, std::integral_constant<int, 4>{});
+                    else cov(std::integral_constant<int, 5>{}, std::integral_constant<int, 12>{});
                 }
             }
             tc::fence_proxy_async();
             tc::tc_fence_before();
             D2_TRACE(1, 16 * it + 2);
             d2_bar_sync_all();                               // 1
+            if (grp == 3)                                    // scale sums of all ten offsets -> DGA columns 36..38 (39: the constant's slot)
+                a.DGA[((size_t)tile * 10 + 9) * D2_ROWS + r] = make_float4(scl_part[0] + s_ex[r][0], scl_part[1] + s_ex[r][1], scl_part[2] + s_ex[r][2], 0.f);
             // ---- gate bits of this thread's 24 hidden columns (for epilogue b1), loaded while b1 runs ---------------------
             uint32_t hbits = 0u;
             {
@@ -500,7 +535,7 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
         attr_dev[attr_i] = 1;
     }
     D2Bwd a;
-    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = dd.ntiles;
+    a.V = dd.V; a.M = M; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = dd.ntiles;
     a.XT = f.XT; a.HT = f.HT; a.ZT = f.ZT; a.maskbits = f.maskbits; a.offs = f.offs;
     a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
     a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.DGA = b.DGA; a.part = b.part;
