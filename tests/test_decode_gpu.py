@@ -200,7 +200,8 @@ def test_decode_matches_oracle_large(level, rc, N):
             assert e["l2"] < 1e-3 and e["amax"] < 5e-3, (what, e, worst_entry(got, want))
             a_, b_ = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
             bad = np.abs(a_ - b_) > 3e-3 * np.maximum(np.abs(b_), 1e-2 * np.abs(b_).max())
-            assert bad.sum() <= max(3, 1e-4 * bad.size), (what, int(bad.sum()), bad.size)
+            if bad.size >= 10000:       # (small tensors -- a few hundred weights -- are covered by the two bounds above)
+                assert bad.sum() <= 1e-4 * bad.size, (what, int(bad.sum()), bad.size)
 
         for k in ("_anchor", "_offset", "_anchor_feat", "_scaling"):
             close(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), k)
