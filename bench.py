@@ -517,9 +517,13 @@ def multi_gpu_check(w: Workload):
                 continue
             scale = max(float(b.abs().max()), 1e-20)
             worst = max(worst, float((a - b).abs().max()) / scale)
-        res = {"views": nv, "grad_max_abs_over_max": worst, "stats_equal": bool(all(torch.equal(a, b) for a, b in zip(got_s, want_s))),
+        # counters (anchor_demon, offset_denom: integer-valued) must be identical; the two sums of floats (opacity, screen-space
+        # gradient norms) come from kernels whose atomics reorder fp32 additions from run to run: 1e-4 of their largest entry
+        counters_equal = bool(torch.equal(got_s[1], want_s[1]) and torch.equal(got_s[3], want_s[3]))
+        sums_close = bool(all(float((a - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-20) for a, b in ((got_s[0], want_s[0]), (got_s[2], want_s[2]))))
+        res = {"views": nv, "grad_max_abs_over_max": worst, "stat_counters_equal": counters_equal, "stat_sums_close": sums_close,
                "visible_count": [int(got_n), int(want_n)], "allreduce_bytes": w.bucket.nbytes(),
-               "ok": bool(worst < 2e-4 and got_n == want_n),
+               "ok": bool(worst < 2e-4 and got_n == want_n and counters_equal and sums_close),
                "what": "rank r renders view r of a " + str(nv) + "-view ring (NCCL: all_gather of rendered images for the cross-view term, in-place "
                        "gradient all-reduce, last-view statistics broadcast, int64 count all-reduce) vs rank 0 rendering every view alone"}
     pc.feat_planes.Q0 = q0

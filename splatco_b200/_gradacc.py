@@ -27,28 +27,32 @@ _ALIGN = 64           # floats (256 bytes): every carved buffer keeps the alignm
 
 
 _last = {}            # device index -> flat buffers of the most recent finished backward pass
-_arena = {}           # device index -> {cur: flat being carved, used: floats taken from it, total: floats carved this pass}
-_arena_size = {}      # device index -> floats the previous pass carved (sizes the next pass's single allocation)
+_arena = {}           # (device index, leaf?) -> {cur: flat being carved, used: floats taken from it, total: floats carved this pass}
+_arena_size = {}      # (device index, leaf?) -> floats the previous pass carved (sizes the next pass's single allocation)
+# Two arenas per pass: gradients of LEAF tensors (parameters: what a multi-GPU caller all-reduces) and gradients of
+# intermediate tensors (the cached TriPlaneAttention outputs, the channel-last plane copies), which autograd consumes
+# inside the pass and nobody needs afterwards.
 
 
 def _end_of_pass(index):
     with _lock:
         table = _passes.pop(index, None)
-        arena = _arena.pop(index, None)
-        if arena is not None:
-            _arena_size[index] = arena["total"]
+        for leaf in (True, False):
+            arena = _arena.pop((index, leaf), None)
+            if arena is not None:
+                _arena_size[(index, leaf)] = arena["total"]
         if table is not None:
             seen, flats = set(), []
-            for flat, _, _ in table.values():
-                if id(flat) not in seen:
+            for flat, _, _, leaf in table.values():
+                if leaf and id(flat) not in seen:
                     seen.add(id(flat))
                     flats.append(flat)
             _last[index] = flats
 
 
 def last_pass_buffers(device):
-    """Flat fp32 buffers that hold the shared gradients of the most recent backward pass on `device` (the
-    parameters' .grad are views of them).  Same sizes on every rank of a replicated model, so a multi-GPU caller
+    """Flat fp32 buffers that hold the shared LEAF gradients of the most recent backward pass on `device` (the
+    parameters' .grad are views of them; gradients of intermediate tensors live elsewhere).  Same sizes on every rank of a replicated model, so a multi-GPU caller
     can all-reduce THEM in place instead of packing each .grad into a bucket (multiview.GradBucket)."""
     device = torch.device(device)
     index = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
@@ -57,7 +61,8 @@ def last_pass_buffers(device):
 
 
 def acquire(device, requests, want_views=False):
-    """requests: list of (key or None, shape).  Returns a list of (pointer, ret): the address to
+    """requests: list of (key or None, shape) or (key or None, shape, is_leaf) -- is_leaf (default True) says whether the
+    gradient belongs to a leaf tensor (a parameter) or to an intermediate one.  Returns a list of (pointer, ret): the address to
     accumulate into and what to return to autograd for that input (None when an earlier node of this
     backward pass already returned the buffer; do not keep `ret`: autograd adopts it as .grad without a
     copy only while nobody else holds it).  key None = private buffer, never shared.  With
@@ -77,34 +82,46 @@ def acquire(device, requests, want_views=False):
             _end_of_pass(index)
             table = {}
     out = [None] * len(requests)
-    todo, total = [], 0
-    for n, (key, shape) in enumerate(requests):
+    pending = {True: [], False: []}
+    for n, req in enumerate(requests):
+        key, shape = req[0], req[1]
+        leaf = bool(req[2]) if len(req) > 2 else True
         hit = table.get(key) if key is not None else None
         if hit is not None:
-            flat, off, numel = hit
+            flat, off, numel, _ = hit
             out[n] = (flat.data_ptr() + 4 * off, None, flat[off:off + numel].view(shape)) if want_views else \
                      (flat.data_ptr() + 4 * off, None)
         else:
             numel = 1
             for s in shape:
                 numel *= int(s)
-            todo.append((n, key, shape, total, numel))
-            total += (numel + _ALIGN - 1) // _ALIGN * _ALIGN
-    if todo:
+            lst = pending[leaf]
+            off = lst[-1][3] + (lst[-1][4] + _ALIGN - 1) // _ALIGN * _ALIGN if lst else 0
+            lst.append((n, key, shape, off, numel))
+    for leaf, todo in pending.items():
+        if not todo:
+            continue
+        total = todo[-1][3] + (todo[-1][4] + _ALIGN - 1) // _ALIGN * _ALIGN
+        akey = (index, leaf)
+        _carve(table, out, todo, total, akey, index in _passes, device, want_views, leaf)
+    return out
+
+
+def _carve(table, out, todo, total, akey, in_pass, device, want_views, leaf):
+    if True:
         # ONE zero-filled allocation per backward pass (sized from what the previous pass carved): the decode nodes, the
         # TriPlaneAttention backward and the plane unpacking all carve from it, so a multi-GPU caller all-reduces one
         # buffer with one collective (multiview.GradBucket) and the pass pays one fill kernel
         total = max(total, 1)
-        in_pass = index in _passes
-        arena = _arena.get(index) if in_pass else None
+        arena = _arena.get(akey) if in_pass else None
         if arena is not None and arena["used"] + total <= arena["cur"].numel():
             flat, start = arena["cur"], arena["used"]
         else:
-            want = max(total, _arena_size.get(index, 0)) if (in_pass and arena is None) else total
+            want = max(total, _arena_size.get(akey, 0)) if (in_pass and arena is None) else total
             flat, start = torch.zeros(want, dtype=torch.float32, device=device), 0
             if in_pass:
                 if arena is None:
-                    arena = _arena[index] = {"cur": flat, "used": 0, "total": 0}
+                    arena = _arena[akey] = {"cur": flat, "used": 0, "total": 0}
                 arena["cur"], arena["used"] = flat, 0
         if arena is not None:
             arena["used"] = start + total
@@ -117,5 +134,4 @@ def acquire(device, requests, want_views=False):
             buf = (piece if piece.numel() == numel else piece[:numel]).view(shape)
             out[n] = (base + 4 * off, buf, buf) if want_views else (base + 4 * off, buf)
             if key is not None:
-                table[key] = (flat, start + off, numel)
-    return out
+                table[key] = (flat, start + off, numel, leaf)

@@ -238,7 +238,7 @@ class _FusedDecode(torch.autograd.Function):
         for n, (o, shp) in enumerate(zip(origs, shapes)):
             if shp is None:
                 continue
-            reqs.append((id(o) if need[n] else None, shp))
+            reqs.append((id(o) if need[n] else None, shp, bool(getattr(o, "is_leaf", True))))
             where.append(n)
         with _lib.on_device(dev):
             got = _gradacc.acquire(dev, reqs)
@@ -305,7 +305,7 @@ class _TriPlaneAttention(torch.autograd.Function):
         # plane gradients go into the same per-backward-pass buffers the decode nodes scatter their
         # direct (un-attended) level-0 plane gradients into (_gradacc)
         with _lib.on_device(dev):
-            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, t.shape) for n, (o, t) in enumerate(zip(ctx.origs, ins))])
+            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, t.shape, bool(o.is_leaf)) for n, (o, t) in enumerate(zip(ctx.origs, ins))])
             ptrs = [g[0] for g in got]
             rets = [g[1] if need[n] else None for n, g in enumerate(got)]
             del got
@@ -344,7 +344,7 @@ class _PackPlanes(torch.autograd.Function):
         dev = ctx.origs[0].device
         need = ctx.needs_input_grad
         with _lib.on_device(dev):
-            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, shp) for n, (o, shp) in enumerate(zip(ctx.origs, ctx.shapes))])
+            got = _gradacc.acquire(dev, [(id(o) if need[n] else None, shp, bool(o.is_leaf)) for n, (o, shp) in enumerate(zip(ctx.origs, ctx.shapes))])
             ptrs = [g[0] for g in got]
             rets = [g[1] if need[n] else None for n, g in enumerate(got)]
             del got
