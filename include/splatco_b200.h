@@ -140,6 +140,12 @@ int splatco_blend_bwd_upstream(int P, int64_t R, int H, int W, const float *bg, 
                                const void *image, const float *dL_dpix, float *dL_dmean2D, float *dL_dconic,
                                float *dL_dopacity, float *dL_dcolor, void *stream);
 
+/* A/B switch of the blend kernels (process-wide; timing and debugging only; 0 keeps the current choice).
+ *   fwd: 1 = warp-synchronous walk of the patch masks (one splat per warp step)
+ *   bwd: 1 = per-visit nine-sum transposition buffer, 2 = two-value matrix-form reduction on mma.sync (default),
+ *        3 = the same with 256-splat batches
+ * Environment: SPLATCO_BLEND_FWD, SPLATCO_BLEND_BWD. */
+int splatco_blend_set_impl(int fwd, int bwd);
 /* Work census of a view's blend (measurement aid, bench.py's issue-slot roofline): out2[0] = (pixel, instance) pairs
  * the front-to-back walk visits before each pixel terminates, out2[1] = LIVE pairs among them (alpha >= 1/255: the pairs
  * that contribute colour and receive gradients).  out2: two device uint64. */

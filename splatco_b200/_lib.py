@@ -52,6 +52,7 @@ SIGNATURES = {
     "splatco_decode_bwd_ws_bytes": (_sz, [_i, _i, _i]),
     "splatco_decode_count_ptr": (_vp, [_vp, _i, _i, _i]),
     "splatco_decode_gathered_rows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "splatco_blend_set_impl": (_i, [_i, _i]),
     "splatco_decode_set_impl": (_i, [_i]),
     "splatco_decode_profile": (_i, [_i]),
     "splatco_decode_profile_read": (_i, [_vp, _vp]),

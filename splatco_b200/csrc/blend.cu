@@ -20,6 +20,7 @@
 // column-wise in its own shared-memory transposition buffer and, every third visit, sums the 27 rows with 16-byte
 // loads and issues ONE global RED per sum -- 32x fewer global atomics than per-pixel atomics, no shuffle butterfly.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace splatco {
 
@@ -87,7 +88,8 @@ __device__ __forceinline__ SplatCoef splat_setup(float sx, float sy, float A, fl
 }
 
 // turn the per-splat 8-bit masks of one staging warp into 8 ballot words s_mask[w][word]
-__device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)[BLEND_WORDS], int word) {
+template <int WORDS>
+__device__ __forceinline__ void publish_masks(uint32_t mask8, uint32_t (*s_mask)[WORDS], int word) {
     const int lane = threadIdx.x & 31;
     uint32_t mine = 0;
 #pragma unroll
@@ -134,7 +136,7 @@ blend_fwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 s_k0[j] = sc.k0; s_k1[j] = sc.k1; s_b[j] = r2.x;
                 mask8 = sc.mask8;
             }
-            publish_masks(mask8, s_mask, h * 8 + warp);
+            publish_masks<BLEND_WORDS>(mask8, s_mask, h * 8 + warp);
         }
         __syncthreads();
         if (__all_sync(0xffffffffu, done)) continue;
@@ -299,7 +301,7 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
                 s_rec[3 * j + 2] = make_float4(r2.x, __uint_as_float(id), r1.y > 0.f ? 1.0f / r1.y : 0.f, 0.f);
                 mask8 = sc.mask8;
             }
-            publish_masks(mask8, s_mask, h * 8 + warp);
+            publish_masks<BLEND_WORDS>(mask8, s_mask, h * 8 + warp);
         }
         __syncthreads();
         // slots whose position is at or behind this warp's deepest contributor cannot receive gradient:
@@ -357,9 +359,225 @@ blend_bwd_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ p
     }
 }
 
+
+// ---- backward, matrix-form reduction (v2) -------------------------------------------------------------
+// Same walk, same skip decisions and the same per-pixel recurrences as blend_bwd_kernel; only the reduction over the
+// 32 pixels of a patch differs.  Every one of the nine per-(patch, splat) sums is  sum_lanes x_lane * w_lane,k  with
+// just two per-visit lane values -- x = D (= dL/dG * G) for the six geometric sums, x = alpha * T for the three colour
+// sums -- and lane weights that are CONSTANT over the whole kernel: the monomials {1, u, v, u^2, uv, v^2} of the
+// lane's patch-centred pixel coordinates (compile-time constants once unrolled) and the pixel's dL/dpixel.  So a lane
+// parks two floats per visit (not nine); 16 visits form a [16 x 32] matrix per value, and at flush time lane (r, h)
+// takes the 16 columns of pixel rows 2h, 2h+1 of visit r with 16-byte loads (rows padded to 36 floats: conflict-free),
+// forms the partial moments with constant-weight FMAs (row-factored: 3 sums per pixel row, combined with v, v^2), the
+// colour dot products against the patch's dL/dpixel table, and one xor-16 exchange completes the nine sums.  The
+// epilogue turns the raw pixel moments into the moments about the splat centre (S_x = sx S - S_u, ...) and issues the
+// global REDs, once per (warp, splat) like before.  (An mma.sync variant of this flush -- 2xTF32 / 3xTF32 -- was
+// measured 13 % slower than the transposition-buffer kernel: the legacy tensor path is slow on sm_100a.)
+constexpr int MR_ROWS = 16, MR_STRIDE = 36;
+constexpr int MR_WARP_FLOATS = 2 * MR_ROWS * MR_STRIDE + 3 * 32 + MR_ROWS;     // X_g, X_d, dL/dpixel table, slot of each row
+template <int BATCH> constexpr size_t bwd2_smem() { return (size_t)BATCH * 48 + (size_t)(BLEND_THREADS / 32) * MR_WARP_FLOATS * sizeof(float); }
+
+template <int BATCH>
+__global__ void __launch_bounds__(BLEND_THREADS, BATCH == 256 ? 4 : 3)
+blend_bwd2_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
+                  const float4 *__restrict__ rec, int W, int H, int gx, const float *__restrict__ bg,
+                  const float *__restrict__ final_T, const int32_t *__restrict__ n_contrib,
+                  const float *__restrict__ dL_dpix, float *__restrict__ dL_dmean2D,
+                  float *__restrict__ dL_dconic, float *__restrict__ dL_dopacity,
+                  float *__restrict__ dL_dcolor, const uint32_t *__restrict__ order) {
+    constexpr int WORDS = BATCH / 32, PER_THREAD = BATCH / BLEND_THREADS;
+    extern __shared__ float4 s_dyn4[];
+    float4 *const s_rec = s_dyn4;                                                   // [BATCH * 3]
+    float *const s_buf_all = reinterpret_cast<float *>(s_dyn4 + BATCH * 3);         // [8][MR_WARP_FLOATS]
+    __shared__ uint32_t s_mask[8][WORDS];
+    __shared__ int s_max[BLEND_THREADS / 32];
+    const int tile = order ? (int)order[blockIdx.x] : (int)blockIdx.x;
+    const int tile_x = tile % gx, tile_y = tile / gx;
+    int px, py;
+    float u, v;
+    pixel_of_thread(tile_x, tile_y, px, py, u, v);
+    const bool inside = px < W && py < H;
+    const float cx = (float)(tile_x * TILE) + 7.5f, cy = (float)(tile_y * TILE) + 7.5f;
+    const int2 range = ranges[tile];
+    const size_t pid = (size_t)py * W + px, HW = (size_t)H * W;
+    const float T_final = inside ? final_T[pid] : 0.f;
+    const int last = inside ? n_contrib[pid] : 0;
+    float T = T_final;
+    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
+    if (inside) { dp0 = dL_dpix[pid]; dp1 = dL_dpix[HW + pid]; dp2 = dL_dpix[2 * HW + pid]; }
+    const float neg_Tf_bg = -T_final * (bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2);
+    float ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t a_rec = (uint32_t)__cvta_generic_to_shared(s_rec);
+    float *const xg = s_buf_all + warp * MR_WARP_FLOATS;
+    float *const xd = xg + MR_ROWS * MR_STRIDE;
+    float *const wc = xd + MR_ROWS * MR_STRIDE;                // [3][32] dL/dpixel of the patch
+    int *const meta = reinterpret_cast<int *>(wc + 96);        // [MR_ROWS] staged slot of each parked visit
+    wc[lane] = dp0; wc[32 + lane] = dp1; wc[64 + lane] = dp2;
+
+    const int warp_last = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0) s_max[warp] = warp_last;
+    __syncthreads();
+    int tile_last = 0;
+#pragma unroll
+    for (int w = 0; w < BLEND_THREADS / 32; ++w) tile_last = max(tile_last, s_max[w]);
+
+    // flush roles of this lane: parked visit fr, pixel rows 2 fh, 2 fh + 1 of the patch
+    const int fr = lane & 15, fh = lane >> 4;
+    const float fv0 = (float)(2 * fh) - 1.5f;
+    const float pcx = (float)((warp & 1) * 8 - 4), pcy = (float)((warp >> 1) * 4 - 6);   // patch centre - tile centre
+    const float half_w = -0.5f * (float)W, half_h = -0.5f * (float)H;
+    const uint32_t a_rowg = (uint32_t)__cvta_generic_to_shared(xg) + (uint32_t)(fr * MR_STRIDE + 16 * fh) * 4u;
+    const uint32_t a_rowd = (uint32_t)__cvta_generic_to_shared(xd) + (uint32_t)(fr * MR_STRIDE + 16 * fh) * 4u;
+    const uint32_t a_wrow = (uint32_t)__cvta_generic_to_shared(wc) + (uint32_t)(16 * fh) * 4u;
+    int nbuf = 0;                                     // parked visits (warp-uniform)
+
+    auto flush = [&]() {
+        __syncwarp();
+        // lane (fr, fh): visit row fr, pixel rows 2 fh and 2 fh + 1 of the patch (source lanes 16 fh .. 16 fh + 15)
+        float S = 0.f, Su = 0.f, Sv = 0.f, Suu = 0.f, Suv = 0.f, Svv = 0.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+#pragma unroll
+        for (int y = 0; y < 2; ++y) {
+            const float4 g0 = lds128(a_rowg + 32u * y), g1 = lds128(a_rowg + 32u * y + 16);
+            const float4 d0 = lds128(a_rowd + 32u * y), d1 = lds128(a_rowd + 32u * y + 16);
+            const float xs[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float ds[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float uc = (float)c - 3.5f;
+                r0 += xs[c]; r1 = fmaf(xs[c], uc, r1); r2 = fmaf(xs[c], uc * uc, r2);
+            }
+            const float vy = fv0 + (float)y;
+            S += r0; Su += r1; Suu += r2;
+            Sv = fmaf(vy, r0, Sv); Suv = fmaf(vy, r1, Suv); Svv = fmaf(vy * vy, r0, Svv);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 w0 = lds128(a_wrow + 128u * k + 32u * y), w1 = lds128(a_wrow + 128u * k + 32u * y + 16);
+                float acc = ds[0] * w0.x;
+                acc = fmaf(ds[1], w0.y, acc); acc = fmaf(ds[2], w0.z, acc); acc = fmaf(ds[3], w0.w, acc);
+                acc = fmaf(ds[4], w1.x, acc); acc = fmaf(ds[5], w1.y, acc); acc = fmaf(ds[6], w1.z, acc); acc = fmaf(ds[7], w1.w, acc);
+                if (k == 0) C0 += acc; else if (k == 1) C1 += acc; else C2 += acc;
+            }
+        }
+        S += __shfl_xor_sync(0xffffffffu, S, 16); Su += __shfl_xor_sync(0xffffffffu, Su, 16); Sv += __shfl_xor_sync(0xffffffffu, Sv, 16);
+        Suu += __shfl_xor_sync(0xffffffffu, Suu, 16); Suv += __shfl_xor_sync(0xffffffffu, Suv, 16); Svv += __shfl_xor_sync(0xffffffffu, Svv, 16);
+        C0 += __shfl_xor_sync(0xffffffffu, C0, 16); C1 += __shfl_xor_sync(0xffffffffu, C1, 16); C2 += __shfl_xor_sync(0xffffffffu, C2, 16);
+        if (fr < nbuf) {
+            const uint32_t addr = a_rec + (uint32_t)meta[fr] * 48u;
+            const float4 r0 = lds128(addr);                            // sx, sy, a2, b2
+            const float4 r2 = lds128(addr + 32);                       // b, id, 1/opacity, -
+            const uint32_t id = __float_as_uint(r2.y);
+            const float sxp = r0.x - pcx, syp = r0.y - pcy;
+            const float Sx = fmaf(sxp, S, -Su), Sy = fmaf(syp, S, -Sv);      // moments about the splat centre
+            if (fh == 0) {
+                const float conA = r0.z * (-2.0f / kLog2e), conB = r0.w * (-1.0f / kLog2e);
+                const float conC = lds128(addr + 16).x * (-2.0f / kLog2e);
+                const float a = S * r2.z, b = half_w * fmaf(conA, Sx, conB * Sy), c = half_h * fmaf(conC, Sy, conB * Sx);
+                const float d = -0.5f * fmaf(sxp, Sx - Su, Suu);
+                if (a != 0.f) atomicAdd(dL_dopacity + id, a);
+                if (b != 0.f) atomicAdd(dL_dmean2D + 3u * id, b);
+                if (c != 0.f) atomicAdd(dL_dmean2D + 3u * id + 1, c);
+                if (d != 0.f) atomicAdd(dL_dconic + 3u * id, d);
+            } else {
+                const float a = -0.5f * (fmaf(sxp, Sy, Suv) - syp * Su), b = -0.5f * fmaf(syp, Sy - Sv, Svv);
+                if (a != 0.f) atomicAdd(dL_dconic + 3u * id + 1, a);
+                if (b != 0.f) atomicAdd(dL_dconic + 3u * id + 2, b);
+                if (C0 != 0.f) atomicAdd(dL_dcolor + 3u * id, C0);
+                if (C1 != 0.f) atomicAdd(dL_dcolor + 3u * id + 1, C1);
+                if (C2 != 0.f) atomicAdd(dL_dcolor + 3u * id + 2, C2);
+            }
+        }
+        __syncwarp();
+        nbuf = 0;
+    };
+
+    // walk positions tile_last-1 .. 0 in batches, back to front; slot j holds position hi-1-j
+    for (int hi = tile_last; hi > 0; hi -= BATCH) {
+        const int nb = min(BATCH, hi);
+        __syncthreads();                        // every warp is done with the previous batch (and has flushed)
+#pragma unroll
+        for (int h = 0; h < PER_THREAD; ++h) {
+            const int j = h * BLEND_THREADS + (int)threadIdx.x;
+            uint32_t mask8 = 0;
+            if (j < nb) {
+                const uint32_t id = point_list[range.x + hi - 1 - j];
+                const float4 r0 = rec[3 * (size_t)id], r1 = rec[3 * (size_t)id + 1], r2 = rec[3 * (size_t)id + 2];
+                const float sx = r0.x - cx, sy = r0.y - cy;
+                const SplatCoef sc = splat_setup(sx, sy, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w);
+                s_rec[3 * j] = sc.k0; s_rec[3 * j + 1] = sc.k1;
+                s_rec[3 * j + 2] = make_float4(r2.x, __uint_as_float(id), r1.y > 0.f ? 1.0f / r1.y : 0.f, 0.f);
+                mask8 = sc.mask8;
+            }
+            publish_masks<WORDS>(mask8, s_mask, h * 8 + warp);
+        }
+        __syncthreads();
+        const int skip = hi - warp_last;
+        const int nwords = (nb + 31) >> 5;
+#pragma unroll 1
+        for (int word = 0; word < nwords; ++word) {
+            uint32_t bits = s_mask[warp][word];
+            const int lo = word * 32;
+            if (skip >= lo + 32) bits = 0;
+            else if (skip > lo) bits &= ~((1u << (skip - lo)) - 1u);
+            while (bits) {
+                const int j = lo + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t addr = a_rec + (uint32_t)j * 48u;
+                const float4 k0 = lds128(addr);
+                const float4 k1 = lds128(addr + 16);
+                float dx, dy;
+                const float p2 = eval_p2(k0, k1.x, u, v, dx, dy);
+                const float e = p2 + k1.y;
+                const bool live = (hi - 1 - j) < last && p2 <= 0.f && e >= kLog2Inv255;   // same decisions as the forward
+                if (!__any_sync(0xffffffffu, live)) continue;
+                float gS = 0.f, dch = 0.f;
+                if (live) {
+                    const float au = ex2_approx(e);            // o * G
+                    const float alpha = fminf(0.99f, au);
+                    const float rcp = rcp_approx(1.0f - alpha);         // 1 - alpha >= 0.01
+                    T *= rcp;
+                    dch = alpha * T;
+                    const float c0 = k1.z, c1 = k1.w, c2 = lds64(addr + 32).x;
+                    const float om = 1.f - last_alpha;
+                    ar0 = fmaf(last_alpha, lc0, om * ar0); lc0 = c0;
+                    ar1 = fmaf(last_alpha, lc1, om * ar1); lc1 = c1;
+                    ar2 = fmaf(last_alpha, lc2, om * ar2); lc2 = c2;
+                    float dL_dalpha = ((c0 - ar0) * dp0 + (c1 - ar1) * dp1 + (c2 - ar2) * dp2) * T;
+                    last_alpha = alpha;
+                    dL_dalpha = fmaf(neg_Tf_bg, rcp, dL_dalpha);
+                    gS = dL_dalpha * au;                       // D = dL/dG * G
+                }
+                xg[nbuf * MR_STRIDE + lane] = gS;
+                xd[nbuf * MR_STRIDE + lane] = dch;
+                if (lane == 0) meta[nbuf] = j;
+                if (++nbuf == MR_ROWS) flush();
+            }
+        }
+        if (nbuf) flush();                      // the records of this batch are about to be overwritten
+    }
+}
+
 }  // namespace splatco
 
 using namespace splatco;
+
+// implementation switches (splatco_blend_set_impl / SPLATCO_BLEND_FWD / SPLATCO_BLEND_BWD); see the header
+static int g_blend_impl[2] = {0, 0};
+static int blend_impl(int which) {
+    if (!g_blend_impl[which]) {
+        const char *e = getenv(which ? "SPLATCO_BLEND_BWD" : "SPLATCO_BLEND_FWD");
+        const int v = e ? atoi(e) : 0, hi = which ? 3 : 1, def = which ? 2 : 1;
+        g_blend_impl[which] = (v >= 1 && v <= hi) ? v : def;
+    }
+    return g_blend_impl[which];
+}
+extern "C" int splatco_blend_set_impl(int fwd, int bwd) {
+    SPLATCO_REQUIRE(fwd >= 0 && fwd <= 1 && bwd >= 0 && bwd <= 3, "blend_set_impl: fwd in 0..1, bwd in 0..3");
+    if (fwd) g_blend_impl[0] = fwd;
+    if (bwd) g_blend_impl[1] = bwd;
+    return 0;
+}
 
 extern "C" int splatco_blend_fwd(int64_t R, int H, int W, const float *bg, const void *geom,
                                  const void *binning, void *image, float *out_color, void *stream) {
@@ -394,14 +612,25 @@ extern "C" int splatco_blend_bwd(int P, int64_t R, int H, int W, const float *bg
     BinWs b = bin_view(const_cast<void *>(binning), R);
     const int gx = ceil_div(W, TILE), gy = ceil_div(H, TILE);
     static unsigned char attr_dev[64];       // cudaFuncSetAttribute is per device
+    const int impl = blend_impl(1);
     const int attr_i = current_device() & 63;
     if (!attr_dev[attr_i]) {
         SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(blend_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(blend_bwd2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem<512>()));
+        SPLATCO_CHECK_CUDA(cudaFuncSetAttribute(blend_bwd2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd2_smem<256>()));
         attr_dev[attr_i] = 1;
     }
-    blend_bwd_kernel<<<gx * gy, BLEND_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
-        im.ranges, b.vals[splatco_sorted_buffer_index(H, W)], reinterpret_cast<const float4 *>(geom), W, H, gx, bg,
-        im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
+    const uint32_t *plist = b.vals[splatco_sorted_buffer_index(H, W)];
+    const float4 *rec = reinterpret_cast<const float4 *>(geom);
+    if (impl == 1)
+        blend_bwd_kernel<<<gx * gy, BLEND_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(
+            im.ranges, plist, rec, W, H, gx, bg, im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
+    else if (impl == 2)
+        blend_bwd2_kernel<512><<<gx * gy, BLEND_THREADS, bwd2_smem<512>(), (cudaStream_t)stream>>>(
+            im.ranges, plist, rec, W, H, gx, bg, im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
+    else
+        blend_bwd2_kernel<256><<<gx * gy, BLEND_THREADS, bwd2_smem<256>(), (cudaStream_t)stream>>>(
+            im.ranges, plist, rec, W, H, gx, bg, im.final_T, im.n_contrib, dL_dpix, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, im.order);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }
