@@ -186,34 +186,53 @@ def test_decode_matches_oracle_large(level, rc, N):
         loss_r.backward()
         # both sides reduce the BatchNorm-backward sums over ~5.6k rows in fp32 in different orders, which
         # shows up at the 1e-3*max|g| floor: 3e-3 here (the reference-generated fixtures above hold 1e-3)
-        def close(got, want, what):
+        truth = None
+        if N > 8000:
+            # The large cases (20-40 k visible anchors, 350 k Gaussians with RANDOM head weights) are ill-conditioned in
+            # fp32: the torch oracle evaluated in fp32 and in fp64 on the SAME parameters differ by up to 2.6e-3 in norm
+            # (mlp_opacity.0.weight at (0, 4, 30000); tools/debug_decode_large.py prints the table).  So the truth is the
+            # fp64 evaluation, and the bar for the GPU path is the north star's 1e-3 -- or, where fp32 itself cannot hold
+            # that, to be at least as close to fp64 as the reference's own fp32 arithmetic is (x1.25 for run-to-run
+            # reduction order).  Entries are additionally held element-wise on the big tensors.
+            cast = lambda v_: v_.double() if v_.dtype.is_floating_point else v_
+            l64 = {k: cast(getattr(pc, k).detach().cpu().clone()).requires_grad_() for k in ("_anchor", "_offset", "_anchor_feat", "_scaling")}
+            p64 = {k: (cast(v.clone()).requires_grad_() if v.dtype.is_floating_point and "running" not in k and "xyz_m" not in k else cast(v))
+                   for k, v in p.items()}
+            r64 = D.decode(p64, l64["_anchor_feat"], l64["_anchor"], l64["_offset"], torch.exp(l64["_scaling"]), vis,
+                           cam.camera_center.cpu().double(), level, K)
+            assert np.array_equal(r64[6].numpy(), ref[6].numpy())
+            gl = torch.Generator().manual_seed(11)
+            loss64 = 0
+            for b in r64[:5]:
+                loss64 = loss64 + (b * torch.randn(b.shape, generator=gl).double()).sum()
+            loss64.backward()
+            truth = {k: v.grad.numpy() for k, v in l64.items()}
+            truth.update({k: v.grad.numpy() for k, v in p64.items() if getattr(v, "grad", None) is not None})
+
+        def close(got, want, what, key=None):
             if N <= 8000:
                 assert rel_err(got, want) < 3e-3, (what, worst_entry(got, want))
                 return
-            # The large cases (20-40 k visible anchors, 350 k Gaussians with RANDOM head weights) contain Gaussians whose
-            # four rotation outputs are all ~1e-3: rot = sr / |sr| and its backward (g - r (r.g)) / |sr| amplify the ~1e-6
-            # difference between the 3xTF32 and the torch-CPU evaluation of sr by 1 / |sr|, which shows up as a ~1 % error
-            # on a few entries (identical for both GPU implementations).  They are held in norm and by a bound on the
-            # worst entry relative to the tensor's largest; everything else still has to agree element-wise.
             from tests.util import full_path_grad_errors
-            e = full_path_grad_errors(got, want)
-            assert e["l2"] < 1e-3 and e["amax"] < 5e-3, (what, e, worst_entry(got, want))
-            a_, b_ = np.asarray(got, np.float64).ravel(), np.asarray(want, np.float64).ravel()
+            t64 = truth[key]
+            e, e_ref = full_path_grad_errors(got, t64), full_path_grad_errors(want, t64)
+            assert e["l2"] < max(1e-3, 1.25 * e_ref["l2"]) and e["amax"] < max(5e-3, 1.25 * e_ref["amax"]), (what, e, e_ref, worst_entry(got, t64))
+            a_, b_ = np.asarray(got, np.float64).ravel(), np.asarray(t64, np.float64).ravel()
             bad = np.abs(a_ - b_) > 3e-3 * np.maximum(np.abs(b_), 1e-2 * np.abs(b_).max())
             if bad.size >= 10000:       # (small tensors -- a few hundred weights -- are covered by the two bounds above)
                 assert bad.sum() <= 1e-4 * bad.size, (what, int(bad.sum()), bad.size)
 
         for k in ("_anchor", "_offset", "_anchor_feat", "_scaling"):
-            close(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), k)
+            close(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), k, k)
         for k, v in pc.feat_planes._feat.named_parameters():
             gr = pw["feat." + k].grad
             if gr is None:
                 assert v.grad is None or float(v.grad.abs().max()) == 0.0, k
                 continue
-            close(v.grad.cpu().numpy(), gr.numpy(), k)
+            close(v.grad.cpu().numpy(), gr.numpy(), k, "feat." + k)
         for name in ("mlp_opacity", "mlp_cov", "mlp_color"):
             for k, v in getattr(pc, name).named_parameters():
-                close(v.grad.cpu().numpy(), pw[f"{name}.{k}"].grad.numpy(), (name, k))
+                close(v.grad.cpu().numpy(), pw[f"{name}.{k}"].grad.numpy(), (name, k), f"{name}.{k}")
 
 
 def test_plane_feature_noise_generated_in_kernel():
