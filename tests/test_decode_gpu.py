@@ -217,10 +217,12 @@ def test_decode_matches_oracle_large(level, rc, N):
             t64 = truth[key]
             e, e_ref = full_path_grad_errors(got, t64), full_path_grad_errors(want, t64)
             assert e["l2"] < max(1e-3, 1.25 * e_ref["l2"]) and e["amax"] < max(5e-3, 1.25 * e_ref["amax"]), (what, e, e_ref, worst_entry(got, t64))
-            a_, b_ = np.asarray(got, np.float64).ravel(), np.asarray(t64, np.float64).ravel()
-            bad = np.abs(a_ - b_) > 3e-3 * np.maximum(np.abs(b_), 1e-2 * np.abs(b_).max())
+            b_ = np.asarray(t64, np.float64).ravel()
+            tol_ = 3e-3 * np.maximum(np.abs(b_), 1e-2 * np.abs(b_).max())
+            bad = np.abs(np.asarray(got, np.float64).ravel() - b_) > tol_
+            bad_ref = np.abs(np.asarray(want, np.float64).ravel() - b_) > tol_
             if bad.size >= 10000:       # (small tensors -- a few hundred weights -- are covered by the two bounds above)
-                assert bad.sum() <= 1e-4 * bad.size, (what, int(bad.sum()), bad.size)
+                assert bad.sum() <= max(1e-4 * bad.size, 1.25 * bad_ref.sum()), (what, int(bad.sum()), int(bad_ref.sum()), bad.size)
 
         for k in ("_anchor", "_offset", "_anchor_feat", "_scaling"):
             close(getattr(pc, k).grad.cpu().numpy(), leaves_cpu[k].grad.numpy(), k, k)

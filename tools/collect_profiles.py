@@ -47,6 +47,11 @@ for name in ("blend_bwd", "blend_fwd", "decode", "rest", "optim"):
 
     for r in rows[2:]:
         k = r[h.index("Kernel Name")].split("(")[0]
+        k = k.replace("void ", "").replace("splatco::", "")
+        if k.startswith("blend_bwd2_kernel"):        # bench.py looks the blend kernels up by stage name
+            k = "blend_bwd_kernel"
+        elif k.startswith("blend_fwd2_kernel"):
+            k = "blend_fwd_kernel"
         e = traffic.setdefault(k, {"launches": 0, "time_us": 0.0, "dram_bytes": 0.0, "issue_active_pct": 0.0, "tensor_active_pct": 0.0,
                                    "warp_instructions": 0.0, "threads_per_instruction": 0.0})
         e["launches"] += 1

@@ -8,9 +8,9 @@ OUT=gpurun_out
 mkdir -p $OUT
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 400 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu --no-sub --no-gpu-baseline > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"blend_bwd_kernel" -s 2 -c 1 -o $OUT/prof_blend_bwd_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:"blend_bwd2?_kernel" -s 2 -c 1 -o $OUT/prof_blend_bwd_$TAG -f \
     python bench.py --steps 1 --warmup 1 --no-cpu --no-sub --no-gpu-baseline > $OUT/ncu_blend_bwd_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"blend_fwd_kernel" -s 6 -c 1 -o $OUT/prof_blend_fwd_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:"blend_fwd2?_kernel" -s 6 -c 1 -o $OUT/prof_blend_fwd_$TAG -f \
     python bench.py --steps 1 --warmup 1 --no-cpu --no-sub --no-gpu-baseline > $OUT/ncu_blend_fwd_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on \
     -k regex:"dec2_|dec_fold_kernel|dec_bwd_fold_kernel|dec_offsets" \
