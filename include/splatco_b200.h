@@ -298,7 +298,7 @@ int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const float *gt, 
                         const float *grad_loss, float *dL_dimg, void *stream);
 
 /* Scaling regulariser of the per-view loss (train.py:195): out[0] = mean_i (scaling[i,0] * scaling[i,1] * scaling[i,2]),
- * scaling [M,3] contiguous fp32, M >= 1; ws: 8 bytes.  bwd writes d_scaling = *grad_loss * d out / d scaling.  Unlike
+ * scaling [M,3] contiguous fp32, M >= 1; ws: 16 bytes.  bwd writes d_scaling = *grad_loss * d out / d scaling.  Unlike
  * torch's prod backward (which counts zeros with a device-to-host read) neither call waits for the GPU. */
 int splatco_scaling_reg_fwd(int M, const float *scaling, void *ws, float *out, void *stream);
 int splatco_scaling_reg_bwd(int M, const float *scaling, const float *grad_loss, float *d_scaling, void *stream);

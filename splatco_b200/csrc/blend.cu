@@ -712,6 +712,7 @@ blend_bwd2_kernel(const int2 *__restrict__ ranges, const uint32_t *__restrict__ 
     }
 }
 
+
 }  // namespace splatco
 
 using namespace splatco;

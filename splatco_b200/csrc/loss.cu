@@ -32,7 +32,7 @@ static LossWindow make_window() {
 __global__ void __launch_bounds__(LS_T * LS_T)
 l1_ssim_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossWindow win,
                    float *__restrict__ d_mu1, float *__restrict__ d_exx, float *__restrict__ d_exy,
-                   double *__restrict__ sums) {
+                   double *__restrict__ sums, double count, float lambda, float *__restrict__ out) {
     __shared__ float s_x[LS_REG][LS_REG + 1], s_y[LS_REG][LS_REG + 1];
     __shared__ float s_h[5][LS_REG][LS_T + 1];          // horizontally filtered x, y, xx, yy, xy
     __shared__ float s_red[2][LS_T * LS_T / 32];
@@ -91,15 +91,21 @@ l1_ssim_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
         double s = 0.0;
         for (int w = 0; w < LS_T * LS_T / 32; ++w) s += (double)s_red[tid][w];
         atomicAdd(&sums[tid], s);
+        __threadfence();
     }
-}
-
-// out[0] = loss, out[1] = l1 mean, out[2] = ssim mean
-__global__ void l1_ssim_finish_kernel(const double *__restrict__ sums, double count, float lambda, float *__restrict__ out) {
-    const double l1 = sums[0] / count, ss = sums[1] / count;
-    out[0] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ss));
-    out[1] = (float)l1;
-    out[2] = (float)ss;
+    __syncthreads();
+    // the CTA that takes the last ticket finishes: out[0] = loss, out[1] = l1 mean, out[2] = ssim mean
+    if (tid == 0) {
+        unsigned int *ticket = reinterpret_cast<unsigned int *>(sums + 2);
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(ticket, 1u) == total - 1) {
+            __threadfence();
+            const double l1 = __ldcg(sums) / count, ss = __ldcg(sums + 1) / count;
+            out[0] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ss));
+            out[1] = (float)l1;
+            out[2] = (float)ss;
+        }
+    }
 }
 
 // dL/dimg = g_loss * [ (1 - lambda) sign(x - y) / count  -  lambda / count * (conv(d_mu1) + 2 x conv(d_exx) + y conv(d_exy)) ]
@@ -281,7 +287,7 @@ template <int NV> struct MvcLaunch {
 // queueing the view's blend / decode backward until the previous view's has drained.  Here: one reduction forward
 // (fp64 accumulator), one elementwise backward  d/ds[i,j] = g / M * prod_{k != j} s[i,k]  (exact with zeros, no sync).
 __global__ void __launch_bounds__(256)
-scaling_reg_fwd_kernel(int M, const float *__restrict__ s, double *__restrict__ sum) {
+scaling_reg_fwd_kernel(int M, const float *__restrict__ s, double *__restrict__ sum, float *__restrict__ out) {
     float a = 0.f;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < M; i += gridDim.x * 256)
         a += s[3 * (size_t)i] * s[3 * (size_t)i + 1] * s[3 * (size_t)i + 2];
@@ -294,10 +300,14 @@ scaling_reg_fwd_kernel(int M, const float *__restrict__ s, double *__restrict__ 
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += (double)red[w];
         atomicAdd(sum, t);
+        __threadfence();
+        // last ticket: the mean
+        if (atomicAdd(reinterpret_cast<unsigned int *>(sum + 1), 1u) == gridDim.x - 1) {
+            __threadfence();
+            out[0] = (float)(__ldcg(sum) / (double)M);
+        }
     }
 }
-
-__global__ void scaling_reg_finish_kernel(int M, const double *__restrict__ sum, float *__restrict__ out) { out[0] = (float)(sum[0] / (double)M); }
 
 __global__ void __launch_bounds__(256)
 scaling_reg_bwd_kernel(int M, const float *__restrict__ s, const float *__restrict__ g_loss, float *__restrict__ ds) {
@@ -318,7 +328,7 @@ static int loss_check(int C, int H, int W) {
 }
 
 extern "C" size_t splatco_loss_ws_bytes(int C, int H, int W) {
-    return 3 * align_up((size_t)C * H * W * sizeof(float)) + align_up(2 * sizeof(double));
+    return 3 * align_up((size_t)C * H * W * sizeof(float)) + align_up(3 * sizeof(double));
 }
 
 extern "C" int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const float *gt, float lambda_dssim, void *ws,
@@ -329,12 +339,11 @@ extern "C" int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const 
     const size_t map = align_up((size_t)C * H * W * sizeof(float));
     char *b = (char *)ws;
     double *sums = (double *)(b + 3 * map);
-    SPLATCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));          // two sums + the finish ticket
     static const LossWindow win = make_window();
     const dim3 grid(ceil_div(W, LS_T), ceil_div(H, LS_T), C);
-    l1_ssim_fwd_kernel<<<grid, LS_T * LS_T, 0, st>>>(H, W, img, gt, win, (float *)b, (float *)(b + map), (float *)(b + 2 * map), sums);
-    SPLATCO_CHECK_LAUNCH();
-    l1_ssim_finish_kernel<<<1, 1, 0, st>>>(sums, (double)C * H * W, lambda_dssim, out3);
+    l1_ssim_fwd_kernel<<<grid, LS_T * LS_T, 0, st>>>(H, W, img, gt, win, (float *)b, (float *)(b + map), (float *)(b + 2 * map), sums,
+                                                     (double)C * H * W, lambda_dssim, out3);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }
@@ -446,11 +455,9 @@ extern "C" int splatco_scaling_reg_fwd(int M, const float *scaling, void *ws, fl
     SPLATCO_REQUIRE(M >= 1, "scaling_reg_fwd: needs at least one row (mean of an empty tensor is NaN in the reference), M=%d", M);
     SPLATCO_REQUIRE(scaling && ws && out, "scaling_reg_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    SPLATCO_CHECK_CUDA(cudaMemsetAsync(ws, 0, sizeof(double), st));
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(double), st));            // the sum + the finish ticket
     const int grid = ceil_div(M, 256 * 8) < 148 * 4 ? ceil_div(M, 256 * 8) : 148 * 4;
-    scaling_reg_fwd_kernel<<<grid, 256, 0, st>>>(M, scaling, (double *)ws);
-    SPLATCO_CHECK_LAUNCH();
-    scaling_reg_finish_kernel<<<1, 1, 0, st>>>(M, (const double *)ws, out);
+    scaling_reg_fwd_kernel<<<grid, 256, 0, st>>>(M, scaling, (double *)ws, out);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }

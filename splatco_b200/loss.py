@@ -92,7 +92,7 @@ class _ScalingReg(torch.autograd.Function):
         M = int(s.shape[0])
         dev = s.device
         with _lib.on_device(dev):
-            ws = torch.empty(8, dtype=torch.uint8, device=dev)
+            ws = torch.empty(16, dtype=torch.uint8, device=dev)
             out = torch.empty(1, dtype=torch.float32, device=dev)
             with stage("scaling_reg_fwd"):
                 check(L.splatco_scaling_reg_fwd(M, ptr(s), ptr(ws), ptr(out), _lib.raw_stream(dev)), "splatco_scaling_reg_fwd")

@@ -55,6 +55,8 @@ def main():
     st.sort_stats("tottime")
     print(f"per step = totals / {a.steps}")
     st.print_stats(45)
+    st.sort_stats("cumtime")
+    st.print_stats(70)
 
 
 if __name__ == "__main__":
