@@ -212,9 +212,9 @@ identify_tile_ranges_kernel(uint32_t n, const uint64_t *__restrict__ keys, int2 
 // Tile-segmented binning (the path splatco_binning takes).  The 64-bit key is (tile << 32 | depth): the
 // tile part only says WHICH segment of the list an instance belongs to.  So instead of six global radix
 // passes over all R pairs, ONE multi-way partition by tile and a per-tile sort in shared memory:
-//   tile_hist     chunks of 4096 Gaussians, one CTA each: per-tile instance counts in a shared-memory
-//                 histogram, written out as one row per chunk (no global atomics)
-//   tile_colscan  per tile: exclusive prefix over the chunks (each chunk's base inside the tile's segment)
+//   tile_hist     chunks of 4096+ Gaussians, one CTA each: per-tile instance counts in a shared-memory histogram;
+//                 each non-empty (chunk, tile) count claims its slice of the tile's segment with one global atomic
+//                 on the tile total, the returned bases are written out as one row per chunk
 //   tile_scan     one CTA: exclusive scan of the T totals -> ranges
 //   tile_scatter  same chunks: slot = range start + chunk base + shared-memory atomic; stores (depth << 32 | id)
 //   tile_sort_*   one CTA per tile: LSD radix sort of the segment on the depth bits in shared memory
@@ -224,7 +224,9 @@ identify_tile_ranges_kernel(uint32_t n, const uint64_t *__restrict__ keys, int2 
 // keep ascending Gaussian id, the reference's emission order [SURVEY.md Appendix A.3].
 // Traffic: 8 B*R scattered + 8 B*R read + 12 B*R written, L2-resident at the BASELINE sizes.
 // =====================================================================================================
-constexpr int TCHUNK = 4096;                       // Gaussians per CTA of tile_hist / tile_scatter
+constexpr int TCHUNK = 4096;                       // Gaussians per CTA of tile_hist / tile_scatter (doubled until the
+                                                   // [chunks][tiles] histogram matrix fits the spare value buffer: tile_chunk())
+constexpr int TCHUNK_MAX = 1 << 17;
 constexpr int TCHUNK_THREADS = 512;
 
 __device__ __forceinline__ bool tile_rect(int i, int P, const int32_t *__restrict__ radii, const float4 *__restrict__ rec,
@@ -238,14 +240,15 @@ __device__ __forceinline__ bool tile_rect(int i, int P, const int32_t *__restric
 }
 
 __global__ void __launch_bounds__(TCHUNK_THREADS)
-tile_hist_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
-                 uint32_t *__restrict__ chunk_hist /*[nchunks][T]*/) {
+tile_hist_kernel(int P, int T, int chunk, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
+                 uint32_t *__restrict__ chunk_base /*[nchunks][T]*/, uint32_t *__restrict__ tile_count /*[T], zeroed*/,
+                 uint32_t *__restrict__ work /*[8]: list lengths [0..2], queue heads [4..6]*/) {
     extern __shared__ uint32_t s_hist[];
     for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) s_hist[t] = 0;
     __syncthreads();
-    const int base = blockIdx.x * TCHUNK;
+    const int base = blockIdx.x * chunk;
 #pragma unroll 1
-    for (int k = 0; k < TCHUNK / TCHUNK_THREADS; ++k) {
+    for (int k = 0; k < chunk / TCHUNK_THREADS; ++k) {
         const int i = base + k * TCHUNK_THREADS + threadIdx.x;
         int r0x, r0y, r1x, r1y;
         if (!tile_rect(i, P, radii, rec, gx, gy, r0x, r0y, r1x, r1y)) continue;
@@ -253,38 +256,15 @@ tile_hist_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *
             for (int x = r0x; x < r1x; ++x) atomicAdd(&s_hist[y * gx + x], 1u);
     }
     __syncthreads();
-    uint32_t *row = chunk_hist + (size_t)blockIdx.x * T;
-    for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) row[t] = s_hist[t];
-}
-
-// chunk_hist[c][t] <- exclusive prefix over c; tile_count[t] = total.  A CTA covers 32 tiles (coalesced rows) with 8
-// groups of threads that each scan a contiguous eighth of the chunks, so the dependent chain per thread is nchunks / 8.
-__global__ void __launch_bounds__(256)
-tile_colscan_kernel(int T, int nchunks, uint32_t *__restrict__ chunk_hist, uint32_t *__restrict__ tile_count,
-                    uint32_t *__restrict__ work /*[8]: list lengths [0..2], queue heads [4..6]*/) {
-    __shared__ uint32_t s_part[8][33];
+    // this chunk's slice of every tile's segment: claimed with one atomic per non-empty (chunk, tile).  The order of the
+    // chunks inside a segment is whatever order the atomics arrive in -- the per-tile sort that follows makes the list
+    // independent of it ((depth, id) is unique within a tile) -- and no second pass over the [chunks][tiles] matrix is
+    // needed to turn counts into offsets.
     if (blockIdx.x == 0 && threadIdx.x < 8) work[threadIdx.x] = 0;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int t = blockIdx.x * 32 + tx;
-    const int per = (nchunks + 7) / 8;
-    const int c0 = ty * per, c1 = min(nchunks, c0 + per);
-    uint32_t sum = 0;
-    if (t < T)
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) sum += chunk_hist[(size_t)c * T + t];
-    s_part[ty][tx] = sum;
-    __syncthreads();
-    uint32_t run = 0, total = 0;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) { const uint32_t p = s_part[g][tx]; run += g < ty ? p : 0u; total += p; }
-    if (t < T) {
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) {
-            const uint32_t v = chunk_hist[(size_t)c * T + t];
-            chunk_hist[(size_t)c * T + t] = run;
-            run += v;
-        }
-        if (ty == 0) tile_count[t] = total;
+    uint32_t *row = chunk_base + (size_t)blockIdx.x * T;
+    for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) {
+        const uint32_t c = s_hist[t];
+        row[t] = c ? atomicAdd(&tile_count[t], c) : 0u;
     }
 }
 
@@ -336,16 +316,16 @@ tile_scan_kernel(int T, const uint32_t *__restrict__ tile_count, int2 *__restric
 }
 
 __global__ void __launch_bounds__(TCHUNK_THREADS)
-tile_scatter_kernel(int P, int T, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
+tile_scatter_kernel(int P, int T, int chunk, const int32_t *__restrict__ radii, const float4 *__restrict__ rec, int gx, int gy,
                     const uint32_t *__restrict__ chunk_base /*[nchunks][T]*/, const uint32_t *__restrict__ tile_start,
                     uint64_t *__restrict__ entries, uint32_t capacity) {
     extern __shared__ uint32_t s_next[];
     const uint32_t *row = chunk_base + (size_t)blockIdx.x * T;
     for (int t = threadIdx.x; t < T; t += TCHUNK_THREADS) s_next[t] = tile_start[t] + row[t];
     __syncthreads();
-    const int base = blockIdx.x * TCHUNK;
+    const int base = blockIdx.x * chunk;
 #pragma unroll 1
-    for (int k = 0; k < TCHUNK / TCHUNK_THREADS; ++k) {
+    for (int k = 0; k < chunk / TCHUNK_THREADS; ++k) {
         const int i = base + k * TCHUNK_THREADS + threadIdx.x;
         int r0x, r0y, r1x, r1y;
         if (!tile_rect(i, P, radii, rec, gx, gy, r0x, r0y, r1x, r1y)) continue;
@@ -673,11 +653,18 @@ extern "C" int splatco_binning_radix(int P, int64_t R, int H, int W, const int32
 
 // 1 when splatco_binning(P, R, H, W) takes the tile-segmented path, whose R may be a CAPACITY (every write is clamped
 // to it); 0 when it falls back to the radix composition, which needs the exact instance count.
-static bool tile_path(int P, int64_t R, int H, int W) {
+// Gaussians per CTA of tile_hist / tile_scatter: the smallest power-of-two multiple of TCHUNK whose [chunks][tiles]
+// histogram matrix fits the 4 B*R value buffer that holds it (4K images have 32 k tiles: 4096-Gaussian chunks of a
+// 15 M-Gaussian view would need 118 M counters for 54 M instances; 16384-Gaussian chunks need 30 M).  0: no fit.
+static int tile_chunk(int P, int64_t R, int H, int W) {
     const int T = ceil_div(W, TILE) * ceil_div(H, TILE);
     const size_t hist_bytes = (size_t)T * sizeof(uint32_t);
-    return !((size_t)ceil_div(P, TCHUNK) * hist_bytes > (size_t)R * sizeof(uint32_t) || hist_bytes > 200 * 1024);
+    if (hist_bytes > 200 * 1024) return 0;
+    for (int chunk = TCHUNK; chunk <= TCHUNK_MAX; chunk *= 2)
+        if ((size_t)ceil_div(P, chunk) * hist_bytes <= (size_t)R * sizeof(uint32_t)) return chunk;
+    return 0;
 }
+static bool tile_path(int P, int64_t R, int H, int W) { return tile_chunk(P, R, H, W) != 0; }
 extern "C" int splatco_binning_accepts_capacity(int P, int64_t R, int H, int W) {
     return (P > 0 && R > 0 && H > 0 && W > 0 && tile_path(P, R, H, W)) ? 1 : 0;
 }
@@ -695,7 +682,8 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
         return 0;
     }
     SPLATCO_REQUIRE(radii && geom && binning, "binning: null pointer");
-    const int nchunks = ceil_div(P, TCHUNK);
+    const int chunk = tile_chunk(P, R, H, W);
+    const int nchunks = chunk ? ceil_div(P, chunk) : 0;
     const size_t hist_bytes = (size_t)T * sizeof(uint32_t);
     BinWs b = bin_view(binning, R);
     const int s = splatco_sorted_buffer_index(H, W);
@@ -703,7 +691,7 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
     // radix composition when they do not fit there or the tile histogram does not fit in shared memory
     // (that path treats R as the EXACT instance count: callers that pass a capacity must ask
     // splatco_binning_accepts_capacity first -- diff_gaussian_rasterization does)
-    if (!tile_path(P, R, H, W))
+    if (!chunk)
         return splatco_binning_radix(P, R, H, W, radii, geom, binning, image, stream);
     GeomWs g = geom_view(const_cast<void *>(geom), P);
     uint32_t *chunk_hist = b.vals[s ^ 1];
@@ -720,14 +708,13 @@ extern "C" int splatco_binning(int P, int64_t R, int H, int W, const int32_t *ra
                                                 (int)tsort_smem(TSORT_NT_L, TSORT_ITEMS_L)));
         attr_dev[attr_i] = 1;
     }
-    tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist);
-    SPLATCO_CHECK_LAUNCH();
-    tile_colscan_kernel<<<ceil_div(T, 32), 256, 0, st>>>(T, nchunks, chunk_hist, im.tile_count, im.work);
+    SPLATCO_CHECK_CUDA(cudaMemsetAsync(im.tile_count, 0, (size_t)T * sizeof(uint32_t), st));
+    tile_hist_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, chunk, radii, g.rec, gx, gy, chunk_hist, im.tile_count, im.work);
     SPLATCO_CHECK_LAUNCH();
     tile_scan_kernel<<<1, 1024, 0, st>>>(T, im.tile_count, im.ranges, im.cursor, (uint32_t)R, im.work, im.lists,
                                          (uint32_t)(TSORT_NT_S * TSORT_ITEMS_S), (uint32_t)(TSORT_NT_L * TSORT_ITEMS_L));
     SPLATCO_CHECK_LAUNCH();
-    tile_scatter_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, radii, g.rec, gx, gy, chunk_hist, im.cursor,
+    tile_scatter_kernel<<<nchunks, TCHUNK_THREADS, hist_bytes, st>>>(P, T, chunk, radii, g.rec, gx, gy, chunk_hist, im.cursor,
                                                                     b.keys[s ^ 1], (uint32_t)R);
     SPLATCO_CHECK_LAUNCH();
     // persistent sort CTAs pull tiles of their size class from the lists tile_scan built
