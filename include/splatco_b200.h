@@ -71,6 +71,8 @@ int splatco_visible_filter(int N, const float *means3D, const float *scales, int
  * anchors (what the boolean indexing at :21-29 computes) and their count (device, in ws; copied to count_host
  * (pinned) asynchronously if not NULL).  ws: splatco_visible_compact_ws_bytes(N). */
 size_t splatco_visible_compact_ws_bytes(int N);
+/* Device address (inside ws) of the visible-anchor count splatco_visible_filter_compact leaves behind. */
+const int32_t *splatco_visible_compact_count_ptr(const void *ws, int N);
 int splatco_visible_filter_compact(int N, const float *means3D, const float *scales, int scale_stride,
                                    const float *rots, float scale_mod, const float *view, const float *proj,
                                    float tanfovx, float tanfovy, int H, int W, int32_t *radii_out, uint8_t *mask_out,
@@ -192,6 +194,14 @@ typedef struct splatco_decode_desc {
     int32_t plane_layout;                  /* 0: plane[] / att[] (and their gradients) are [rc,E,E] as the
                                               reference stores them; 1: [E,E,8] channel-last copies made by
                                               splatco_pack_planes (rc <= 8)                              */
+    const int32_t *V_dev;                  /* NULL: V is the exact number of visible anchors.  Else (forward of the two-stage
+                                              implementation only): DEVICE pointer to the count -- e.g.
+                                              splatco_visible_compact_count_ptr -- read by the kernels; V is then only an
+                                              upper bound (grids, buffer rows), `vis` has at least V entries, and the host
+                                              need not wait for the prefilter before it queues the decode             */
+    int32_t V_layout;                      /* rows the workspaces were sized / laid out for (the V passed to
+                                              splatco_decode_*_ws_bytes); 0 = V.  A forward queued with V_dev uses
+                                              V = V_layout = capacity; its backward passes the exact V and the same V_layout */
 } splatco_decode_desc;
 
 /* Gradient destinations (same shapes as the inputs).  EVERY destination is ACCUMULATED into (+=):

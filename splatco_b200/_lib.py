@@ -30,6 +30,7 @@ SIGNATURES = {
     "splatco_sorted_buffer_index": (_i, [_i, _i]),
     "splatco_visible_filter": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp]),
     "splatco_visible_compact_ws_bytes": (_sz, [_i]),
+    "splatco_visible_compact_count_ptr": (_vp, [_vp, _i]),
     "splatco_visible_filter_compact": (_i, [_i, _vp, _vp, _i, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd": (_i, [_i, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "splatco_preprocess_fwd_counted": (_i, [_i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _i, _i, _vp, _vp, _vp, _vp]),

@@ -399,11 +399,12 @@ __device__ __forceinline__ int level_base(int l, int rc) { return l == 0 ? 0 : (
 // every table; the BatchNorm running statistics are updated by CTA 0 alone.
 constexpr int FOLD_CTAS = 16;
 __global__ void __launch_bounds__(256)
-dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const double *__restrict__ stats,
+dec_fold_kernel(DecWeights w, int V_host, const int32_t *__restrict__ Vdev, int rc, int level, int DP, int LDX, const double *__restrict__ stats,
                 float *__restrict__ mu, float *__restrict__ rstd, float *__restrict__ WpT, float *__restrict__ WcT,
                 float *__restrict__ bgeo, float *__restrict__ W1T, float *__restrict__ b1e, float *__restrict__ W2T,
                 float *__restrict__ b2, float *__restrict__ WpG, float *__restrict__ WcG, int update_running) {
     __shared__ float s_mu[DEC_MAX_DP + GD + 4], s_rstd[DEC_MAX_DP + GD + 4];
+    const int V = Vdev ? __ldg(Vdev) : V_host;          // (row count still on the device: splatco_decode_desc::V_dev)
     const int tid = threadIdx.x;
     const int gtid = blockIdx.x * 256 + tid, nthr = gridDim.x * 256;
     const int ncols = DP + GD;
@@ -417,7 +418,7 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
         s_rstd[c] = (float)(1.0 / sqrt(var + (double)w.eps));
         if (!first) continue;
         mu[c] = s_mu[c]; rstd[c] = s_rstd[c];
-        if (update_running) {
+        if (update_running && V >= 2) {       // (V < 2 is an error the caller raises; with V_dev it is only known here)
             const float unb = (float)(V > 1 ? var * (double)V / (double)(V - 1) : var);
             const float m = w.momentum;
             if (c < DP) {
@@ -434,7 +435,7 @@ dec_fold_kernel(DecWeights w, int V, int rc, int level, int DP, int LDX, const d
             }
         }
     }
-    if (first && update_running && tid == 0)
+    if (first && update_running && V >= 2 && tid == 0)
         for (int l = 0; l <= level; ++l) {
             if (w.bn_nbt[l]) *w.bn_nbt[l] += 1;
             if (w.cbn_nbt[l]) *w.cbn_nbt[l] += 1;
@@ -579,9 +580,10 @@ dec_heads_act_kernel(int V, float *__restrict__ Z, float *__restrict__ neural_op
 
 // exclusive per-anchor offsets from maskbits + scanned block offsets (same 256-wide partition)
 __global__ void __launch_bounds__(256)
-dec_offsets_kernel(int V, const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ block_offsets,
-                   uint32_t *__restrict__ offs) {
+dec_offsets_kernel(int V_host, const int32_t *__restrict__ Vdev, const uint32_t *__restrict__ maskbits,
+                   const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ offs) {
     __shared__ uint32_t s_warp[8];
+    const int V = Vdev ? __ldg(Vdev) : V_host;
     const int v = blockIdx.x * 256 + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t c = v < V ? __popc(maskbits[v]) : 0u;
@@ -1048,7 +1050,7 @@ static int v1_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_o
     dec_gather_kernel<<<gather_grid(V), GATHER_WARPS * 32, GATHER_WARPS * 2 * dd.LDX * sizeof(float), st>>>(
         p, V, dd.rc, dd.DP, dd.LDX, f.X, f.XIN, f.stats, use_tc ? f.XT : nullptr);
     SPLATCO_CHECK_LAUNCH();
-    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
+    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, V, nullptr, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
                                        f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
     SPLATCO_CHECK_LAUNCH();
     const int nb = ceil_div(V, 256);
@@ -1081,7 +1083,7 @@ static int v1_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_o
     }
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
     SPLATCO_CHECK_LAUNCH();
-    dec_offsets_kernel<<<nb, 256, 0, st>>>(V, f.maskbits, f.boff, f.offs);
+    dec_offsets_kernel<<<nb, 256, 0, st>>>(V, nullptr, f.maskbits, f.boff, f.offs);
     SPLATCO_CHECK_LAUNCH();
     if (M_host) SPLATCO_CHECK_CUDA(cudaMemcpyAsync(M_host, f.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return 0;
@@ -1364,17 +1366,19 @@ B2View b2_view(void *ws, const D2Dims &d) {
 }
 
 template <int LEVEL, int RC>
-int launch_gather2(bool packed, cudaStream_t st, const DecPtrs &p, const D2Dims &d, float4 *XT, double *stats) {
-    if (packed) dec2_gather_kernel<LEVEL, RC, true><<<d.ntiles, D2_ROWS, 0, st>>>(p, d.V, d.LDX, XT, stats);
-    else dec2_gather_kernel<LEVEL, RC, false><<<d.ntiles, D2_ROWS, 0, st>>>(p, d.V, d.LDX, XT, stats);
+int launch_gather2(bool packed, cudaStream_t st, const DecPtrs &p, const D2Dims &d, int V, const int32_t *Vdev, float4 *XT, double *stats) {
+    const int grid = Vdev ? d.ntiles : ceil_div(V, D2_ROWS);
+    if (packed) dec2_gather_kernel<LEVEL, RC, true><<<grid, D2_ROWS, 0, st>>>(p, V, Vdev, d.LDX, XT, stats);
+    else dec2_gather_kernel<LEVEL, RC, false><<<grid, D2_ROWS, 0, st>>>(p, V, Vdev, d.LDX, XT, stats);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }
 template <int LEVEL, int RC>
-int launch_inputs2(bool packed, cudaStream_t st, const DecPtrs &p, const DecInputGrads &gi, const D2Dims &d, const float4 *XT,
+int launch_inputs2(bool packed, cudaStream_t st, const DecPtrs &p, const DecInputGrads &gi, const D2Dims &d, int V, const float4 *XT,
                    const float4 *DUT, const float *mu, const float *rstd, const float *m1, const float *m2) {
-    if (packed) dec2_bwd_inputs_kernel<LEVEL, RC, true><<<d.ntiles, D2_ROWS, 0, st>>>(p, gi, d.V, XT, DUT, mu, rstd, m1, m2);
-    else dec2_bwd_inputs_kernel<LEVEL, RC, false><<<d.ntiles, D2_ROWS, 0, st>>>(p, gi, d.V, XT, DUT, mu, rstd, m1, m2);
+    const int grid = ceil_div(V, D2_ROWS);
+    if (packed) dec2_bwd_inputs_kernel<LEVEL, RC, true><<<grid, D2_ROWS, 0, st>>>(p, gi, V, XT, DUT, mu, rstd, m1, m2);
+    else dec2_bwd_inputs_kernel<LEVEL, RC, false><<<grid, D2_ROWS, 0, st>>>(p, gi, V, XT, DUT, mu, rstd, m1, m2);
     SPLATCO_CHECK_LAUNCH();
     return 0;
 }
@@ -1395,24 +1399,32 @@ int launch_inputs2(bool packed, cudaStream_t st, const DecPtrs &p, const DecInpu
         return -1;                                                                                           \
     }()
 
+// rows the workspaces are laid out for (splatco_decode_desc::V_layout; 0 = V)
+inline int d2_layout_rows(const splatco_decode_desc *d) { return d->V_layout > 0 ? d->V_layout : d->V; }
+
 int v2_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask, int32_t *M_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (d->V == 0) { if (M_host) *M_host = 0; return 0; }
-    SPLATCO_REQUIRE(d->V >= 2, "decode: BatchNorm in train mode needs more than 1 visible anchor (got %d)", d->V);
+    const int32_t *Vdev = d->V_dev;
+    // with the count still on the device the BatchNorm precondition (V >= 2) is the caller's to check once it knows V
+    SPLATCO_REQUIRE(Vdev || d->V >= 2, "decode: BatchNorm in train mode needs more than 1 visible anchor (got %d)", d->V);
+    SPLATCO_REQUIRE(d->V <= d2_layout_rows(d), "decode_fwd: V = %d exceeds V_layout = %d", d->V, d->V_layout);
+    SPLATCO_REQUIRE(!Vdev || !d->noise, "decode_fwd: an explicit noise tensor needs the exact V on the host");
     SPLATCO_REQUIRE(ws && neural_opacity && mask, "decode_fwd: null pointer");
-    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    const D2Dims dd = d2_dims(d2_layout_rows(d), d->rc, d->level);     // layout (and, with V_dev, grid) dimensions
+    const int V = d->V;                                                  // exact, or the capacity when V_dev is set
     F2View f = f2_view(ws, dd);
     const DecPtrs p = make_ptrs(d);
     const DecWeights w = make_weights(d);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.stats, 0, 2 * (size_t)dd.LDX * sizeof(double), st));
-    if (D2_DISPATCH(launch_gather2, dd.level, dd.rc, d->plane_layout != 0, st, p, dd, f.XT, f.stats)) return -2;
-    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
+    if (D2_DISPATCH(launch_gather2, dd.level, dd.rc, d->plane_layout != 0, st, p, dd, V, Vdev, f.XT, f.stats)) return -2;
+    dec_fold_kernel<<<FOLD_CTAS, 256, 0, st>>>(w, V, Vdev, dd.rc, dd.level, dd.DP, dd.LDX, f.stats, f.mu, f.rstd, f.WpT, f.WcT,
                                               f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.WpG, f.WcG, d->update_running);
     SPLATCO_CHECK_LAUNCH();
     dec2_combine_kernel<<<24, 256, 0, st>>>(dd.DP, dd.nk, dd.NB, f.WpT, f.WcT, f.bgeo, f.W1T, f.b1e, f.W2T, f.b2, f.W1S, f.W1R,
                                             f.W2B, f.b2blk, f.W2R);
     SPLATCO_CHECK_LAUNCH();
-    const int nb = ceil_div(dd.V, 256);
+    const int nb = ceil_div(V, 256);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(f.bsum, 0, (size_t)nb * sizeof(uint32_t), st));
     static unsigned char attr_dev[64];
     const int attr_i = current_device() & 63;
@@ -1421,16 +1433,16 @@ int v2_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity,
         attr_dev[attr_i] = 1;
     }
     D2Fwd a;
-    a.V = dd.V; a.nch = dd.nch; a.nk = dd.nk; a.ntiles = dd.ntiles; a.trace = g_decode_profile == 2;
+    a.V = V; a.Vdev = Vdev; a.nch = dd.nch; a.nk = dd.nk; a.trace = g_decode_profile == 2;
     a.XT = f.XT; a.W1S = f.W1S; a.W2B = f.W2B; a.b2blk = f.b2blk; a.HT = f.HT; a.ZT = f.ZT;
     a.nopac = neural_opacity; a.mask_out = mask; a.maskbits = f.maskbits; a.block_sums = f.bsum;
     prof_record(0, st);
-    dec2_mlp_fwd_kernel<<<min(dd.ntiles, D2_MAX_CTAS), D2_THREADS, D2F_SMEM, st>>>(a);
+    dec2_mlp_fwd_kernel<<<min(ceil_div(V, D2_ROWS), D2_MAX_CTAS), D2_THREADS, D2F_SMEM, st>>>(a);
     SPLATCO_CHECK_LAUNCH();
     prof_record(1, st);
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb, f.bsum, f.boff, f.total);
     SPLATCO_CHECK_LAUNCH();
-    dec_offsets_kernel<<<nb, 256, 0, st>>>(dd.V, f.maskbits, f.boff, f.offs);
+    dec_offsets_kernel<<<nb, 256, 0, st>>>(V, Vdev, f.maskbits, f.boff, f.offs);
     SPLATCO_CHECK_LAUNCH();
     if (M_host) SPLATCO_CHECK_CUDA(cudaMemcpyAsync(M_host, f.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     return 0;
@@ -1440,9 +1452,9 @@ int v2_decode_emit(const splatco_decode_desc *d, const void *ws, int M, float *x
                    float *scaling, float *rot, void *stream) {
     if (d->V == 0 || M == 0) return 0;
     SPLATCO_REQUIRE(ws && xyz && color && opacity && scaling && rot, "decode_emit: null pointer");
-    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    const D2Dims dd = d2_dims(d2_layout_rows(d), d->rc, d->level);
     F2View f = f2_view(const_cast<void *>(ws), dd);
-    dec2_compact_kernel<<<ceil_div(d->V * KO, 256), 256, 0, (cudaStream_t)stream>>>(d->V, dd.nch, f.XT, f.ZT, f.maskbits, f.offs,
+    dec2_compact_kernel<<<ceil_div(d->V * KO, 256), 256, 0, (cudaStream_t)stream>>>(d->V, d->V_dev, dd.nch, f.XT, f.ZT, f.maskbits, f.offs,
                                                                                  xyz, color, opacity, scaling, rot);
     SPLATCO_CHECK_LAUNCH();
     return 0;
@@ -1523,6 +1535,8 @@ extern "C" const int32_t *splatco_decode_count_ptr(const void *ws, int V, int rc
 extern "C" int splatco_decode_fwd(const splatco_decode_desc *d, void *ws, float *neural_opacity, uint8_t *mask,
                                   int32_t *M_host, void *stream) {
     if (check_desc(d)) return -1;
+    SPLATCO_REQUIRE(use_v2(d->rc) || (!d->V_dev && (d->V_layout == 0 || d->V_layout == d->V)),
+                    "decode_fwd: V_dev / V_layout need the two-stage implementation (rc <= 5, SPLATCO_DECODE_IMPL != 1)");
     return use_v2(d->rc) ? v2_decode_fwd(d, ws, neural_opacity, mask, M_host, stream)
                          : v1_decode_fwd(d, ws, neural_opacity, mask, M_host, stream);
 }

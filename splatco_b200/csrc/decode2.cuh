@@ -62,6 +62,9 @@ __host__ __device__ inline void d2_kslice(int nk, int s, int &c0, int &nc) {
     nc = 2 * (q + (s < r ? 1 : 0));
 }
 
+// row count known on the host (p == nullptr) or left on the device by the prefilter (splatco_decode_desc::V_dev)
+__device__ __forceinline__ int d2_count(const int32_t *p, int v) { return p ? __ldg(p) : v; }
+
 __device__ __forceinline__ int d2_zcol_op(int k) { return k; }
 __device__ __forceinline__ int d2_zcol_cov(int k, int q) { return D2_ZCOV + 7 * k + q; }
 __device__ __forceinline__ int d2_zcol_col(int k, int q) { return D2_ZCOL + 3 * k + q; }
@@ -99,10 +102,13 @@ __device__ __forceinline__ float warp_colsum8(const float (&g)[8], int lane, int
 // =======================================================================================================
 template <int LEVEL, int RC, bool PACKED>
 __global__ void __launch_bounds__(D2_ROWS)
-dec2_gather_kernel(DecPtrs p, int V, int LDX, float4 *__restrict__ XT, double *__restrict__ stats) {
+dec2_gather_kernel(DecPtrs p, int V_host, const int32_t *__restrict__ Vdev, int LDX, float4 *__restrict__ XT,
+                   double *__restrict__ stats) {
     constexpr int NS = LEVEL == 0 ? 6 : (LEVEL == 1 ? 9 : 12);
     constexpr int DP = NS * RC, NPC = (DP + 3) / 4, NCH = D2_P_CH0 + NPC;
     __shared__ float s_part[4][2][DEC_MAX_DP + GD + 9];
+    const int V = d2_count(Vdev, V_host);
+    if ((int)blockIdx.x * D2_ROWS >= V) return;          // (grid sized for an upper bound of V)
     const int r = threadIdx.x, lane = r & 31, warp = r >> 5;
     const int v = blockIdx.x * D2_ROWS + r;
     const bool valid = v < V;
@@ -331,7 +337,8 @@ constexpr uint32_t D2F_RING = 2 * D2F_ULO;                          // 147456
 constexpr uint32_t D2F_SMEM = D2F_RING + 2 * D2_RING_SLOT;          // 221184
 
 struct D2Fwd {
-    int V, nch, nk, ntiles, trace;
+    int V, nch, nk, trace;
+    const int32_t *Vdev;
     const float4 *XT;
     const uint8_t *W1S, *W2B;
     const float *b2blk;
@@ -373,7 +380,8 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
     for (int q = 0; q < 3; ++q) d2_kslice(a.nk, q, sl_c0[q], sl_nc[q]);
     auto slice_src = [&](int q) { return a.W1S + (size_t)sl_c0[q] * HD * 32; };
     auto slice_bytes = [&](int q) { return (uint32_t)sl_nc[q] * HD * 32; };
-    const int ntl = (a.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
+    const int Vn = d2_count(a.Vdev, a.V), ntiles = (Vn + D2_ROWS - 1) / D2_ROWS;
+    const int ntl = ntiles > (int)blockIdx.x ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;     // tiles of this CTA
 
     if (warp == D2_WORKERS / 32) {
         // =========================== control warp ===========================
@@ -450,7 +458,7 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
         for (int it = 0; it < ntl; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int row = tile * D2_ROWS + r;
-            const bool valid = row < a.V;
+            const bool valid = row < Vn;
             const uint32_t par = it & 1;
             D2_TRACE(0, 8 * it + 0);
             tc::mbar_wait(&barU, par);
@@ -546,10 +554,11 @@ dec2_mlp_fwd_kernel(D2Fwd a) {
 
 // compaction + post-processing (gaussian_renderer/__init__.py:96-111), one thread per (anchor, offset)
 __global__ void __launch_bounds__(256)
-dec2_compact_kernel(int V, int nch, const float4 *__restrict__ XT, const float4 *__restrict__ ZT,
+dec2_compact_kernel(int V_host, const int32_t *__restrict__ Vdev, int nch, const float4 *__restrict__ XT, const float4 *__restrict__ ZT,
                     const uint32_t *__restrict__ maskbits, const uint32_t *__restrict__ offs, float *__restrict__ xyz,
                     float *__restrict__ color, float *__restrict__ opacity, float *__restrict__ scaling, float *__restrict__ rot) {
     const int t = blockIdx.x * 256 + threadIdx.x;
+    const int V = d2_count(Vdev, V_host);
     if (t >= V * KO) return;
     const int v = t / KO, k = t - v * KO;
     const uint32_t bits = maskbits[v];

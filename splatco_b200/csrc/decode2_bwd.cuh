@@ -510,8 +510,11 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     SPLATCO_REQUIRE(fwd_ws && bwd_ws && g, "decode_bwd: null pointer");
     SPLATCO_REQUIRE(M == 0 || (d_xyz && d_color && d_opacity && d_scaling && d_rot), "decode_bwd: null upstream gradient");
     SPLATCO_REQUIRE(g->anchor_feat && g->anchor && g->offset && g->scaling, "decode_bwd: null per-anchor gradient");
+    SPLATCO_REQUIRE(!d->V_dev, "decode_bwd: the backward needs the exact V on the host (V_dev must be NULL)");
+    SPLATCO_REQUIRE(d->V <= d2_layout_rows(d), "decode_bwd: V = %d exceeds V_layout = %d", d->V, d->V_layout);
     cudaStream_t st = (cudaStream_t)stream;
-    const D2Dims dd = d2_dims(d->V, d->rc, d->level);
+    const D2Dims dd = d2_dims(d2_layout_rows(d), d->rc, d->level);       // workspace layout (the forward's)
+    const int V = d->V, ntiles = ceil_div(V, D2_ROWS);                     // exact row / tile counts
     F2View f = f2_view(const_cast<void *>(fwd_ws), dd);
     B2View b = b2_view(bwd_ws, dd);
     const DecPtrs p = make_ptrs(d);
@@ -535,12 +538,12 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
         attr_dev[attr_i] = 1;
     }
     D2Bwd a;
-    a.V = dd.V; a.M = M; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = dd.ntiles;
+    a.V = V; a.M = M; a.nch = dd.nch; a.nk = dd.nk; a.NB = dd.NB; a.ntiles = ntiles;
     a.XT = f.XT; a.HT = f.HT; a.ZT = f.ZT; a.maskbits = f.maskbits; a.offs = f.offs;
     a.d_xyz = d_xyz; a.d_color = d_color; a.d_opacity = d_opacity; a.d_scaling = d_scaling; a.d_rot = d_rot; a.d_nopac = d_neural_opacity;
     a.W2R = f.W2R; a.W1R = f.W1R; a.DUT = b.DUT; a.DGA = b.DGA; a.part = b.part;
     a.trace = g_decode_profile == 2;
-    const int ctas = min(dd.ntiles, D2_MAX_CTAS);
+    const int ctas = min(ntiles, D2_MAX_CTAS);
     prof_record(2, st);
     dec2_mlp_bwd_kernel<<<ctas, D2_THREADS, D2B_SMEM, st>>>(a);
     SPLATCO_CHECK_LAUNCH();
@@ -550,10 +553,10 @@ int v2_decode_bwd(const splatco_decode_desc *d, const void *fwd_ws, void *bwd_ws
     dec2_expand_kernel<<<48, 256, 0, st>>>(dd.DP, dd.LDX, b.red, f.WpT, f.WcT, f.bgeo, f.W1T, b.S1, b.S0, b.gW1T, b.gb1,
                                            b.gW2T, b.gb2);
     SPLATCO_CHECK_LAUNCH();
-    dec_bwd_fold_kernel<<<dim3(BWD_FOLD_CTAS, BWD_FOLD_SECTIONS), 256, 0, st>>>(w, gw, dd.V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
+    dec_bwd_fold_kernel<<<dim3(BWD_FOLD_CTAS, BWD_FOLD_SECTIONS), 256, 0, st>>>(w, gw, V, dd.rc, dd.level, dd.DP, dd.LDX, f.mu, f.rstd, f.WpG, f.WcG, b.S1, b.S0,
                                                    b.gW1T, b.gb1, b.gW2T, b.gb2, b.m1, b.m2);
     SPLATCO_CHECK_LAUNCH();
-    if (D2_DISPATCH(launch_inputs2, dd.level, dd.rc, d->plane_layout != 0, st, p, gi, dd, f.XT, b.DUT, f.mu, f.rstd, b.m1, b.m2)) return -2;
+    if (D2_DISPATCH(launch_inputs2, dd.level, dd.rc, d->plane_layout != 0, st, p, gi, dd, V, f.XT, b.DUT, f.mu, f.rstd, b.m1, b.m2)) return -2;
     return 0;
 }
 

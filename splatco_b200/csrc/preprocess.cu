@@ -402,6 +402,11 @@ extern "C" size_t splatco_visible_compact_ws_bytes(int N) {
     return 2 * align_up(nb * sizeof(uint32_t)) + align_up(sizeof(uint32_t));
 }
 
+extern "C" const int32_t *splatco_visible_compact_count_ptr(const void *ws, int N) {
+    const size_t nb = (size_t)(N > 0 ? (N + PRE_THREADS - 1) / PRE_THREADS : 1);
+    return ws ? reinterpret_cast<const int32_t *>((const char *)ws + 2 * align_up(nb * sizeof(uint32_t))) : nullptr;
+}
+
 extern "C" int splatco_visible_filter_compact(int N, const float *means3D, const float *scales, int scale_stride,
                                               const float *rots, float scale_mod, const float *view, const float *proj,
                                               float tanfovx, float tanfovy, int H, int W, int32_t *radii_out,

@@ -38,6 +38,7 @@ class DecodeDesc(C.Structure):
         ("bn_nbt", _vp * 3), ("cbn_nbt", _vp * 3),
         ("w1", _vp * 3), ("b1", _vp * 3), ("w2", _vp * 3), ("b2", _vp * 3),
         ("app_vec", _vp), ("noise", _vp), ("noise_q", C.c_float), ("noise_seed", C.c_uint64), ("plane_layout", C.c_int32),
+        ("V_dev", _vp), ("V_layout", C.c_int32),
     ]
 
 
@@ -86,7 +87,8 @@ def _c(t):
 class DecodeConfig:
     """Everything that is not a differentiable tensor input."""
     __slots__ = ("N", "K", "rc", "level", "E", "use_dist", "app_dim", "xyz_min", "xyz_max", "cam",
-                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "noise_q", "noise_seed", "plan", "raster", "packed")
+                 "bn_eps", "bn_momentum", "update_running", "buffers", "vis_idx", "noise", "noise_q", "noise_seed", "plan", "raster", "packed",
+                 "pending")
 
 
 # order of the differentiable parameter list handed to the autograd Function
@@ -158,6 +160,7 @@ def _fill_desc(cfg: DecodeConfig, V, anchor_feat, anchor, offset, scaling, att, 
     d.noise = cfg.noise.data_ptr() if cfg.noise is not None else None
     d.noise_q, d.noise_seed = cfg.noise_q, cfg.noise_seed
     d.plane_layout = 1 if cfg.packed else 0
+    d.V_dev, d.V_layout = None, 0
     return d
 
 
@@ -178,9 +181,17 @@ class _FusedDecode(torch.autograd.Function):
         else:
             pc = [t if _plain(t) else _c(t) for t in params]
             plan.param_ids = ids if all(a is b for a, b in zip(pc, params)) else None
-        V = int(cfg.vis_idx.shape[0])
         K = cfg.K
+        cp = cfg.pending if (cfg.raster is not None and 1 <= cfg.rc <= 5) else None
+        if cfg.pending is not None and cp is None:       # not the two-stage decode after all: the round-1 order
+            cfg.pending.event.synchronize()
+            cfg.vis_idx = cfg.pending.idx[:int(cfg.pending.counter[0])]
+            cfg.pending = None
+        # V: exact, or (cp: count still on the device) the capacity N every buffer of this view is sized for
+        V = int(cfg.vis_idx.shape[0])
         desc = _fill_desc(cfg, V, anchor_feat_c, anchor_c, offset_c, scaling_c, (a_xy, a_xz, a_yz), app_c, pc)
+        if cp is not None:
+            desc.V_dev, desc.V_layout = cp.count_ptr, V
         stream = _lib.raw_stream(dev)
         with _lib.on_device(dev):
             ws = _lib.empty_u8(L.splatco_decode_fwd_ws_bytes(V, cfg.rc, cfg.level), dev)
@@ -202,8 +213,19 @@ class _FusedDecode(torch.autograd.Function):
                     check(L.splatco_decode_emit(C.byref(desc), _p(ws), VK, *[_p(b) for b in bufs], stream),
                           "splatco_decode_emit")
                 sp = _dgr.preprocess_speculative(*bufs, L.splatco_decode_count_ptr(_p(ws), V, cfg.rc, cfg.level), cfg.raster)
-                sp.event.synchronize()             # M, R have landed; binning + blend keep running behind it
+                sp.event.synchronize()             # M, R (and V) have landed; binning + blend keep running behind it
                 M = int(counter[0])
+                if cp is not None:
+                    from .diff_gaussian_rasterization import clear_compaction
+                    clear_compaction(cp)
+                    V_cap, V = V, int(cp.counter[0])
+                    if V == 1:                      # (V = 0: an empty view, legal as before)
+                        raise RuntimeError(f"splatco_decode_fwd failed (-1): decode: BatchNorm in train mode needs more than 1 "
+                                           f"visible anchor (got {V})")
+                    desc.V, desc.V_dev = V, None   # the backward (and everything after the sync) works with the exact V
+                    cfg.vis_idx = cp.idx[:V]
+                    nopac, mask = nopac[:V * K], mask[:V * K]
+                    cfg.pending = None
                 xyz, color, opacity, scl, rot = [b[:M] for b in bufs]
                 _dgr.publish_speculated(sp, M, (xyz, color, opacity, scl, rot))
             else:
@@ -214,6 +236,8 @@ class _FusedDecode(torch.autograd.Function):
                     check(L.splatco_decode_emit(C.byref(desc), _p(ws), M, _p(xyz), _p(color), _p(opacity), _p(scl), _p(rot),
                                                 stream), "splatco_decode_emit")
         ctx.cfg, ctx.desc, ctx.ws, ctx.M, ctx.V = cfg, desc, ws, M, V
+        ctx.V_rows = int(desc.V_layout) or V                    # rows the workspaces are laid out for
+        _v_last[id(cfg.plan)] = V
         # everything a pointer in desc refers to stays alive with the node
         ctx.keep = (tensors, app_c, pc, cfg.vis_idx, cfg.noise, cfg.xyz_min, cfg.xyz_max, cfg.cam)
         # the forward input OBJECTS: their identity keys the shared gradient buffers of a backward pass
@@ -257,7 +281,7 @@ class _FusedDecode(torch.autograd.Function):
                 ups = [u if u is not None else z(*s) for u, s in zip(ups[:5], ((M, 3), (M, 3), (M, 1), (M, 3), (M, 4)))] + [ups[5]]
             stream = _lib.raw_stream(dev)
             with _lib.on_device(dev):
-                bws = _lib.empty_u8(L.splatco_decode_bwd_ws_bytes(V, cfg.rc, cfg.level), dev)
+                bws = _lib.empty_u8(L.splatco_decode_bwd_ws_bytes(ctx.V_rows, cfg.rc, cfg.level), dev)
                 with stage("decode_bwd"):
                     check(L.splatco_decode_bwd(C.byref(desc), _p(ctx.ws), _p(bws), M, *[_p(u) for u in ups],
                                                gd, stream), "splatco_decode_bwd")
@@ -511,7 +535,10 @@ def _plan_for(pc, feat, level, heads) -> _ModelPlan:
     return plan
 
 
-def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
+_v_last = {}        # id(model) -> visible-anchor count of its last view (sizing heuristics only)
+
+
+def collect_model(pc, viewpoint_camera, visible_mask, update_running=True, defer_count=False):
     """Read the reference model's attributes (duck-typed GaussianModel) into
     (cfg, differentiable inputs)."""
     if getattr(pc, "use_feat_bank", False):
@@ -551,16 +578,27 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
     att = _ta_cache_for(plan.levels[0][0]).get(tuple(params[0:3]), tuple(_par(m, "weight") for m in plan.ta_weights))
     # the visible-anchor list LAST: everything above is independent of it and overlaps with the GPU finishing the
     # prefilter (and whatever was queued before it); prefilter_voxel already compacted the indices on the device
+    cfg.pending = None
     if visible_mask is None:
         cfg.vis_idx = torch.arange(cfg.N, dtype=torch.int32, device=dev)
+        v_est = cfg.N
     else:
-        from .diff_gaussian_rasterization import take_compaction
-        got = take_compaction(visible_mask)
-        cfg.vis_idx = got[0] if got is not None else torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
+        from .diff_gaussian_rasterization import pending_compaction, take_compaction
+        cp = pending_compaction(visible_mask) if defer_count else None
+        if cp is not None:
+            # render() path on the two-stage decode: the visible-anchor COUNT stays on the device (desc.V_dev), the decode
+            # is queued on N-row buffers, and the host learns V together with M and R at the ONE sync of the view
+            cfg.pending = cp
+            cfg.vis_idx = cp.idx
+            v_est = _v_last.get(id(plan), (3 * cfg.N) // 4)
+        else:
+            got = take_compaction(visible_mask)
+            cfg.vis_idx = got[0] if got is not None else torch.nonzero(visible_mask).squeeze(1).to(torch.int32)
+            v_est = int(cfg.vis_idx.shape[0])
     # channel-last copies of every sampled plane (direct planes of the active levels + the attended ones)
     nper = len(PER_LEVEL)
     planes = [params[l * nper + q] for l in range(level + 1) for q in range(3)] + list(att)
-    packed = _pack_cache_for(plan.levels[0][0]).get(planes, int(cfg.vis_idx.shape[0]))
+    packed = _pack_cache_for(plan.levels[0][0]).get(planes, v_est)
     cfg.packed = packed is not None
     if cfg.packed:
         for l in range(level + 1):
@@ -573,6 +611,8 @@ def collect_model(pc, viewpoint_camera, visible_mask, update_running=True):
 
 
 _noise_calls = 0
+# SPLATCO_DEFER_COUNT=0: wait for the prefilter's count before the decode is queued (the round-1 order; A/B timing)
+DEFER_COUNT = _os.environ.get("SPLATCO_DEFER_COUNT", "1") != "0"
 
 
 def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_training=False, _raster_settings=None,
@@ -583,7 +623,10 @@ def generate_neural_gaussians(viewpoint_camera, pc, visible_mask=None, is_traini
     # the per-anchor inputs first (pc.get_scaling launches two kernels): collect_model ends by waiting for the
     # prefilter's visible-anchor count, and everything queued before that wait overlaps with the GPU's backlog
     scaling_in = _scaling if _scaling is not None else pc.get_scaling
-    cfg, att, app_vec, params = collect_model(pc, viewpoint_camera, visible_mask)
+    # (an explicit noise tensor -- tests -- is [V, ncol]: it needs V on the host first)
+    defer = (_raster_settings is not None and DEFER_COUNT and getattr(pc.feat_planes, "_splatco_noise", None) is None
+             and _register().splatco_decode_get_impl() == 2)
+    cfg, att, app_vec, params = collect_model(pc, viewpoint_camera, visible_mask, defer_count=defer)
     cfg.raster = _raster_settings
     # GaussianLearner.inference always passes Q = self.Q0 (0.03 while training, 0 in render.py):
     # U(-.5,.5)*Q is added to the plane features of the non-TA levels (scene/grids.py:159-164)

@@ -378,7 +378,7 @@ class GaussianRasterizer(nn.Module):
 
 # ---- prefilter with the index list render() needs next -------------------------------------------------------
 class _Compaction:
-    __slots__ = ("mask", "version", "idx", "counter", "event")
+    __slots__ = ("mask", "version", "idx", "counter", "event", "ws", "count_ptr")
 
 
 def visible_mask_compact(means3D, scales, rotations, raster_settings):
@@ -411,11 +411,28 @@ def visible_mask_compact(means3D, scales, rotations, raster_settings):
                                                    _stream_ptr(dev)), "splatco_visible_filter_compact")
             cp.event = torch.cuda.Event()
             cp.event.record(torch.cuda.current_stream(dev))
+            cp.ws = ws                                       # holds the device-side count (cp.count_ptr)
+            cp.count_ptr = L.splatco_visible_compact_count_ptr(ptr(ws), N)
         _debug_sync(rs, "visible_filter")
         cp.mask = mask_u8.view(torch.bool)
         cp.version = cp.mask._version
         _spec_slot.compaction = cp
         return cp.mask
+
+
+def pending_compaction(visible_mask):
+    """The pending compaction record of `visible_mask` WITHOUT waiting for it: `.idx` (int32 [N], the first V entries
+    valid once the filter has run), `.count_ptr` (device address of V), `.counter` / `.event` (the pinned read-back).
+    The decode queues itself on these and reads V after its own sync.  None if the mask is not the last prefilter's."""
+    cp = getattr(_spec_slot, "compaction", None)
+    if cp is None or cp.mask is not visible_mask or visible_mask._version != cp.version:
+        return None
+    return cp
+
+
+def clear_compaction(cp):
+    if getattr(_spec_slot, "compaction", None) is cp:
+        _spec_slot.compaction = None
 
 
 def take_compaction(visible_mask):
