@@ -133,3 +133,38 @@ def test_eval_mode_render_matches_training_forward():
     pc.train()
     assert set(pkg) == {"render", "viewspace_points", "visibility_filter", "radii"}
     assert torch.equal(pkg["render"], img_train)
+
+
+def test_deferred_visible_count_equals_waiting_for_it():
+    """Round 2: render() queues the decode on N-row buffers with the visible-anchor count still on the device
+    (splatco_decode_desc::V_dev) and learns V, M and R at one sync.  Everything the view produces -- image, per-Gaussian
+    outputs, BatchNorm running statistics, every parameter gradient -- must equal the path that waits for V first."""
+    from splatco_b200 import decode as dec
+    from splatco_b200.gaussian_renderer import prefilter_voxel, render
+    W, H = 200, 144
+    cam = _cams(W, H)[1]
+    bg = torch.ones(3, device="cuda")
+    results = []
+    for defer in (True, False):
+        pc = _model(seed=11)
+        old = dec.DEFER_COUNT
+        dec.DEFER_COUNT = defer
+        try:
+            vm = prefilter_voxel(cam, pc, PIPE, bg)
+            pkg = render(cam, pc, PIPE, bg, visible_mask=vm, retain_grad=True)
+            (pkg["render"].square().mean() + 0.1 * pkg["scaling"].sum() + pkg["neural_opacity"].sum()).backward()
+        finally:
+            dec.DEFER_COUNT = old
+        grads = {n: p.grad.detach().clone() for n, p in zip(range(10 ** 6), pc.parameters()) if p.grad is not None}
+        stats = {k: v.detach().clone() for k, v in pc.feat_planes._feat.state_dict().items() if "running" in k or "num_batches" in k}
+        results.append((pkg, grads, stats))
+    (a, ga, sa), (b, gb, sb) = results
+    for k in ("render", "radii", "selection_mask", "neural_opacity", "scaling", "visibility_filter"):
+        assert torch.equal(a[k], b[k]), k
+    assert sa.keys() == sb.keys() and len(sa) >= 6
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert ga.keys() == gb.keys() and len(ga) > 20
+    for k in ga:
+        # (atomic accumulation order differs from run to run: equal to rounding)
+        assert (ga[k] - gb[k]).abs().max().item() <= 1e-5 * max(gb[k].abs().max().item(), 1e-20), k
