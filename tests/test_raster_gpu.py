@@ -313,3 +313,51 @@ def test_upstream_structure_comparator_matches_product_and_oracle():
     prod = run(L.splatco_blend_bwd)
     for name, a, b in zip(("mean2D", "conic", "opacity", "colour"), up, prod):
         assert rel_err(a, b) < 2e-3, name
+
+
+@pytest.mark.parametrize("W,H,M,sigma", [(250, 131, 40_000, (0.3, 12.0)), (64, 48, 3_000, (4.0, 60.0)), (333, 200, 150_000, (0.2, 1.5))])
+def test_blend_implementations_agree_on_hard_splat_mixes(W, H, M, sigma):
+    """The round-2 blend kernels against the round-1 ones on the SAME binned state: the per-pixel candidate lists of
+    blend_fwd2 are only a filter in front of an unchanged evaluation, so image, final_T and n_contrib must be identical
+    bit for bit -- on image sizes that are not multiples of the tile, splats from sub-pixel to screen-filling, needle-shaped
+    conics and opacities straddling 1/255; the matrix-form reduction of blend_bwd2 must reproduce the nine sums of the
+    transposition-buffer kernel to rounding."""
+    from splatco_b200 import _lib
+    from splatco_b200._lib import check, ptr
+    cam, means, colors, opac, scales, rots = scene(M, W, H, 17, sigma_px=sigma)
+    g = torch.Generator().manual_seed(5)
+    scales = scales * torch.exp(1.5 * torch.randn(scales.shape, generator=g))          # strongly anisotropic (needles)
+    opac = opac.clone()
+    opac[::7] = 1.0 / 255.0 * (0.5 + torch.rand(opac[::7].shape, generator=g))           # around the alpha cut
+    opac[3::11] = 0.999
+    color, radii, state, st = gpu_forward(cam, means, colors, opac, scales, rots, [0.1, 0.3, 0.9])
+    L = _lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    bg = torch.tensor([0.1, 0.3, 0.9], device="cuda")
+    P, R = state.P, state.RL
+    assert R > 0
+    try:
+        outs = []
+        for impl in (1, 2):
+            check(L.splatco_blend_set_impl(impl, 0), "set_impl")
+            img = torch.empty(3, H, W, device="cuda")
+            check(L.splatco_blend_fwd(R, H, W, ptr(bg), ptr(state.geom), ptr(state.binning), ptr(state.image), ptr(img), stream), "blend_fwd")
+            torch.cuda.synchronize()
+            u = unpack_state(state)
+            outs.append((img.clone(), u["final_T"].copy(), u["n_contrib"].copy()))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32)) and np.array_equal(outs[0][2], outs[1][2])
+        dL = torch.randn(3, H, W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) / (3 * H * W)
+        grads = []
+        for impl in (1, 2, 3):
+            check(L.splatco_blend_set_impl(0, impl), "set_impl")
+            gs = [torch.zeros(P, c, device="cuda") for c in (3, 3, 1, 3)]
+            check(L.splatco_blend_bwd(P, R, H, W, ptr(bg), ptr(state.geom), ptr(state.binning), ptr(state.image), ptr(dL),
+                                      *[ptr(t) for t in gs], stream), "blend_bwd")
+            torch.cuda.synchronize()
+            grads.append([t.double().cpu().numpy() for t in gs])
+        for impl_g in grads[1:]:
+            for name, a, b in zip(("mean2D", "conic", "opacity", "color"), impl_g, grads[0]):
+                assert rel_err(a, b) < 5e-4, (name, rel_err(a, b))      # fp32 sums in different orders (atomics)
+    finally:
+        check(L.splatco_blend_set_impl(2, 2), "set_impl")
