@@ -28,68 +28,113 @@ static LossWindow make_window() {
     return w;
 }
 
+// Tiles of 32 x 16 pixels, 256 threads.  The first version (16 x 16 tiles, one tap = one 4-byte shared-memory load) was bound
+// by the shared-memory pipe (ncu: LSU 48 %, mio_throttle the top stall, 5.5 M bank conflicts).  Here the horizontal pass
+// gives each thread FOUR adjacent output columns of a row: it fetches the 14 (16) inputs they share with 16-byte loads
+// (a quarter warp reads 128 contiguous bytes: conflict-free) and the vertical pass gives each thread two vertically
+// adjacent pixels (12 loads for 2 x 11 taps); the rows of the intermediate maps are padded to 33 floats.
+constexpr int LT_W = 32, LT_H = 16, LT_RW = LT_W + 2 * LS_R + 2 /*44: 16-byte rows*/, LT_RH = LT_H + 2 * LS_R /*26*/;
+constexpr int LT_ITEMS = LT_RH * (LT_W / 4);           // 208 (row, group of 4 columns) items of the horizontal pass
+
 // sums[0] += sum |x - y|, sums[1] += sum ssim_map   (fp64 accumulators: the means are over ~1.6 M terms)
-__global__ void __launch_bounds__(LS_T * LS_T)
+__global__ void __launch_bounds__(256)
 l1_ssim_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossWindow win,
                    float *__restrict__ d_mu1, float *__restrict__ d_exx, float *__restrict__ d_exy,
                    double *__restrict__ sums, double count, float lambda, float *__restrict__ out) {
-    __shared__ float s_x[LS_REG][LS_REG + 1], s_y[LS_REG][LS_REG + 1];
-    __shared__ float s_h[5][LS_REG][LS_T + 1];          // horizontally filtered x, y, xx, yy, xy
-    __shared__ float s_red[2][LS_T * LS_T / 32];
+    __shared__ __align__(16) float s_x[LT_RH][LT_RW], s_y[LT_RH][LT_RW];
+    __shared__ float s_h[5][LT_RH][LT_W + 1];           // horizontally filtered x, y, xx, yy, xy
+    __shared__ float s_red[2][8];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * LS_T, y0 = blockIdx.y * LS_T;
+    const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    for (int r = tid; r < LS_REG * LS_REG; r += LS_T * LS_T) {
-        const int ry = r / LS_REG, rx = r - ry * LS_REG;
+    for (int r = tid; r < LT_RH * LT_RW; r += 256) {
+        const int ry = r / LT_RW, rx = r - ry * LT_RW;
         const int gy = y0 + ry - LS_R, gx = x0 + rx - LS_R;
         float a = 0.f, b = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) { a = __ldg(img + plane + (size_t)gy * W + gx); b = __ldg(gt + plane + (size_t)gy * W + gx); }
         s_x[ry][rx] = a; s_y[ry][rx] = b;
     }
     __syncthreads();
-    for (int r = tid; r < LS_REG * LS_T; r += LS_T * LS_T) {
-        const int ry = r / LS_T, cx = r - ry * LS_T;
-        float hx = 0.f, hy = 0.f, hxx = 0.f, hyy = 0.f, hxy = 0.f;
+    if (tid < LT_ITEMS) {
+        const int ry = tid >> 3, cx0 = (tid & 7) * 4;
+        const float4 *px = reinterpret_cast<const float4 *>(&s_x[ry][cx0]), *py = reinterpret_cast<const float4 *>(&s_y[ry][cx0]);
+        const float4 a0 = px[0], a1 = px[1], a2 = px[2], a3 = px[3], b0 = py[0], b1 = py[1], b2 = py[2], b3 = py[3];
+        const float xs[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+        const float ys[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+        float acc[4][5];
 #pragma unroll
-        for (int k = 0; k < LS_K; ++k) {
-            const float a = s_x[ry][cx + k], b = s_y[ry][cx + k], g = win.g[k];
-            hx = fmaf(g, a, hx); hy = fmaf(g, b, hy);
-            hxx = fmaf(g, a * a, hxx); hyy = fmaf(g, b * b, hyy); hxy = fmaf(g, a * b, hxy);
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) acc[o][m] = 0.f;
+#pragma unroll
+        for (int p = 0; p < LS_K + 3; ++p) {
+            const float a = xs[p], b = ys[p], aa = a * a, bb = b * b, ab = a * b;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int k = p - o;
+                if (k >= 0 && k < LS_K) {
+                    const float g = win.g[k];
+                    acc[o][0] = fmaf(g, a, acc[o][0]); acc[o][1] = fmaf(g, b, acc[o][1]);
+                    acc[o][2] = fmaf(g, aa, acc[o][2]); acc[o][3] = fmaf(g, bb, acc[o][3]); acc[o][4] = fmaf(g, ab, acc[o][4]);
+                }
+            }
         }
-        s_h[0][ry][cx] = hx; s_h[1][ry][cx] = hy; s_h[2][ry][cx] = hxx; s_h[3][ry][cx] = hyy; s_h[4][ry][cx] = hxy;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) s_h[m][ry][cx0 + o] = acc[o][m];
     }
     __syncthreads();
-    const int ly = tid / LS_T, lx = tid - ly * LS_T;
-    const int gy = y0 + ly, gx = x0 + lx;
-    float l1 = 0.f, m = 0.f;
-    if (gy < H && gx < W) {
-        float mu1 = 0.f, mu2 = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+    const int lx = tid & 31, ly0 = (tid >> 5) * 2;
+    const int gx = x0 + lx;
+    float v[2][5];
 #pragma unroll
-        for (int k = 0; k < LS_K; ++k) {
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int m = 0; m < 5; ++m) v[q][m] = 0.f;
+#pragma unroll
+    for (int k = 0; k < LS_K + 1; ++k) {
+        float h[5];
+#pragma unroll
+        for (int m = 0; m < 5; ++m) h[m] = s_h[m][ly0 + k][lx];
+        if (k < LS_K) {
             const float g = win.g[k];
-            mu1 = fmaf(g, s_h[0][ly + k][lx], mu1); mu2 = fmaf(g, s_h[1][ly + k][lx], mu2);
-            exx = fmaf(g, s_h[2][ly + k][lx], exx); eyy = fmaf(g, s_h[3][ly + k][lx], eyy);
-            exy = fmaf(g, s_h[4][ly + k][lx], exy);
+#pragma unroll
+            for (int m = 0; m < 5; ++m) v[0][m] = fmaf(g, h[m], v[0][m]);
         }
-        const float s1 = exx - mu1 * mu1, s2 = eyy - mu2 * mu2, s12 = exy - mu1 * mu2;
-        const float A = 2.f * mu1 * mu2 + LS_C1, B = 2.f * s12 + LS_C2;
-        const float Cc = mu1 * mu1 + mu2 * mu2 + LS_C1, D = s1 + s2 + LS_C2;
-        const float inv = 1.f / (Cc * D);
-        m = A * B * inv;
-        // partial derivatives of m with E[x], E[x^2], E[xy] as the independent variables
-        const size_t o = plane + (size_t)gy * W + gx;
-        d_mu1[o] = 2.f * mu2 * (B - A) * inv - m * 2.f * mu1 * (D - Cc) * inv;
-        d_exx[o] = -m / D;
-        d_exy[o] = 2.f * A * inv;
-        l1 = fabsf(s_x[ly + LS_R][lx + LS_R] - s_y[ly + LS_R][lx + LS_R]);
+        if (k >= 1) {
+            const float g = win.g[k - 1];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) v[1][m] = fmaf(g, h[m], v[1][m]);
+        }
+    }
+    float l1 = 0.f, msum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int gy = y0 + ly0 + q;
+        if (gy < H && gx < W) {
+            const float mu1 = v[q][0], mu2 = v[q][1], exx = v[q][2], eyy = v[q][3], exy = v[q][4];
+            const float s1 = exx - mu1 * mu1, s2 = eyy - mu2 * mu2, s12 = exy - mu1 * mu2;
+            const float A = 2.f * mu1 * mu2 + LS_C1, B = 2.f * s12 + LS_C2;
+            const float Cc = mu1 * mu1 + mu2 * mu2 + LS_C1, D = s1 + s2 + LS_C2;
+            const float inv = 1.f / (Cc * D);
+            const float m = A * B * inv;
+            // partial derivatives of m with E[x], E[x^2], E[xy] as the independent variables
+            const size_t o = plane + (size_t)gy * W + gx;
+            d_mu1[o] = 2.f * mu2 * (B - A) * inv - m * 2.f * mu1 * (D - Cc) * inv;
+            d_exx[o] = -m / D;
+            d_exy[o] = 2.f * A * inv;
+            msum += m;
+            l1 += fabsf(s_x[ly0 + q + LS_R][lx + LS_R] - s_y[ly0 + q + LS_R][lx + LS_R]);
+        }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { l1 += __shfl_xor_sync(0xffffffffu, l1, d); m += __shfl_xor_sync(0xffffffffu, m, d); }
-    if ((tid & 31) == 0) { s_red[0][tid >> 5] = l1; s_red[1][tid >> 5] = m; }
+    for (int d = 16; d > 0; d >>= 1) { l1 += __shfl_xor_sync(0xffffffffu, l1, d); msum += __shfl_xor_sync(0xffffffffu, msum, d); }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = l1; s_red[1][tid >> 5] = msum; }
     __syncthreads();
     if (tid < 2) {
         double s = 0.0;
-        for (int w = 0; w < LS_T * LS_T / 32; ++w) s += (double)s_red[tid][w];
+        for (int w = 0; w < 8; ++w) s += (double)s_red[tid][w];
         atomicAdd(&sums[tid], s);
         __threadfence();
     }
@@ -100,26 +145,26 @@ l1_ssim_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
         const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
         if (atomicAdd(ticket, 1u) == total - 1) {
             __threadfence();
-            const double l1 = __ldcg(sums) / count, ss = __ldcg(sums + 1) / count;
-            out[0] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ss));
-            out[1] = (float)l1;
+            const double l1m = __ldcg(sums) / count, ss = __ldcg(sums + 1) / count;
+            out[0] = (float)((1.0 - (double)lambda) * l1m + (double)lambda * (1.0 - ss));
+            out[1] = (float)l1m;
             out[2] = (float)ss;
         }
     }
 }
 
 // dL/dimg = g_loss * [ (1 - lambda) sign(x - y) / count  -  lambda / count * (conv(d_mu1) + 2 x conv(d_exx) + y conv(d_exy)) ]
-__global__ void __launch_bounds__(LS_T * LS_T)
+__global__ void __launch_bounds__(256)
 l1_ssim_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__restrict__ gt, LossWindow win,
                    const float *__restrict__ d_mu1, const float *__restrict__ d_exx, const float *__restrict__ d_exy,
                    const float *__restrict__ g_loss, float c_l1, float c_ssim, float *__restrict__ dimg) {
-    __shared__ float s_m[3][LS_REG][LS_REG + 1];
-    __shared__ float s_h[3][LS_REG][LS_T + 1];
+    __shared__ __align__(16) float s_m[3][LT_RH][LT_RW];
+    __shared__ float s_h[3][LT_RH][LT_W + 1];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * LS_T, y0 = blockIdx.y * LS_T;
+    const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
     const size_t plane = (size_t)blockIdx.z * H * W;
-    for (int r = tid; r < LS_REG * LS_REG; r += LS_T * LS_T) {
-        const int ry = r / LS_REG, rx = r - ry * LS_REG;
+    for (int r = tid; r < LT_RH * LT_RW; r += 256) {
+        const int ry = r / LT_RW, rx = r - ry * LT_RW;
         const int gy = y0 + ry - LS_R, gx = x0 + rx - LS_R;
         float a = 0.f, b = 0.f, c = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
@@ -129,32 +174,59 @@ l1_ssim_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
         s_m[0][ry][rx] = a; s_m[1][ry][rx] = b; s_m[2][ry][rx] = c;
     }
     __syncthreads();
-    for (int r = tid; r < LS_REG * LS_T; r += LS_T * LS_T) {
-        const int ry = r / LS_T, cx = r - ry * LS_T;
-        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+    if (tid < LT_ITEMS) {
+        const int ry = tid >> 3, cx0 = (tid & 7) * 4;
 #pragma unroll
-        for (int k = 0; k < LS_K; ++k) {
-            const float g = win.g[k];
-            h0 = fmaf(g, s_m[0][ry][cx + k], h0); h1 = fmaf(g, s_m[1][ry][cx + k], h1); h2 = fmaf(g, s_m[2][ry][cx + k], h2);
+        for (int m = 0; m < 3; ++m) {
+            const float4 *pm = reinterpret_cast<const float4 *>(&s_m[m][ry][cx0]);
+            const float4 a0 = pm[0], a1 = pm[1], a2 = pm[2], a3 = pm[3];
+            const float xs[16] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < LS_K + 3; ++p)
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int k = p - o;
+                    if (k >= 0 && k < LS_K) acc[o] = fmaf(win.g[k], xs[p], acc[o]);
+                }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) s_h[m][ry][cx0 + o] = acc[o];
         }
-        s_h[0][ry][cx] = h0; s_h[1][ry][cx] = h1; s_h[2][ry][cx] = h2;
     }
     __syncthreads();
-    const int ly = tid / LS_T, lx = tid - ly * LS_T;
-    const int gy = y0 + ly, gx = x0 + lx;
-    if (gy >= H || gx >= W) return;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+    const int lx = tid & 31, ly0 = (tid >> 5) * 2;
+    const int gx = x0 + lx;
+    float v[2][3];
 #pragma unroll
-    for (int k = 0; k < LS_K; ++k) {
-        const float g = win.g[k];
-        v0 = fmaf(g, s_h[0][ly + k][lx], v0); v1 = fmaf(g, s_h[1][ly + k][lx], v1); v2 = fmaf(g, s_h[2][ly + k][lx], v2);
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) v[q][m] = 0.f;
+#pragma unroll
+    for (int k = 0; k < LS_K + 1; ++k) {
+        float h[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) h[m] = s_h[m][ly0 + k][lx];
+        if (k < LS_K) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) v[0][m] = fmaf(win.g[k], h[m], v[0][m]);
+        }
+        if (k >= 1) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) v[1][m] = fmaf(win.g[k - 1], h[m], v[1][m]);
+        }
     }
-    const size_t o = plane + (size_t)gy * W + gx;
-    const float x = __ldg(img + o), y = __ldg(gt + o);
-    const float dssim = v0 + 2.f * x * v1 + y * v2;
-    const float d = x - y;
-    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    dimg[o] = __ldg(g_loss) * (c_l1 * sgn - c_ssim * dssim);
+    const float gl = __ldg(g_loss);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int gy = y0 + ly0 + q;
+        if (gy >= H || gx >= W) continue;
+        const size_t o = plane + (size_t)gy * W + gx;
+        const float x = __ldg(img + o), y = __ldg(gt + o);
+        const float dssim = v[q][0] + 2.f * x * v[q][1] + y * v[q][2];
+        const float d = x - y;
+        const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        dimg[o] = gl * (c_l1 * sgn - c_ssim * dssim);
+    }
 }
 
 
@@ -341,8 +413,8 @@ extern "C" int splatco_l1_ssim_fwd(int C, int H, int W, const float *img, const 
     double *sums = (double *)(b + 3 * map);
     SPLATCO_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(double), st));          // two sums + the finish ticket
     static const LossWindow win = make_window();
-    const dim3 grid(ceil_div(W, LS_T), ceil_div(H, LS_T), C);
-    l1_ssim_fwd_kernel<<<grid, LS_T * LS_T, 0, st>>>(H, W, img, gt, win, (float *)b, (float *)(b + map), (float *)(b + 2 * map), sums,
+    const dim3 grid(ceil_div(W, LT_W), ceil_div(H, LT_H), C);
+    l1_ssim_fwd_kernel<<<grid, 256, 0, st>>>(H, W, img, gt, win, (float *)b, (float *)(b + map), (float *)(b + 2 * map), sums,
                                                      (double)C * H * W, lambda_dssim, out3);
     SPLATCO_CHECK_LAUNCH();
     return 0;
@@ -356,8 +428,8 @@ extern "C" int splatco_l1_ssim_bwd(int C, int H, int W, const float *img, const 
     const char *b = (const char *)ws;
     static const LossWindow win = make_window();
     const float count = (float)((double)C * H * W);
-    const dim3 grid(ceil_div(W, LS_T), ceil_div(H, LS_T), C);
-    l1_ssim_bwd_kernel<<<grid, LS_T * LS_T, 0, (cudaStream_t)stream>>>(H, W, img, gt, win, (const float *)b, (const float *)(b + map),
+    const dim3 grid(ceil_div(W, LT_W), ceil_div(H, LT_H), C);
+    l1_ssim_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(H, W, img, gt, win, (const float *)b, (const float *)(b + map),
                                                                       (const float *)(b + 2 * map), grad_loss,
                                                                       (1.f - lambda_dssim) / count, lambda_dssim / count, dL_dimg);
     SPLATCO_CHECK_LAUNCH();

@@ -243,6 +243,7 @@ class _FusedDecode(torch.autograd.Function):
         # the forward input OBJECTS: their identity keys the shared gradient buffers of a backward pass
         ctx.origs = (anchor_feat, anchor, offset, scaling, att_xy, att_xz, att_yz, app_vec) + tuple(params)
         ctx.mark_non_differentiable(mask)
+        ctx.set_materialize_grads(False)          # unused outputs (neural_opacity, the mask) get no zero-filled gradients
         return xyz, color, opacity, scl, rot, nopac, mask
 
     @staticmethod

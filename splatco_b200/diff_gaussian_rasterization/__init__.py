@@ -311,10 +311,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.state = st
         ctx.save_for_backward(means3D, scales, rotations)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)          # no zero-filled gradient tensor for `radii`
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
+        if grad_out_color is None:
+            return (None,) * 9
         means3D, scales, rotations = ctx.saved_tensors
         g = rasterize_backward_state(ctx.state, grad_out_color, means3D, scales, rotations, ctx.raster_settings)
         # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings)

@@ -102,12 +102,9 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
             _scaling=_get_scaling(pc, remember=False))
 
     # zero tensor whose .grad receives the 2D (screen-space) mean gradients (reference :133-138)
-    screenspace_points = torch.zeros_like(xyz, dtype=pc.get_anchor.dtype, requires_grad=True, device="cuda") + 0
-    if retain_grad:
-        try:
-            screenspace_points.retain_grad()
-        except Exception:
-            pass
+    # (the reference adds `+ 0` to make it a non-leaf and calls retain_grad(); a leaf holds the same .grad after backward
+    # without the extra add kernel in the forward and the gradient copy in the backward)
+    screenspace_points = torch.zeros_like(xyz, dtype=pc.get_anchor.dtype, requires_grad=True, device="cuda")
 
     rasterizer = GaussianRasterizer(raster_settings=settings)
     rendered_image, radii = rasterizer(
