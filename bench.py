@@ -211,7 +211,7 @@ class Workload:
         self.info["M"], self.info["V"] = float(np.mean(Ms)), float(np.mean(Vs))
         return float(total.item()) if host_inputs else total
 
-    def timed(self, fn, n, host_inputs):
+    def timed(self, fn, n, host_inputs, tag=None):
         import torch.distributed as dist
         # the cyclic collector is paused inside the timed region (a generation-2 pass over the autograd graphs of a
         # step costs tens of ms and lands on a random step); per-step host times are kept as a diagnostic
@@ -233,16 +233,21 @@ class Workload:
         gc.enable()
         d = sorted((b - a) * 1e3 for a, b in zip(ts[:-1], ts[1:]))
         gd = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
-        self.host_ms[getattr(fn, "__name__", "fn") + ("_host_inputs" if host_inputs else "")] = {
+        tag = tag or (getattr(fn, "__name__", "fn") + ("_host_inputs" if host_inputs else ""))
+        self.host_ms[tag] = {
             "host_median": round(d[len(d) // 2], 3), "host_max": round(d[-1], 3),
             "gpu_median": round(gd[len(gd) // 2], 3), "gpu_max": round(gd[-1], 3)}
         if self.world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
         if self.world > 1:
-            t = torch.tensor([ms], device=self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            # diagnostic: every rank's own total and slowest step (the reported time is the max over ranks)
+            mine = torch.tensor([ms, gd[-1], gd[len(gd) // 2]], device=self.device)
+            allr = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(allr, mine)
+            self.host_ms[tag]["per_rank"] = [
+                {"total_ms": round(float(a[0]), 2), "gpu_max": round(float(a[1]), 2), "gpu_median": round(float(a[2]), 2)} for a in allr]
+            ms = max(float(a[0]) for a in allr)
         return ms
 
     def instance_counts(self):
@@ -571,7 +576,7 @@ def run_ours(args):
     # of the decode are bracketed by events inside the library in the same pass.
     L.splatco_decode_profile(1)
     with profiling.collect() as prof:
-        ms_stage = w.timed(w.step, args.steps, False)
+        ms_stage = w.timed(w.step, args.steps, False, tag="stage_pass")
     stage_sum = prof.summary()
     mlp_ms = None
     if L.splatco_decode_get_impl() == 2:
