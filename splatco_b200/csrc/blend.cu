@@ -2,23 +2,22 @@
 // [SURVEY.md Appendix A.4, A.5; reference call site gaussian_renderer/__init__.py:163-171 and the
 // autograd backward triggered at train.py:240].
 //
-// One CTA per 16x16 tile, one thread per pixel; warps cover 8x4-pixel patches.  ncu showed the first
-// version of these kernels to be instruction-issue bound (81 % issue-active, DRAM < 1 % of peak), so
-// the design goal is the fewest instructions per (pixel, splat) pair:
+// One CTA per 16x16 tile, one thread per pixel; warps cover 8x4-pixel patches.  ncu showed these kernels to be
+// instruction-issue bound from the first version on (81 % issue-active, DRAM < 1 % of peak), so the design goal is
+// the fewest instructions per LIVE (pixel, splat) pair.  Common to every kernel here:
 //  * splats are staged through shared memory in batches of 512 (two per thread); the staging thread precomputes, once
 //    per (tile, splat), the conic pre-scaled into the log2 domain (P2 = log2(e) * power, evaluated from
 //    (dx, dy) exactly like the reference so threshold decisions keep full fp32 precision) and
 //    log2(opacity), which is folded into the exponent so the alpha >= 1/255 cut is a compare BEFORE the
 //    ex2 (culled pairs never touch the SFU);
-//  * the staging thread also intersects the splat's alpha >= 1/255 bounding box with the 8 warp
-//    patches; ballots turn that into one 32-bit word per (warp, 32 splats) and each warp walks only the
-//    set bits, in list order — semantics per pixel are unchanged (a culled splat has alpha < 1/255 on
-//    every pixel of the patch and would have been skipped);
-//  * a warp leaves as soon as all its pixels are saturated, the CTA when every warp has.
-// Backward: same staging / culling / skip decisions (bit-identical exponent).  Per (pixel, splat) the lanes form the
-// six moments of D = dL/dG * G about the splat centre and three colour terms; each warp parks the 9 partials of a visit
-// column-wise in its own shared-memory transposition buffer and, every third visit, sums the 27 rows with 16-byte
-// loads and issues ONE global RED per sum -- 32x fewer global atomics than per-pixel atomics, no shuffle butterfly.
+//  * a warp leaves as soon as all its pixels are saturated, the CTA when every warp has; CTAs run longest tile first.
+// Two generations are kept behind splatco_blend_set_impl (A/B timing; the tests compare them):
+//  round 1  blend_fwd_kernel / blend_bwd_kernel: the splat's alpha >= 1/255 bounding box against the 8 patches -> one
+//           mask word per (warp, 32 splats); warps walk their set bits in list order, one splat per warp step.  The
+//           backward forms nine partial sums per visit and reduces them through a per-warp transposition buffer.
+//  round 2  blend_fwd2_kernel (per-row alpha >= 1/255 spans -> per-PIXEL candidate bit lists; every lane walks its own
+//           list) and blend_bwd2_kernel (same walk as round 1, two parked values per visit and a matrix-form reduction
+//           with constant weights).  The defaults; see the comments at the kernels.
 #include "common.cuh"
 #include <stdlib.h>
 
