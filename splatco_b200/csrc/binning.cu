@@ -363,6 +363,13 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
     const int2 rg = ranges[tile];
     const uint32_t n = (uint32_t)(rg.y - rg.x);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // The lowest depth byte is left out of the radix passes: after the passes on bytes 1..3 only keys that agree in their
+    // top 24 bits can still be out of order -- a handful per tile (2048 depths spread over >= 2^20 values) -- and the
+    // run-fixing step below orders those by (full key, id).  A tile whose depths collide massively in the top 24 bits
+    // is sorted again with all four passes.
+    int first_pass = n >= 64u ? 1 : 0;
+    uint32_t *key, *val;
+  for (;;) {
     uint32_t k_or = 0u, k_and = 0xffffffffu;
     for (uint32_t i = tid; i < n; i += NT) {
         const uint64_t e = entries[rg.x + i];
@@ -383,7 +390,7 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
     int cur = 0;
     const uint32_t wbase = warp * 32 * ITEMS;
 #pragma unroll 1
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = first_pass; pass < 4; ++pass) {
         const int shift = 8 * pass;
         if (((varying >> shift) & 255u) == 0u) continue;       // uniform across the CTA
         __syncthreads();                                       // the previous scatter (or the load) is complete
@@ -443,21 +450,28 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
         cur ^= 1;
     }
     __syncthreads();
-    // equal-depth runs (rare): order by Gaussian id; the thread at the head of a run sorts it
-    uint32_t *key = s_dyn + cur * 2 * CAP, *val = key + CAP;
+    // runs of keys that agree above the bits the passes covered (equal depths, or equal top 24 bits when the low byte was
+    // left out): order by (key, Gaussian id); the thread at the head of a run sorts it
+    key = s_dyn + cur * 2 * CAP; val = key + CAP;
+    const int cs = 8 * first_pass;
+    int bad = 0;
     for (uint32_t i = tid; i + 1 < n; i += NT) {
-        if (key[i] == key[i + 1] && (i == 0 || key[i - 1] != key[i])) {
+        const uint32_t ki = key[i] >> cs;
+        if (ki == (key[i + 1] >> cs) && (i == 0 || (key[i - 1] >> cs) != ki)) {
             uint32_t e = i + 1;
-            while (e + 1 < n && key[e + 1] == key[i]) ++e;
-            for (uint32_t a = i + 1; a <= e; ++a) {            // insertion sort of val[i..e]
-                const uint32_t v = val[a];
+            while (e + 1 < n && (key[e + 1] >> cs) == ki) ++e;
+            if (first_pass && e - i >= 32u) { bad = 1; continue; }
+            for (uint32_t a = i + 1; a <= e; ++a) {            // insertion sort of (key, val)[i..e]
+                const uint32_t kk = key[a], v = val[a];
                 uint32_t b = a;
-                while (b > i && val[b - 1] > v) { val[b] = val[b - 1]; --b; }
-                val[b] = v;
+                while (b > i && (key[b - 1] > kk || (key[b - 1] == kk && val[b - 1] > v))) { key[b] = key[b - 1]; val[b] = val[b - 1]; --b; }
+                key[b] = kk; val[b] = v;
             }
         }
     }
-    __syncthreads();
+    if (!__syncthreads_or(bad)) break;                        // (also orders the run fixing before the copy-out)
+    first_pass = 0;
+  }
     const uint64_t hi = (uint64_t)tile << 32;
     for (uint32_t i = tid; i < n; i += NT) {
         keys_out[rg.x + i] = hi | key[i];

@@ -361,3 +361,38 @@ def test_blend_implementations_agree_on_hard_splat_mixes(W, H, M, sigma):
                 assert rel_err(a, b) < 5e-4, (name, rel_err(a, b))      # fp32 sums in different orders (atomics)
     finally:
         check(L.splatco_blend_set_impl(2, 2), "set_impl")
+
+
+@pytest.mark.parametrize("quantum", [0.25, 2.0 ** -18])
+def test_binning_with_massive_depth_collisions(quantum):
+    """Depths quantised in view space: with quantum 0.25 thousands of Gaussians of a tile share the SAME depth (ties
+    resolved by id), with 2^-18 they agree in the top 24 key bits and differ in the low byte -- the per-tile sort leaves
+    that byte to its run-fixing step and must fall back to all four passes when the runs are long.  Keys, permutation and
+    ranges must still equal the oracle's and the literal radix composition's bit for bit."""
+    from splatco_b200 import _lib
+    from splatco_b200._lib import check, ptr
+    W, H, M = 320, 200, 60_000
+    cam, means, colors, opac, scales, rots = scene(M, W, H, 23, sigma_px=(0.5, 3.0))
+    Wv = cam.world_view_transform.double()
+    pv = torch.cat([means.double(), torch.ones(M, 1, dtype=torch.float64)], dim=1) @ Wv
+    g = torch.Generator().manual_seed(2)
+    zq = torch.round(pv[:, 2] / 0.25) * 0.25
+    if quantum < 0.25:
+        zq = zq + quantum * torch.randint(0, 40, (M,), generator=g).double()      # 40 values inside one 24-bit bucket
+    pv[:, 2] = zq
+    means = (pv @ torch.linalg.inv(Wv))[:, :3].float().contiguous()
+    fw = oracle_forward(cam, means, colors, opac, scales, rots, [0.0, 0.0, 0.0])
+    color, radii, state, _ = gpu_forward(cam, means, colors, opac, scales, rots, [0.0, 0.0, 0.0])
+    g_ = unpack_state(state)
+    bn = fw["bn"]
+    assert state.R == bn.R
+    assert np.array_equal(g_["keys"], bn.keys), "sorted tile|depth keys differ"
+    assert np.array_equal(g_["point_list"], bn.point_list), "sort permutation differs"
+    assert np.array_equal(g_["ranges"], bn.ranges)
+    keys = g_["keys"]
+    same = keys[1:] == keys[:-1]
+    if quantum == 0.25:
+        assert same.mean() > 0.5          # the case really is dominated by ties
+    else:
+        top = (keys >> np.uint64(8))
+        assert (top[1:] == top[:-1]).mean() > 0.5 and same.mean() < 0.5       # long runs that are NOT plain ties
