@@ -91,6 +91,8 @@ class ClockSampler:
         self.index, self.proc, self.path = index, None, None
 
     def start(self):
+        if os.environ.get("SPLATCO_BENCH_NO_SAMPLER") == "1":       # diagnostic: is the poller itself disturbing the run?
+            return
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -223,6 +225,10 @@ class Workload:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ts = [time.perf_counter()]
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+        st0 = torch.cuda.memory_stats(self.device)
+        memhist = os.environ.get("SPLATCO_BENCH_MEMHIST") == "1"        # diagnostic: who asks for new segments in here?
+        if memhist:
+            torch.cuda.memory._record_memory_history(max_entries=200000)
         e0.record()
         for i in range(n):
             fn(host_inputs)
@@ -231,22 +237,41 @@ class Workload:
         e1.record()
         torch.cuda.synchronize()
         gc.enable()
+        st1 = torch.cuda.memory_stats(self.device)
+        if memhist:
+            snap = torch.cuda.memory._snapshot()
+            torch.cuda.memory._record_memory_history(enabled=None)
+            seen = []
+            for tr in snap.get("device_traces", []):
+                for k, ev in enumerate(tr):
+                    if ev.get("action") == "segment_alloc":
+                        # the allocation request that follows the new segment carries the Python stack
+                        nxt = next((e for e in tr[k + 1:k + 4] if e.get("action") == "alloc"), ev)
+                        fr = [f"{os.path.basename(f['filename'])}:{f['line']}:{f['name']}" for f in nxt.get("frames", []) if f["filename"].endswith(".py") and "site-packages" not in f["filename"]][:8]
+                        seen.append({"size_mb": round(ev["size"] / 1e6, 1), "frames": fr})
+            sys.stderr.write(f"[memhist rank {self.rank} {tag or getattr(fn, '__name__', 'fn')}] " + json.dumps(seen) + "\n")
         d = sorted((b - a) * 1e3 for a, b in zip(ts[:-1], ts[1:]))
         gd = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
         tag = tag or (getattr(fn, "__name__", "fn") + ("_host_inputs" if host_inputs else ""))
         self.host_ms[tag] = {
             "host_median": round(d[len(d) // 2], 3), "host_max": round(d[-1], 3),
-            "gpu_median": round(gd[len(gd) // 2], 3), "gpu_max": round(gd[-1], 3)}
+            "gpu_median": round(gd[len(gd) // 2], 3), "gpu_max": round(gd[-1], 3),
+            # cudaMalloc / cudaFree calls of torch's caching allocator inside the timed region (0 / 0 in steady state)
+            "cuda_mallocs": int(st1.get("num_device_alloc", 0) - st0.get("num_device_alloc", 0)),
+            "cuda_frees": int(st1.get("num_device_free", 0) - st0.get("num_device_free", 0)),
+            "reserved_mb_grown": {k: round((st1.get(f"reserved_bytes.{k}.current", 0) - st0.get(f"reserved_bytes.{k}.current", 0)) / 1e6, 1)
+                                  for k in ("large_pool", "small_pool")}}
         if self.world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
         if self.world > 1:
             # diagnostic: every rank's own total and slowest step (the reported time is the max over ranks)
-            mine = torch.tensor([ms, gd[-1], gd[len(gd) // 2]], device=self.device)
+            mine = torch.tensor([ms, gd[-1], gd[len(gd) // 2], float(self.host_ms[tag]["cuda_mallocs"])], device=self.device)
             allr = [torch.zeros_like(mine) for _ in range(self.world)]
             dist.all_gather(allr, mine)
             self.host_ms[tag]["per_rank"] = [
-                {"total_ms": round(float(a[0]), 2), "gpu_max": round(float(a[1]), 2), "gpu_median": round(float(a[2]), 2)} for a in allr]
+                {"total_ms": round(float(a[0]), 2), "gpu_max": round(float(a[1]), 2), "gpu_median": round(float(a[2]), 2),
+                 "cuda_mallocs": int(a[3])} for a in allr]
             ms = max(float(a[0]) for a in allr)
         return ms
 
@@ -566,6 +591,21 @@ def run_ours(args):
         time.sleep(0.5)
     for _ in range(warm):
         w.step(False)
+    # ... and on until torch's caching allocator is in steady state: a cudaMalloc inside the timed region costs 10-100 ms when
+    # peer access is enabled (multi-GPU), and the pool keeps growing by a block every few steps for a while (how many
+    # buffers of a size are alive at once depends on how far the host runs ahead)
+    extra = 0
+    while extra < 16:
+        n0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
+        w.step(False)
+        extra += 1
+        torch.cuda.synchronize()
+        grew = torch.tensor([float(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - n0)], device=device)
+        if world > 1:
+            dist.all_reduce(grew, op=dist.ReduceOp.MAX)
+        if float(grew.item()) == 0.0 and extra >= 2:
+            break
+    warm += extra
     launches0 = L.splatco_launch_count()
     ms_dev = w.timed(w.step, args.steps, False)
     launches = L.splatco_launch_count() - launches0

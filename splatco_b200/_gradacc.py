@@ -34,6 +34,26 @@ _arena_size = {}      # (device index, leaf?) -> floats the previous pass carved
 # inside the pass and nobody needs afterwards.
 
 
+_pools = {}           # device index -> torch.cuda.MemPool the arenas are allocated from
+
+
+def _zeros(numel, device):
+    """The arena allocation.  On CUDA it comes from a PRIVATE memory pool: a multi-GPU caller all-reduces the leaf arena on
+    NCCL's stream, so after `p.grad = None` its block stays unavailable until that stream's event has passed; the next
+    pass's arena then took the best-fitting free block of the shared pool -- the decode backward's workspace -- whose owner
+    had to cudaMalloc a new one (10-100 ms with peer access enabled, a stall every rank shares through the all-reduce;
+    found with the allocator's history: every new segment came from that one line).  In their own pool the arenas can only
+    take each other's blocks and the pool stops growing after a couple of passes."""
+    if device.type != "cuda" or not hasattr(torch.cuda, "MemPool"):
+        return torch.zeros(numel, dtype=torch.float32, device=device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _pools.get(index)
+    if pool is None:
+        pool = _pools[index] = torch.cuda.MemPool()
+    with torch.cuda.use_mem_pool(pool, device=device):
+        return torch.zeros(numel, dtype=torch.float32, device=device)
+
+
 def _end_of_pass(index):
     with _lock:
         table = _passes.pop(index, None)
@@ -118,7 +138,7 @@ def _carve(table, out, todo, total, akey, in_pass, device, want_views, leaf):
             flat, start = arena["cur"], arena["used"]
         else:
             want = max(total, _arena_size.get(akey, 0)) if (in_pass and arena is None) else total
-            flat, start = torch.zeros(want, dtype=torch.float32, device=device), 0
+            flat, start = _zeros(want, device), 0
             if in_pass:
                 if arena is None:
                     arena = _arena[akey] = {"cur": flat, "used": 0, "total": 0}

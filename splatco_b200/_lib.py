@@ -146,12 +146,17 @@ def on_device(device):
 # V, M and R change a little from view to view and, once the optimizer moves the anchors, from iteration to iteration.
 # torch's caching allocator only reuses a block for a request it fits, so workspaces sized to the exact byte keep
 # missing the cache and fall through to cudaMalloc (milliseconds, and device-synchronising when it has to free first):
-# measured as 25-45 ms outlier iterations in a training loop.  Sizes are therefore rounded up to 8 steps per octave
-# (<= 12.5 % slack), which makes consecutive requests land on the same few block sizes.
+# measured as 25-45 ms outlier iterations in a training loop.  Sizes are therefore rounded up to 4 steps per octave
+# (<= 25 % slack), which makes consecutive requests land on the same few block sizes.
+# (4 steps per octave since round 2: with several GPUs in one process group every cudaMalloc also maps the new block into
+# the peers' address spaces and costs 10-100 ms -- a stall all ranks then share through the gradient all-reduce)
+BUCKET_BITS = int(os.environ.get("SPLATCO_BUCKET_BITS", "3"))      # 2^(BITS-1) size steps per octave
+
+
 def bucket(n: int) -> int:
     if n <= 4096:
         return n
-    step = 1 << (n.bit_length() - 4)
+    step = 1 << (n.bit_length() - BUCKET_BITS)
     return (n + step - 1) // step * step
 
 
