@@ -327,12 +327,30 @@ def stage_table(w: Workload, stage_sum, ms_stage, R, M, V):
     return stages, alg_bytes, dom
 
 
+def warm_until_quiescent(w, device, world, limit=16):
+    """Extra untimed steps until one passes without a cudaMalloc of torch's caching allocator on any rank; returns how many."""
+    import torch.distributed as dist
+    extra = 0
+    while extra < limit:
+        n0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
+        w.step(False)
+        extra += 1
+        torch.cuda.synchronize()
+        grew = torch.tensor([float(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - n0)], device=device)
+        if world > 1:
+            dist.all_reduce(grew, op=dist.ReduceOp.MAX)
+        if float(grew.item()) == 0.0 and extra >= 2:
+            break
+    return extra
+
+
 def sub_record(args, name, device, rank, world, steps=4, warm=3):
     """A short measurement of another BASELINE config inside the same bench line: value, e2e, dominant-stage roofline."""
     from splatco_b200 import profiling
     w = Workload(args, name, device, rank, world)
     for _ in range(warm):
         w.step(False)
+    warm += warm_until_quiescent(w, device, world, limit=8)
     ms_dev = w.timed(w.step, steps, False)
     ms_e2e = w.timed(w.step, steps, True)
     with profiling.collect() as prof:
@@ -594,18 +612,7 @@ def run_ours(args):
     # ... and on until torch's caching allocator is in steady state: a cudaMalloc inside the timed region costs 10-100 ms when
     # peer access is enabled (multi-GPU), and the pool keeps growing by a block every few steps for a while (how many
     # buffers of a size are alive at once depends on how far the host runs ahead)
-    extra = 0
-    while extra < 16:
-        n0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
-        w.step(False)
-        extra += 1
-        torch.cuda.synchronize()
-        grew = torch.tensor([float(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - n0)], device=device)
-        if world > 1:
-            dist.all_reduce(grew, op=dist.ReduceOp.MAX)
-        if float(grew.item()) == 0.0 and extra >= 2:
-            break
-    warm += extra
+    warm += warm_until_quiescent(w, device, world)
     launches0 = L.splatco_launch_count()
     ms_dev = w.timed(w.step, args.steps, False)
     launches = L.splatco_launch_count() - launches0
