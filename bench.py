@@ -66,7 +66,8 @@ def ncu_evidence():
     """Per-kernel numbers of the latest committed `ncu --set full` capture (profiles/*_traffic.json, written by
     tools/collect_profiles.py): dram bytes per launch, issue-active, tensor-pipe-active."""
     d = os.path.join(ROOT, "profiles")
-    files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json")) if os.path.isdir(d) else []
+    # capture tags grow r1a .. r1z, r2a .. r2z, r2aa ..: order by (length, name)
+    files = sorted((f for f in os.listdir(d) if f.endswith("_traffic.json")), key=lambda f: (len(f), f)) if os.path.isdir(d) else []
     if not files:
         return {}
     ev = json.load(open(os.path.join(d, files[-1])))
