@@ -455,18 +455,30 @@ tile_sort_radix_kernel(const int2 *__restrict__ ranges, const uint64_t *__restri
     key = s_dyn + cur * 2 * CAP; val = key + CAP;
     const int cs = 8 * first_pass;
     int bad = 0;
-    for (uint32_t i = tid; i + 1 < n; i += NT) {
-        const uint32_t ki = key[i] >> cs;
-        if (ki == (key[i + 1] >> cs) && (i == 0 || (key[i - 1] >> cs) != ki)) {
-            uint32_t e = i + 1;
-            while (e + 1 < n && (key[e + 1] >> cs) == ki) ++e;
-            if (first_pass && e - i >= 32u) { bad = 1; continue; }
-            for (uint32_t a = i + 1; a <= e; ++a) {            // insertion sort of (key, val)[i..e]
-                const uint32_t kk = key[a], v = val[a];
-                uint32_t b = a;
-                while (b > i && (key[b - 1] > kk || (key[b - 1] == kk && val[b - 1] > v))) { key[b] = key[b - 1]; val[b] = val[b - 1]; --b; }
-                key[b] = kk; val[b] = v;
+    // two phases, so that no thread reads keys while a run head permutes its run: first every run head notes where its run
+    // ends (in the inactive key buffer), then the heads sort
+    uint32_t *run_end = s_dyn + (cur ^ 1) * 2 * CAP;
+    for (uint32_t i = tid; i < n; i += NT) {
+        uint32_t e = 0;
+        if (i + 1 < n) {
+            const uint32_t ki = key[i] >> cs;
+            if (ki == (key[i + 1] >> cs) && (i == 0 || (key[i - 1] >> cs) != ki)) {
+                e = i + 1;
+                while (e + 1 < n && (key[e + 1] >> cs) == ki) ++e;
             }
+        }
+        run_end[i] = e;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i + 1 < n; i += NT) {
+        const uint32_t e = run_end[i];
+        if (e == 0) continue;
+        if (first_pass && e - i >= 32u) { bad = 1; continue; }
+        for (uint32_t a = i + 1; a <= e; ++a) {                // insertion sort of (key, val)[i..e]
+            const uint32_t kk = key[a], v = val[a];
+            uint32_t b = a;
+            while (b > i && (key[b - 1] > kk || (key[b - 1] == kk && val[b - 1] > v))) { key[b] = key[b - 1]; val[b] = val[b - 1]; --b; }
+            key[b] = kk; val[b] = v;
         }
     }
     if (!__syncthreads_or(bad)) break;                        // (also orders the run fixing before the copy-out)
