@@ -94,3 +94,38 @@ def test_argument_validation_of_the_training_loop_entry_points():
     assert L.splatco_adam_step(-1, None, 0.9, 0.999, 1e-15, None) < 0 and "bad tensor list" in err()
     assert L.splatco_adam_step(0, None, 0.9, 0.999, 1e-15, None) == 0            # nothing to update is not an error
     assert L.splatco_mv_consistency_ws_bytes(4) >= 6 * 8 + 6 * 4 and L.splatco_grow_ws_bytes(1000) >= 1000 * (4 + 12 + 4 + 4 + 1 + 24)
+
+
+def test_round2_switches_and_count_pointer():
+    """The A/B switch of the blend kernels validates its arguments; the device-count pointer of the prefilter's
+    compaction (handed to splatco_decode_desc::V_dev) sits in the last chunk of its workspace."""
+    L = _lib.lib()
+    err = lambda: L.splatco_last_error().decode()
+    assert L.splatco_blend_set_impl(0, 0) == 0
+    assert L.splatco_blend_set_impl(3, 0) < 0 and "blend_set_impl" in err()
+    assert L.splatco_blend_set_impl(0, 9) < 0 and "blend_set_impl" in err()
+    assert L.splatco_blend_set_impl(2, 2) == 0                      # the defaults
+    for N in (1, 256, 257, 100_000):
+        ws_bytes = L.splatco_visible_compact_ws_bytes(N)
+        base = 1 << 20
+        p = L.splatco_visible_compact_count_ptr(C.c_void_p(base), N)
+        assert p is not None and base < p <= base + ws_bytes - 4 and (p - base) % 256 == 0, (N, p, ws_bytes)
+    assert not L.splatco_visible_compact_count_ptr(None, 10)
+
+
+def test_decode_descriptor_mirror_matches_the_header():
+    """ctypes mirror of splatco_decode_desc: the round-2 fields (V_dev, V_layout) exist and the struct size is what the
+    C compiler lays out for the header (checked by compiling a one-line probe with gcc)."""
+    import subprocess
+    import tempfile
+    from splatco_b200.decode import DecodeDesc, DecodeGrads
+    names = [f[0] for f in DecodeDesc._fields_]
+    assert names[-2:] == ["V_dev", "V_layout"] and names[1] == "V"
+    src = '#include <stdio.h>\n#include "splatco_b200.h"\nint main(void){printf("%zu %zu\\n", sizeof(splatco_decode_desc), sizeof(splatco_decode_grads));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "probe.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "probe")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        a, b = map(int, subprocess.check_output([exe]).split())
+    assert a == C.sizeof(DecodeDesc) and b == C.sizeof(DecodeGrads), (a, C.sizeof(DecodeDesc), b, C.sizeof(DecodeGrads))
