@@ -184,8 +184,10 @@ class _FusedDecode(torch.autograd.Function):
         K = cfg.K
         cp = cfg.pending if (cfg.raster is not None and 1 <= cfg.rc <= 5) else None
         if cfg.pending is not None and cp is None:       # not the two-stage decode after all: the round-1 order
+            from .diff_gaussian_rasterization import clear_compaction
             cfg.pending.event.synchronize()
             cfg.vis_idx = cfg.pending.idx[:int(cfg.pending.counter[0])]
+            clear_compaction(cfg.pending)
             cfg.pending = None
         # V: exact, or (cp: count still on the device) the capacity N every buffer of this view is sized for
         V = int(cfg.vis_idx.shape[0])
