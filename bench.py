@@ -328,19 +328,22 @@ def stage_table(w: Workload, stage_sum, ms_stage, R, M, V):
     return stages, alg_bytes, dom
 
 
-def warm_until_quiescent(w, device, world, limit=16):
-    """Extra untimed steps until one passes without a cudaMalloc of torch's caching allocator on any rank; returns how many."""
+def warm_until_quiescent(w, device, world, limit=24, batch=4):
+    """Extra untimed steps, in free-running batches like the timed loop (how many gradient arenas c10d still holds -- and so
+    how far the arena pool has to grow -- depends on how fast the host issues steps), until a batch passes without a
+    cudaMalloc of torch's caching allocator on any rank; returns how many steps were run."""
     import torch.distributed as dist
     extra = 0
     while extra < limit:
         n0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0)
-        w.step(False)
-        extra += 1
+        for _ in range(batch):
+            w.step(False)
+        extra += batch
         torch.cuda.synchronize()
         grew = torch.tensor([float(torch.cuda.memory_stats(device).get("num_device_alloc", 0) - n0)], device=device)
         if world > 1:
             dist.all_reduce(grew, op=dist.ReduceOp.MAX)
-        if float(grew.item()) == 0.0 and extra >= 2:
+        if float(grew.item()) == 0.0:
             break
     return extra
 
@@ -351,7 +354,7 @@ def sub_record(args, name, device, rank, world, steps=4, warm=3):
     w = Workload(args, name, device, rank, world)
     for _ in range(warm):
         w.step(False)
-    warm += warm_until_quiescent(w, device, world, limit=8)
+    warm += warm_until_quiescent(w, device, world, limit=8, batch=4)
     ms_dev = w.timed(w.step, steps, False)
     ms_e2e = w.timed(w.step, steps, True)
     with profiling.collect() as prof:
