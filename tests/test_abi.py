@@ -129,3 +129,16 @@ def test_decode_descriptor_mirror_matches_the_header():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         a, b = map(int, subprocess.check_output([exe]).split())
     assert a == C.sizeof(DecodeDesc) and b == C.sizeof(DecodeGrads), (a, C.sizeof(DecodeDesc), b, C.sizeof(DecodeGrads))
+
+
+def test_tile_segmented_binning_reaches_the_4k_sweep_sizes():
+    """splatco_binning_accepts_capacity (pure host arithmetic): since round 2 the tile-segmented path grows its chunk size
+    until the [chunks][tiles] matrix fits, so the 4K render sweep (BASELINE configs[4]) no longer falls back to the
+    six-pass radix composition; images whose tile histogram exceeds shared memory still do."""
+    L = _lib.lib()
+    assert L.splatco_binning_accepts_capacity(680_000, 2_660_000, 545, 980) == 1          # C2
+    assert L.splatco_binning_accepts_capacity(6_600_000, 24_000_000, 1080, 1920) == 1      # C4
+    assert L.splatco_binning_accepts_capacity(15_000_000, 54_000_000, 2160, 3840) == 1     # C5, 20 M Gaussians
+    assert L.splatco_binning_accepts_capacity(750_000, 2_700_000, 2160, 3840) == 1         # C5, 1 M
+    assert L.splatco_binning_accepts_capacity(1_000_000, 4_000_000, 4320, 7680) == 0       # 8K: 129,600 tiles > 200 KB histogram
+    assert L.splatco_binning_accepts_capacity(0, 10, 545, 980) == 0 and L.splatco_binning_accepts_capacity(10, 0, 545, 980) == 0
