@@ -27,3 +27,21 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
                         "--warmup", "0", "--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_committed_evidence_is_readable_by_the_bench():
+    """The roofline object takes `traffic` and the issue-slot numbers from the newest committed ncu capture and `peak` from
+    MEASURED_PEAKS.json: both helpers must parse what is in the tree (a malformed file would only show up on the GPU box)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    ev = bench.ncu_evidence()
+    assert ev["_file"].startswith("profiles/r2") and ev["_file"].endswith("_traffic.json")
+    tags = sorted((f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json")), key=lambda f: (len(f), f))
+    assert ev["_file"] == "profiles/" + tags[-1]
+    kernels = {k: v for k, v in ev.items() if isinstance(v, dict)}
+    for name in ("blend_bwd", "blend_fwd"):          # names as tools/collect_profiles.py normalises them
+        hit = [v for k, v in kernels.items() if name in k]
+        assert hit, f"{name} missing from {ev['_file']}"
+        assert hit[0]["dram_bytes"] > 0 and 0 < hit[0]["issue_active_pct"] <= 100
+    peak, src = bench.peaks()
+    assert src in ("measured", "fallback") and 3000 < peak < 9000
